@@ -1,0 +1,152 @@
+"""CPU tests (-m "not gpu"): pin the oracle restatement (oracle/lpcnet_oracle.c).
+
+ * against the committed golden vectors produced by the untouched reference (tests/golden/make_golden.py);
+ * against the compiled reference itself (oracle/_ref) when it is present (build container) — marked `ref`;
+ * unit-level: tables (FFT twiddles/bitrev, DCT), activations, u-law, frame network taps.
+"""
+import ctypes
+import hashlib
+import json
+import os
+import numpy as np
+import pytest
+import helpers as H
+from fixtures import make_feature_batch, make_packets
+
+needs_ref = pytest.mark.skipif(not H.have_ref(), reason="compiled reference (oracle/_ref) not present")
+
+
+def test_model_blobs_are_deterministic():
+    dig = json.load(open(os.path.join(H.GOLDEN, "digests.json")))
+    assert hashlib.sha256(H.blob("int8")).hexdigest() == dig["model_int8_sha256"]
+    assert hashlib.sha256(H.blob("float")).hexdigest() == dig["model_float_sha256"]
+    assert hashlib.sha256(H.codebooks().tobytes()).hexdigest() == dig["codebooks_sha256"]
+
+
+def test_oracle_matches_golden_int8():
+    gold = np.load(os.path.join(H.GOLDEN, "synth_A.npz"))["pcm"]
+    got = H.oracle_synth(make_feature_batch(range(4), 40), "int8")
+    assert (gold[:, :320] == 0).all()            # FEATURES_DELAY warm-up frames are silent (lpcnet.c:239-243)
+    assert np.abs(gold[:, 320:]).max() > 1000    # the fixture is not degenerate
+    np.testing.assert_array_equal(got, gold)
+
+
+def test_oracle_matches_golden_float():
+    gold = np.load(os.path.join(H.GOLDEN, "synth_B.npz"))["pcm"]
+    got = H.oracle_synth(make_feature_batch(range(4), 40), "float")
+    np.testing.assert_array_equal(got, gold)
+
+
+def test_oracle_matches_golden_decode():
+    gold = np.load(os.path.join(H.GOLDEN, "decode_A.npz"))["pcm"]
+    got = H.oracle_decode(np.stack([make_packets(s, 6) for s in range(3)]), "int8")
+    np.testing.assert_array_equal(got, gold)
+
+
+def test_oracle_matches_golden_digests():
+    dig = json.load(open(os.path.join(H.GOLDEN, "digests.json")))
+    big = make_feature_batch(range(16), 150)
+    assert hashlib.sha256(H.oracle_synth(big, "int8").tobytes()).hexdigest() == dig["synth_A_16x150"]
+    assert hashlib.sha256(H.oracle_synth(big, "float").tobytes()).hexdigest() == dig["synth_B_16x150"]
+    pk = np.stack([make_packets(s, 25) for s in range(8)])
+    assert hashlib.sha256(H.oracle_decode(pk, "int8").tobytes()).hexdigest() == dig["decode_A_8x25"]
+
+
+def test_int8_pair_constraint_and_sparsity():
+    """The synthetic model respects WeightClip (lpcnet.py:216-232) so maddubs cannot saturate, and hits the
+    (5,5,20)% block densities => 1382 blocks."""
+    import gen_model
+    common, only8, _ = gen_model.make_model()
+    arrs = {n: a for n, _, a in common + only8}
+    w = arrs["sparse_gru_a_recurrent_weights"].astype(np.int32).reshape(-1, 8, 4)
+    assert w.shape[0] == 1382
+    assert (np.abs(w[:, :, 0]) + np.abs(w[:, :, 1])).max() <= 127
+    assert (np.abs(w[:, :, 2]) + np.abs(w[:, :, 3])).max() <= 127
+    idx = arrs["sparse_gru_a_recurrent_weights_idx"]
+    assert idx.size == 144 + 1382
+    wb = arrs["gru_b_weights"].astype(np.int32).reshape(-1, 8, 4)
+    assert wb.shape[0] == 576
+    assert (np.abs(wb[:, :, 0]) + np.abs(wb[:, :, 1])).max() <= 127
+
+
+@needs_ref
+@pytest.mark.ref
+def test_tables_match_reference():
+    L = H.oracle_lib()
+    tw = np.zeros(640, np.float32); br = np.zeros(320, np.int32); dct = np.zeros(324, np.float32)
+    lg = np.zeros(256, np.float32); u2l = np.zeros(256, np.float32)
+    L.oracle_get_tables(H.oracle_model(), tw.ctypes.data, br.ctypes.data, dct.ctypes.data, lg.ctypes.data, u2l.ctypes.data)
+    R = H.ref_lib("A")
+
+    class KissState(ctypes.Structure):   # kiss_fft_state (src/kiss_fft.h)
+        _fields_ = [("nfft", ctypes.c_int), ("scale", ctypes.c_float), ("shift", ctypes.c_int),
+                    ("factors", ctypes.c_int16 * 16), ("bitrev", ctypes.POINTER(ctypes.c_int16)),
+                    ("twiddles", ctypes.POINTER(ctypes.c_float)), ("arch", ctypes.c_void_p)]
+    k = KissState.in_dll(R, "kfft")
+    assert k.nfft == 320 and list(k.factors[:8]) == [5, 64, 4, 16, 4, 4, 4, 1]
+    np.testing.assert_array_equal(np.ctypeslib.as_array(k.bitrev, (320,)).astype(np.int32), br)
+    np.testing.assert_array_equal(np.ctypeslib.as_array(k.twiddles, (640,)).view(np.uint32), tw.view(np.uint32))
+    ref_dct = np.ctypeslib.as_array((ctypes.c_float * 324).in_dll(R, "dct_table"))
+    np.testing.assert_array_equal(ref_dct.view(np.uint32), dct.view(np.uint32))
+    ref_u2l = np.array([R.ref_ulaw2lin(float(i)) for i in range(256)], dtype=np.float32)
+    np.testing.assert_array_equal(ref_u2l.view(np.uint32), u2l.view(np.uint32))
+
+
+@needs_ref
+@pytest.mark.ref
+def test_activations_and_ulaw_match_reference():
+    L, R, m = H.oracle_lib(), H.ref_lib("A"), H.oracle_model()
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.normal(0, 3, 20000), rng.uniform(-12, 12, 20000), [0.0, -0.0, 1e-8, 50.0, -50.0]]).astype(np.float32)
+    x = x[: x.size // 8 * 8]
+    out = np.zeros_like(x)
+    R.ref_activation(out.ctypes.data, x.ctypes.data, x.size, 2)   # ACTIVATION_TANH
+    mine = np.array([L.oracle_tanh(m, float(v)) for v in x], dtype=np.float32)
+    np.testing.assert_array_equal(out.view(np.uint32), mine.view(np.uint32))
+    R.ref_activation(out.ctypes.data, x.ctypes.data, x.size, 1)   # ACTIVATION_SIGMOID
+    mine = np.array([L.oracle_sigmoid(m, float(v)) for v in x], dtype=np.float32)
+    np.testing.assert_array_equal(out.view(np.uint32), mine.view(np.uint32))
+    v = np.concatenate([rng.normal(0, 3000, 20000), rng.uniform(-40000, 40000, 5000), [0.0, 32767.0, -32768.0]]).astype(np.float32)
+    assert [R.ref_lin2ulaw(float(t)) for t in v] == [L.oracle_lin2ulaw(float(t)) for t in v]
+
+
+@needs_ref
+@pytest.mark.ref
+def test_frame_network_matches_reference():
+    L, R = H.oracle_lib(), H.ref_lib("A")
+    f = make_feature_batch([5], 12)[0]
+    b = H.blob("int8")
+    ga = np.zeros((12, 1152), np.float32); gb = np.zeros((12, 48), np.float32); lpc = np.zeros((12, 16), np.float32)
+    assert R.ref_frame_network(b, len(b), f.ctypes.data, 20, 12, ga.ctypes.data, gb.ctypes.data, lpc.ctypes.data) == 0
+    st = L.oracle_state_create(H.oracle_model())
+    for t in range(12):
+        a = np.zeros(1152, np.float32); c = np.zeros(48, np.float32); l = np.zeros(16, np.float32)
+        L.oracle_frame_network(st, f[t].ctypes.data, a.ctypes.data, c.ctypes.data, l.ctypes.data)
+        np.testing.assert_array_equal(a.view(np.uint32), ga[t].view(np.uint32))
+        np.testing.assert_array_equal(c.view(np.uint32), gb[t].view(np.uint32))
+        np.testing.assert_array_equal(l.view(np.uint32), lpc[t].view(np.uint32))
+    L.oracle_state_destroy(st)
+    assert np.abs(lpc[3:]).max() > 0.1
+
+
+@needs_ref
+@pytest.mark.ref
+@pytest.mark.parametrize("build,kind", [("A", "int8"), ("B", "float")])
+def test_oracle_matches_reference_fresh_streams(build, kind):
+    f = make_feature_batch(range(100, 106), 80)      # streams not in the goldens
+    np.testing.assert_array_equal(H.oracle_synth(f, kind), H.ref_synth(f, build))
+
+
+@needs_ref
+@pytest.mark.ref
+def test_decode_packet_matches_reference():
+    L, R = H.oracle_lib(), H.ref_lib("A")
+    st = L.oracle_state_create(H.oracle_model())
+    vq = np.zeros(18, np.float32)
+    pk = make_packets(77, 40)
+    for t in range(40):
+        fr = np.zeros((4, 36), np.float32); fo = np.zeros((4, 36), np.float32)
+        R.ref_decode_packet(fr.ctypes.data, vq.ctypes.data, pk[t].ctypes.data)
+        L.oracle_decode_packet(st, fo.ctypes.data, pk[t].ctypes.data)
+        np.testing.assert_array_equal(fr.view(np.uint32), fo.view(np.uint32))
+    L.oracle_state_destroy(st)
