@@ -1,0 +1,100 @@
+/* lpcnet_b200.h — batched C-ABI of the B200-native LPCNet synthesis engine (the throughput surface).
+ *
+ * The reference API (include/lpcnet.h) drives ONE stream, 160 samples per call.  The hot path
+ * (reference src/lpcnet.c:235-271 `lpcnet_synthesize_tail_impl` -> :146 `run_sample_network`) is strictly serial
+ * inside a stream, so GPU throughput comes from stepping thousands of independent streams in lockstep.  This
+ * header is the extension SURVEY.md 8(b) calls for: the same operations as `lpcnet_synthesize` /
+ * `lpcnet_decode`, applied to a batch of independent streams that all start from a fresh `lpcnet_create()` state
+ * (reference src/lpcnet.c:174-200: zero state, RNG seeded with "LPCNet").
+ *
+ * Plain C: pointers + sizes only.  Host-pointer entry points copy features in and PCM out inside the call;
+ * `_device` variants take CUDA device pointers (already resident inputs) and a CUDA stream handle.
+ * All functions return 0 on success, negative on error (message: lpcnet_b200_last_error()).
+ */
+#ifndef LPCNET_B200_H
+#define LPCNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifndef LPCNET_EXPORT
+# if defined(__GNUC__)
+#  define LPCNET_EXPORT __attribute__ ((visibility ("default")))
+# else
+#  define LPCNET_EXPORT
+# endif
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct LPCNetB200Batch LPCNetB200Batch;
+
+/* Number of usable CUDA devices (0 => the engine cannot run; there is no CPU fallback). */
+LPCNET_EXPORT int lpcnet_b200_device_count(void);
+/* Last error message of the calling thread ("" if none). */
+LPCNET_EXPORT const char *lpcnet_b200_last_error(void);
+/* Library/ABI version: major*10000 + minor*100 + patch. */
+LPCNET_EXPORT int lpcnet_b200_version(void);
+
+/* Create `n_streams` independent synthesis streams on CUDA device `device`, all using the model in the "DNNw"
+ * blob (same format/validation as reference lpcnet_load_model, src/lpcnet.c:202 + src/parse_lpcnet_weights.c:115-221;
+ * both the int8 DOT_PROD and the float flavour are accepted and select the arithmetic).  `lpc_gamma` is the
+ * reference's compile-time LPC_GAMMA (generated nnet_data.h; training_tf2/dump_lpcnet.py:313-319); pass 1.0f for
+ * "no weighting".  Returns NULL on error. */
+LPCNET_EXPORT LPCNetB200Batch *lpcnet_b200_batch_create(int n_streams, const unsigned char *blob, int blob_len,
+                                                        float lpc_gamma, int device);
+LPCNET_EXPORT void lpcnet_b200_batch_destroy(LPCNetB200Batch *b);
+/* lpcnet_reset() (reference src/lpcnet.c:174) applied to every stream. */
+LPCNET_EXPORT int lpcnet_b200_batch_reset(LPCNetB200Batch *b);
+LPCNET_EXPORT int lpcnet_b200_batch_streams(const LPCNetB200Batch *b);
+
+/* VQ codebooks for the decoder front-end (reference src/lpcnet_dec.c:129-143 reads ceps_codebook1..3 [1024][17]
+ * and ceps_codebook_diff4 [4096][18]; the reference links them from the un-shipped ceps_codebooks.c).
+ * `cb` = the four arrays concatenated in that order (3*1024*17 + 4096*18 floats). */
+LPCNET_EXPORT int lpcnet_b200_batch_set_codebooks(LPCNetB200Batch *b, const float *cb, size_t n_floats);
+
+/* == lpcnet_synthesize() per stream, `nframes` times ==
+ * features: [n_streams][nframes][feature_stride] floats (first 20 of each frame used; stride 20 or 36 typical)
+ * pcm     : [n_streams][nframes*samples_per_frame] int16
+ * samples_per_frame is the reference's N argument (160 in the demo/decoder; any 1..160). */
+LPCNET_EXPORT int lpcnet_b200_batch_synthesize(LPCNetB200Batch *b, const float *features, int nframes,
+                                               int feature_stride, int samples_per_frame, short *pcm);
+LPCNET_EXPORT int lpcnet_b200_batch_synthesize_device(LPCNetB200Batch *b, const float *d_features, int nframes,
+                                                      int feature_stride, int samples_per_frame, short *d_pcm,
+                                                      void *cuda_stream);
+
+/* == lpcnet_decode() per stream, `npackets` times ==
+ * packets: [n_streams][npackets][8] bytes ; pcm: [n_streams][npackets*640] int16 */
+LPCNET_EXPORT int lpcnet_b200_batch_decode(LPCNetB200Batch *b, const unsigned char *packets, int npackets, short *pcm);
+LPCNET_EXPORT int lpcnet_b200_batch_decode_device(LPCNetB200Batch *b, const unsigned char *d_packets, int npackets,
+                                                  short *d_pcm, void *cuda_stream);
+
+/* ---- introspection used by the tests and the benchmark ---- */
+/* Device time (ms, CUDA events on the engine's stream) the per-sample kernel took in the last synthesize/decode
+ * call, summed over its launches; *launches receives how many engine kernels that call launched in total. */
+LPCNET_EXPORT float lpcnet_b200_batch_last_sample_kernel_ms(const LPCNetB200Batch *b, int *launches);
+/* Algorithmic bytes one synthesized sample of one stream must read: total and the
+ * sparse-GEMV-only subset (GRU_A weights + indices). */
+LPCNET_EXPORT int lpcnet_b200_batch_algorithmic_bytes(const LPCNetB200Batch *b, long *total, long *sparse_gemv);
+/* 1 if the loaded blob is the float (DISABLE_DOT_PROD) flavour, 0 for int8. */
+LPCNET_EXPORT int lpcnet_b200_batch_is_float(const LPCNetB200Batch *b);
+/* Copy the per-stream recurrent state of stream `s` to host (tests): gru_a[384], gru_b[16], last_sig[16],
+ * misc[2]={last_exc, frame_count}, rng[4]. Any pointer may be NULL. */
+LPCNET_EXPORT int lpcnet_b200_batch_get_state(LPCNetB200Batch *b, int s, float *gru_a, float *gru_b, float *last_sig,
+                                              int *misc, uint32_t *rng);
+/* Frame-network tap (tests): conditioning of the most recent frame for stream s: gru_a_condition[1152],
+ * gru_b_condition[48], lpc[16]. */
+LPCNET_EXPORT int lpcnet_b200_batch_get_frame_taps(LPCNetB200Batch *b, int s, float *ga, float *gb, float *lpc);
+
+/* Default model / codebooks for the lpcnet.h single-stream API (the reference compiles its model in; this
+ * library loads it at run time).  Also settable through env LPCNET_B200_MODEL / LPCNET_B200_CODEBOOKS (file
+ * paths) and LPCNET_B200_LPC_GAMMA. */
+LPCNET_EXPORT int lpcnet_b200_set_default_model(const unsigned char *blob, int len, float lpc_gamma);
+LPCNET_EXPORT int lpcnet_b200_set_default_codebooks(const float *cb, size_t n_floats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,205 @@
+import ctypes
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liblpcnet_b200.so")
+c_p = ctypes.c_void_p
+
+
+class LPCNetB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load liblpcnet_b200.so (built in-tree by lpcnet_b200.build).  Fails loudly if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        raise LPCNetB200Error("liblpcnet_b200.so is not built (run `python -m lpcnet_b200.build`); there is no fallback path")
+    L = ctypes.CDLL(_SO)
+    L.lpcnet_b200_last_error.restype = ctypes.c_char_p
+    L.lpcnet_b200_batch_create.restype = c_p
+    L.lpcnet_b200_batch_create.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.c_float, ctypes.c_int]
+    L.lpcnet_b200_batch_destroy.argtypes = [c_p]
+    L.lpcnet_b200_batch_reset.argtypes = [c_p]
+    L.lpcnet_b200_batch_streams.argtypes = [c_p]
+    L.lpcnet_b200_batch_set_codebooks.argtypes = [c_p, c_p, ctypes.c_size_t]
+    L.lpcnet_b200_batch_synthesize.argtypes = [c_p, c_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_p]
+    L.lpcnet_b200_batch_synthesize_device.argtypes = [c_p, c_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_p, c_p]
+    L.lpcnet_b200_batch_decode.argtypes = [c_p, c_p, ctypes.c_int, c_p]
+    L.lpcnet_b200_batch_decode_device.argtypes = [c_p, c_p, ctypes.c_int, c_p, c_p]
+    L.lpcnet_b200_batch_last_sample_kernel_ms.restype = ctypes.c_float
+    L.lpcnet_b200_batch_last_sample_kernel_ms.argtypes = [c_p, c_p]
+    L.lpcnet_b200_batch_algorithmic_bytes.argtypes = [c_p, c_p, c_p]
+    L.lpcnet_b200_batch_is_float.argtypes = [c_p]
+    L.lpcnet_b200_batch_get_state.argtypes = [c_p, ctypes.c_int, c_p, c_p, c_p, c_p, c_p]
+    L.lpcnet_b200_debug_frame_network.argtypes = [c_p, c_p, ctypes.c_int, ctypes.c_int, c_p, c_p, c_p]
+    L.lpcnet_b200_set_default_model.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_float]
+    L.lpcnet_b200_set_default_codebooks.argtypes = [c_p, ctypes.c_size_t]
+    L.lpcnet_b200_host_alloc.restype = c_p
+    L.lpcnet_b200_host_alloc.argtypes = [ctypes.c_size_t]
+    L.lpcnet_b200_host_free.argtypes = [c_p]
+    # reference API (include/lpcnet.h)
+    L.lpcnet_create.restype = c_p
+    L.lpcnet_destroy.argtypes = [c_p]
+    L.lpcnet_init.argtypes = [c_p]
+    L.lpcnet_reset.argtypes = [c_p]
+    L.lpcnet_load_model.argtypes = [c_p, ctypes.c_char_p, ctypes.c_int]
+    L.lpcnet_synthesize.restype = None
+    L.lpcnet_synthesize.argtypes = [c_p, c_p, c_p, ctypes.c_int]
+    L.lpcnet_decoder_create.restype = c_p
+    L.lpcnet_decoder_destroy.argtypes = [c_p]
+    L.lpcnet_decoder_init.argtypes = [c_p]
+    L.lpcnet_decode.argtypes = [c_p, c_p, c_p]
+    _lib = L
+    return L
+
+
+def _err():
+    return (lib().lpcnet_b200_last_error() or b"").decode()
+
+
+def device_count():
+    return lib().lpcnet_b200_device_count()
+
+
+class Batch:
+    """n independent synthesis streams stepped in lockstep on one GPU (include/lpcnet_b200.h)."""
+
+    def __init__(self, n_streams, blob, lpc_gamma=1.0, device=0, codebooks=None):
+        self._L = lib()
+        self._h = self._L.lpcnet_b200_batch_create(int(n_streams), blob, len(blob), float(lpc_gamma), int(device))
+        if not self._h:
+            raise LPCNetB200Error("lpcnet_b200_batch_create: " + _err())
+        self.n = int(n_streams)
+        if codebooks is not None:
+            cb = np.ascontiguousarray(codebooks, dtype=np.float32)
+            if self._L.lpcnet_b200_batch_set_codebooks(self._h, cb.ctypes.data, cb.size) != 0:
+                raise LPCNetB200Error(_err())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.lpcnet_b200_batch_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reset(self):
+        if self._L.lpcnet_b200_batch_reset(self._h) != 0:
+            raise LPCNetB200Error(_err())
+
+    def synthesize(self, features, samples_per_frame=160):
+        """features [n][T][stride>=20] float32 (host) -> pcm [n][T*samples_per_frame] int16 (host)."""
+        f = np.ascontiguousarray(features, dtype=np.float32)
+        assert f.ndim == 3 and f.shape[0] == self.n
+        T, stride = f.shape[1], f.shape[2]
+        pcm = np.empty((self.n, T * samples_per_frame), dtype=np.int16)
+        if self._L.lpcnet_b200_batch_synthesize(self._h, f.ctypes.data, T, stride, samples_per_frame, pcm.ctypes.data) != 0:
+            raise LPCNetB200Error("lpcnet_b200_batch_synthesize: " + _err())
+        return pcm
+
+    def synthesize_device(self, d_features_ptr, nframes, stride, d_pcm_ptr, samples_per_frame=160, cuda_stream=None):
+        r = self._L.lpcnet_b200_batch_synthesize_device(self._h, d_features_ptr, nframes, stride, samples_per_frame, d_pcm_ptr, cuda_stream)
+        if r != 0:
+            raise LPCNetB200Error("lpcnet_b200_batch_synthesize_device: " + _err())
+
+    def decode(self, packets):
+        """packets [n][P][8] uint8 -> pcm [n][P*640] int16."""
+        p = np.ascontiguousarray(packets, dtype=np.uint8)
+        assert p.ndim == 3 and p.shape[0] == self.n and p.shape[2] == 8
+        pcm = np.empty((self.n, p.shape[1] * 640), dtype=np.int16)
+        if self._L.lpcnet_b200_batch_decode(self._h, p.ctypes.data, p.shape[1], pcm.ctypes.data) != 0:
+            raise LPCNetB200Error("lpcnet_b200_batch_decode: " + _err())
+        return pcm
+
+    def decode_device(self, d_packets_ptr, npackets, d_pcm_ptr, cuda_stream=None):
+        if self._L.lpcnet_b200_batch_decode_device(self._h, d_packets_ptr, npackets, d_pcm_ptr, cuda_stream) != 0:
+            raise LPCNetB200Error("lpcnet_b200_batch_decode_device: " + _err())
+
+    def last_sample_kernel_ms(self):
+        k = ctypes.c_int(0)
+        ms = self._L.lpcnet_b200_batch_last_sample_kernel_ms(self._h, ctypes.byref(k))
+        return float(ms), int(k.value)
+
+    def algorithmic_bytes(self):
+        a, b = ctypes.c_long(0), ctypes.c_long(0)
+        self._L.lpcnet_b200_batch_algorithmic_bytes(self._h, ctypes.byref(a), ctypes.byref(b))
+        return int(a.value), int(b.value)
+
+    def get_state(self, s):
+        ga = np.zeros(384, np.float32); gb = np.zeros(16, np.float32); ls = np.zeros(16, np.float32)
+        misc = np.zeros(2, np.int32); rng = np.zeros(4, np.uint32)
+        if self._L.lpcnet_b200_batch_get_state(self._h, int(s), ga.ctypes.data, gb.ctypes.data, ls.ctypes.data, misc.ctypes.data, rng.ctypes.data) != 0:
+            raise LPCNetB200Error(_err())
+        return dict(gru_a=ga, gru_b=gb, last_sig=ls, last_exc=int(misc[0]), frame_count=int(misc[1]), rng=rng)
+
+    def debug_frame_network(self, features):
+        f = np.ascontiguousarray(features, dtype=np.float32)
+        T, stride = f.shape[1], f.shape[2]
+        ga = np.zeros((self.n, T, 1152), np.float32); gb = np.zeros((self.n, T, 48), np.float32); lpc = np.zeros((self.n, T, 16), np.float32)
+        if self._L.lpcnet_b200_debug_frame_network(self._h, f.ctypes.data, T, stride, ga.ctypes.data, gb.ctypes.data, lpc.ctypes.data) != 0:
+            raise LPCNetB200Error(_err())
+        return ga, gb, lpc
+
+
+class LPCNet:
+    """Mirror of the reference single-stream API: lpcnet_create / lpcnet_load_model / lpcnet_synthesize / lpcnet_reset."""
+
+    def __init__(self, blob=None):
+        self._L = lib()
+        self._st = self._L.lpcnet_create()
+        if not self._st:
+            raise LPCNetB200Error("lpcnet_create: " + _err())
+        if blob is not None:
+            self.load_model(blob)
+
+    def load_model(self, blob):
+        if self._L.lpcnet_load_model(self._st, blob, len(blob)) != 0:
+            raise LPCNetB200Error("lpcnet_load_model: " + _err())
+
+    def reset(self):
+        self._L.lpcnet_reset(self._st)
+
+    def synthesize(self, features, N=160):
+        f = np.ascontiguousarray(features, dtype=np.float32)
+        out = np.zeros(N, dtype=np.int16)
+        self._L.lpcnet_synthesize(self._st, f.ctypes.data, out.ctypes.data, N)
+        return out
+
+    def close(self):
+        if getattr(self, "_st", None):
+            self._L.lpcnet_destroy(self._st)
+            self._st = None
+
+    __del__ = close
+
+
+class LPCNetDecoder:
+    """Mirror of lpcnet_decoder_create / lpcnet_decode (model is loaded through the leading LPCNetState member)."""
+
+    def __init__(self, blob=None):
+        self._L = lib()
+        self._st = self._L.lpcnet_decoder_create()
+        if not self._st:
+            raise LPCNetB200Error("lpcnet_decoder_create: " + _err())
+        if blob is not None and self._L.lpcnet_load_model(self._st, blob, len(blob)) != 0:
+            raise LPCNetB200Error("lpcnet_load_model: " + _err())
+
+    def decode(self, packet):
+        p = np.ascontiguousarray(packet, dtype=np.uint8)
+        out = np.zeros(640, dtype=np.int16)
+        if self._L.lpcnet_decode(self._st, p.ctypes.data, out.ctypes.data) != 0:
+            raise LPCNetB200Error("lpcnet_decode: " + _err())
+        return out
+
+    def close(self):
+        if getattr(self, "_st", None):
+            self._L.lpcnet_decoder_destroy(self._st)
+            self._st = None
+
+    __del__ = close

@@ -1,0 +1,140 @@
+// engine.h — internal structures shared by the host-side model loader and the sm_100a kernels.
+// Not part of the C ABI (include/*.h is).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace lpcnet_b200 {
+
+// ---- model dimensions (default LPCNet: training_tf2/lpcnet.py:234; generated nnet_data.h) ----
+constexpr int NA = 384;            // GRU_A units
+constexpr int NB = 16;             // GRU_B units
+constexpr int COND = 128;          // conditioning width
+constexpr int PITCH_EMBED = 64;
+constexpr int NB_FEAT = 20;
+constexpr int FRAME_IN = NB_FEAT + PITCH_EMBED;   // 84
+constexpr int LPC_ORDER = 16;
+constexpr int NB_BANDS = 18;
+constexpr int FRAME_SIZE = 160;
+constexpr int FEATURES_DELAY = 2;
+constexpr int WINDOW_SIZE = 320;
+constexpr int FREQ_SIZE = 161;
+
+// ---- per-sample kernel geometry ----
+constexpr int STREAMS_PER_CTA = 32;          // lane == stream
+constexpr int NWC = 16;                      // compute warps: each owns NGRP/NWC neuron groups of GRU_A and one GRU_B neuron
+constexpr int NGRP = NA / 8;                 // 48 groups of 8 neurons (one 8-row block group per gate)
+constexpr int GPW = NGRP / NWC;              // 3
+constexpr int SAMPLE_THREADS = (NWC + 1) * 32;   // + 1 sampler warp (tree sampler, LPC filter, u-law, de-emphasis)
+constexpr int XS_BYTES = (NA / 4) * 32 * 4;  // quantised GRU_A state of 32 streams: [96 words][32 lanes]
+constexpr int FCW_ROW = 33;                  // dual_fc rows padded 32->33 floats (bank-conflict-free per-lane row gather)
+constexpr int PCM_ROW = 162;                 // int16 per stream in the PCM staging tile (81 words: odd => conflict-free)
+constexpr int NWB = 12;                      // warps used by the GRU_B input GEMV: (row-group 0..5) x (K half 0..1)
+
+// ---- shared-memory map of the per-sample kernel ----
+// Everything whose size does not depend on the model's sparsity pattern sits at a COMPILE-TIME offset (keeps the
+// addresses out of registers); only the four block-sparse arrays are placed at run-time offsets behind them.
+// [SM_IMAGE, SM_IMAGE + image_bytes) is copied verbatim from the global "SMEM image" built at model-load time
+// (TMA bulk copies); [0, SM_IMAGE) is the mutable working set.
+constexpr uint32_t al128(uint32_t x) { return (x + 127u) & ~127u; }
+constexpr uint32_t SM_XS    = 0;                                   // 2 x XS_BYTES: double-buffered quantised GRU_A state
+constexpr uint32_t SM_XB    = SM_XS + 2 * XS_BYTES;                // 2 x [4 words][32]: quantised GRU_B state
+constexpr uint32_t SM_ACCB  = SM_XB + 2 * 4 * 32 * 4;              // int32 [2][48][32]: K-half partial sums of the GRU_B input GEMV
+constexpr uint32_t SM_HBS   = SM_ACCB + 2 * 3 * NB * 32 * 4;       // float [16][32]: GRU_B state for the sampler warp
+constexpr uint32_t SM_IDX   = SM_HBS + NB * 32 * 4;                // int32 [3][32]: last_sig_ulaw, pred_ulaw, last_exc
+constexpr uint32_t SM_PCM   = SM_IDX + 3 * 32 * 4;                 // int16 [32][PCM_ROW]
+constexpr uint32_t SM_MBAR  = al128(SM_PCM + 32 * PCM_ROW * 2);    // 8-byte mbarrier of the image copy
+constexpr uint32_t SM_IMAGE = SM_MBAR + 128;
+// image, fixed part (offsets relative to SM_IMAGE)
+constexpr uint32_t IM_RCP   = 0;                                   // u16 [2048] RCPPS table ((T-0x3f000000)>>11)
+constexpr uint32_t IM_LOGIT = IM_RCP + 2048 * 2;                   // float [256] sampling_logit_table
+constexpr uint32_t IM_U2L   = IM_LOGIT + 256 * 4;                  // float [256] ulaw2lin
+constexpr uint32_t IM_FCW   = IM_U2L + 256 * 4;                    // float [256][FCW_ROW] dual_fc weights
+constexpr uint32_t IM_FCB   = IM_FCW + 256 * FCW_ROW * 4;          // float [2][256]
+constexpr uint32_t IM_FCF   = IM_FCB + 512 * 4;                    // float [2][256]
+constexpr uint32_t IM_PARA  = IM_FCF + 512 * 4;                    // float [NWC][GPW][3 gates][16] = recurrent su-bias[8], diag[8]
+constexpr uint32_t IM_DIRA  = IM_PARA + NWC * GPW * 3 * 16 * 4;    // uint32 [NWC][GPW][3][2] = {first block, padded (even) block count}
+constexpr uint32_t IM_GRPA  = IM_DIRA + NWC * GPW * 3 * 2 * 4;     // uint32 [NWC][GPW] neuron-group id
+constexpr uint32_t IM_DIRB  = IM_GRPA + NWC * GPW * 4;             // uint32 [NWB][2]
+constexpr uint32_t IM_WBREC = IM_DIRB + NWB * 2 * 4;               // int8 [6][4][8][4] GRU_B recurrent blocks
+constexpr uint32_t IM_PARB  = IM_WBREC + 3 * NB * NB;              // float [96]: input-side su-bias[48], recurrent-side su-bias[48]
+constexpr uint32_t IM_VAR   = al128(IM_PARB + 6 * NB * 4);         // start of the variable-size arrays
+
+struct SmemLayout {          // run-time part; offsets are absolute (from the start of dynamic shared memory)
+    uint32_t wA;        // int8 GRU_A blocks, 32 B each = [8 out][4 in], ordered (warp, slot, gate, block)
+    uint32_t metaA;     // u16 per block: byte offset of the x word-row ((pos/4)*128)
+    uint32_t wB;        // int8 GRU_B input blocks, ordered (row group, K half, block)
+    uint32_t metaB;     // u16 per block
+    uint32_t image_bytes;
+    uint32_t total_bytes;
+    uint32_t nblkA_padded, nblkB_padded;
+};
+
+// Device-resident model (one per batch; weights replicated per GPU, ~4 MB).
+struct DeviceModel {
+    int is_float;                    // 0: int8 DOT_PROD semantics (oracle A); 1: float semantics (oracle B)
+    float lpc_gamma;
+    SmemLayout L;
+    uint8_t *image;                  // [L.image_bytes] global copy of the SMEM image
+    // per-sample gathers (L2-resident): [256][3*NA] each
+    float *emb_sig, *emb_pred, *emb_exc;
+    // frame network (fp32, reference layouts kept: column-major W[j*N+i], conv W[(k*in+i)*out+o])
+    float *embed_pitch;              // [256][64]
+    float *conv1_w, *conv1_b, *conv2_w, *conv2_b;
+    float *dense1_w, *dense1_b, *dense2_w, *dense2_b;
+    float *gad_w, *gad_b, *gbd_w, *gbd_b;
+    // tables
+    uint16_t *rcp16;                 // [2048]
+    float *dct;                      // [18*18]
+    float *twiddles;                 // [320*2]
+    int16_t *bitrev;                 // [320]
+    float *gamma_pow;                // [16] gamma^(i+1) accumulated in float exactly like lpc_weighting (freq.c:299-308)
+    float *pitch_pow;                // [64] (float)(pow(2.f, k/21.)*32) for the packet decoder (lpcnet_dec.c:124)
+    float *codebooks;                // cb1,cb2,cb3,diff4 or NULL
+    // accounting
+    long algo_bytes_total, algo_bytes_sparse;
+    int nblkA, nblkB;
+};
+
+struct SampleParams {
+    SmemLayout L;
+    const uint8_t *image;
+    const float *emb_sig, *emb_pred, *emb_exc;
+    const float *condA;      // [nframes][n][3*NA]
+    const float *condB;      // [nframes][n][3*NB]
+    const float *lpc_raw;    // [nframes + 2][n][16]  (frame f uses entry f: the LPC of frame f-2)
+    const float *gamma_pow;  // [16]
+    float *hA;               // [NA][n]
+    float *hB;               // [NB][n]
+    float *last_sig;         // [16][n]
+    float *deemph;           // [n]
+    int *last_exc;           // [n]
+    uint32_t *rng;           // [4][n]
+    short *pcm;              // stream s, frame f, sample t at pcm[s*pcm_stream_stride + f*spf + t]
+    long long pcm_stream_stride;
+    int n_streams, nframes, spf;
+};
+
+// ---- host-side API of the internal modules ----
+int model_load(DeviceModel *m, const unsigned char *blob, int len, float lpc_gamma);   // 0 / -1 (sets error)
+void model_free(DeviceModel *m);
+int debug_build_image(const unsigned char *blob, int len, unsigned char *out, size_t cap, SmemLayout *L);
+void set_error(const char *fmt, ...);
+
+struct FrameState {           // per-batch persistent state of the 100 Hz path
+    float *conv1_state;       // [n][FRAME_IN*2]
+    float *conv2_state;       // [n][COND*2]
+    float *lpc_carry;         // [2][n][16] raw LPC of the two previous frames
+    float *vq_mem;            // [n][18] decoder memory
+};
+
+void launch_frame_network(const DeviceModel &m, const FrameState &fs, const float *d_features, long long stream_stride,
+                          int frame_stride, int n, int nframes, int frame_count0, float *condA, float *condB,
+                          float *lpc_raw /* [nframes+2][n][16], entries 0,1 = carry */, cudaStream_t st);
+void launch_decode_packets(const DeviceModel &m, const FrameState &fs, const uint8_t *d_packets, int n, int npackets,
+                           float *d_features /* [n][4*npackets][20] */, cudaStream_t st);
+cudaError_t launch_sample_kernel(const SampleParams &p, cudaStream_t st);
+int sample_kernel_smem_ok(uint32_t bytes);
+
+}  // namespace lpcnet_b200

@@ -1,0 +1,345 @@
+// model.cu — "DNNw" blob ingest and device model construction.
+//
+// Replaces (reference file:line): parse_weights / parse_record  src/parse_lpcnet_weights.c:37-77,
+// find_idx_check :90-113, the per-layer *_init validators :115-221 and the generated init_lpcnet_model
+// (training_tf2/dump_lpcnet.py:147,181,199,224,242,252).  Instead of pointing layer structs into the blob it builds
+//   * the shared-memory image of the per-sample kernel (block-sparse int8 GRU_A/GRU_B weights re-ordered by
+//     owning warp, su-bias/diag per row group, dual_fc, sampler tables) and
+//   * plain device copies of the frame-rate fp32 layers and the three 1.18 MB gather tables.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+#include "engine.h"
+
+namespace lpcnet_b200 {
+
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...)
+{
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+const char *get_error() { return g_err; }
+
+static const uint16_t kRcpTable[2048] = {
+#include "rcpps_table.inc"
+};
+
+namespace {
+
+struct WeightHead { char head[4]; int version; int type; int size; int block_size; char name[44]; };
+static_assert(sizeof(WeightHead) == 64, "DNNw header is 64 bytes (nnet.h:53-60)");
+
+struct Arr { const unsigned char *data; int size; int type; };
+
+// parse_record semantics (parse_lpcnet_weights.c:37-52): walk 64-byte headers, reject malformed records.
+bool parse_blob(const unsigned char *d, int len, std::vector<std::pair<std::string, Arr>> &out)
+{
+    while (len > 0) {
+        if (len < 64) return false;
+        const WeightHead *h = reinterpret_cast<const WeightHead *>(d);
+        if (h->block_size < h->size) return false;
+        if (h->block_size > len - 64) return false;
+        if (h->name[43] != 0) return false;
+        if (h->size <= 0) return false;
+        out.push_back({std::string(h->name), Arr{d + 64, h->size, h->type}});
+        d += 64 + h->block_size; len -= 64 + h->block_size;
+    }
+    return true;
+}
+
+const Arr *find(const std::vector<std::pair<std::string, Arr>> &v, const char *name)
+{
+    for (auto &p : v) if (p.first == name) return &p.second;
+    return nullptr;
+}
+const float *need_f(const std::vector<std::pair<std::string, Arr>> &v, const char *name, int count)
+{
+    const Arr *a = find(v, name);
+    if (!a || a->size != count * 4) { set_error("model: array '%s' missing or wrong size (want %d floats)", name, count); return nullptr; }
+    return reinterpret_cast<const float *>(a->data);
+}
+// find_idx_check (parse_lpcnet_weights.c:90-113)
+const int *need_idx(const std::vector<std::pair<std::string, Arr>> &v, const char *name, int nb_in, int nb_out, int *total)
+{
+    const Arr *a = find(v, name);
+    *total = 0;
+    if (!a) { set_error("model: index array '%s' missing", name); return nullptr; }
+    const int *idx = reinterpret_cast<const int *>(a->data);
+    int remain = a->size / 4;
+    const int *p = idx;
+    while (remain > 0) {
+        int nb = *p++;
+        if (nb < 0 || remain < nb + 1) { set_error("model: '%s' truncated", name); return nullptr; }
+        for (int i = 0; i < nb; i++) { int pos = *p++; if (pos < 0 || pos + 3 >= nb_in || (pos & 3)) { set_error("model: '%s' bad position", name); return nullptr; } }
+        nb_out -= 8; remain -= nb + 1; *total += nb;
+    }
+    if (nb_out != 0) { set_error("model: '%s' does not cover all output rows", name); return nullptr; }
+    return idx;
+}
+
+template <typename T> T *to_device(const T *h, size_t count)
+{
+    T *d = nullptr;
+    if (cudaMalloc(&d, count * sizeof(T)) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(d, h, count * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return nullptr; }
+    return d;
+}
+
+uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace
+
+struct HostModel {               // everything model_load needs after parsing, before any CUDA call
+    std::vector<uint8_t> img;
+    const float *embed_pitch, *conv1_w, *conv1_b, *conv2_w, *conv2_b, *dense1_w, *dense1_b, *dense2_w, *dense2_b;
+    const float *gad_w, *gad_b, *gbd_w, *gbd_b, *emb_sig, *emb_pred, *emb_exc;
+};
+
+static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *blob, int len, float lpc_gamma)
+{
+    memset(m, 0, sizeof(*m));
+    m->lpc_gamma = lpc_gamma;
+    std::vector<std::pair<std::string, Arr>> A;
+    if (!blob || len <= 0 || !parse_blob(blob, len, A)) { set_error("model: malformed DNNw blob"); return -1; }
+
+#define NEED(var, name, count) const float *var = need_f(A, name, count); if (!var) return -1;
+    NEED(embed_pitch, "embed_pitch_weights", 256 * PITCH_EMBED)
+    NEED(conv1_w, "feature_conv1_weights", 3 * FRAME_IN * COND) NEED(conv1_b, "feature_conv1_bias", COND)
+    NEED(conv2_w, "feature_conv2_weights", 3 * COND * COND) NEED(conv2_b, "feature_conv2_bias", COND)
+    NEED(dense1_w, "feature_dense1_weights", COND * COND) NEED(dense1_b, "feature_dense1_bias", COND)
+    NEED(dense2_w, "feature_dense2_weights", COND * COND) NEED(dense2_b, "feature_dense2_bias", COND)
+    NEED(gad_w, "gru_a_dense_feature_weights", COND * 3 * NA) NEED(gad_b, "gru_a_dense_feature_bias", 3 * NA)
+    NEED(gbd_w, "gru_b_dense_feature_weights", COND * 3 * NB) NEED(gbd_b, "gru_b_dense_feature_bias", 3 * NB)
+    NEED(emb_sig, "gru_a_embed_sig_weights", 256 * 3 * NA) NEED(emb_pred, "gru_a_embed_pred_weights", 256 * 3 * NA)
+    NEED(emb_exc, "gru_a_embed_exc_weights", 256 * 3 * NA)
+    NEED(ga_bias, "sparse_gru_a_bias", 6 * NA) NEED(ga_subias, "sparse_gru_a_subias", 6 * NA)
+    NEED(ga_diag, "sparse_gru_a_recurrent_weights_diag", 3 * NA)
+    NEED(gb_bias, "gru_b_bias", 6 * NB) NEED(gb_subias, "gru_b_subias", 6 * NB)
+    NEED(fc_w, "dual_fc_weights", 256 * 2 * NB) NEED(fc_b, "dual_fc_bias", 512) NEED(fc_f, "dual_fc_factor", 512)
+#undef NEED
+    int nblkA = 0, nblkB = 0;
+    const int *idxA = need_idx(A, "sparse_gru_a_recurrent_weights_idx", NA, 3 * NA, &nblkA); if (!idxA) return -1;
+    const int *idxB = need_idx(A, "gru_b_weights_idx", NA, 3 * NB, &nblkB); if (!idxB) return -1;
+    const Arr *wA = find(A, "sparse_gru_a_recurrent_weights");
+    const Arr *wB = find(A, "gru_b_weights");
+    const Arr *wBrec = find(A, "gru_b_recurrent_weights");
+    if (!wA || !wB || !wBrec) { set_error("model: recurrent weight arrays missing"); return -1; }
+    if (wA->size == 32 * nblkA) m->is_float = 0;
+    else if (wA->size == 128 * nblkA) m->is_float = 1;
+    else { set_error("model: sparse_gru_a_recurrent_weights has %d bytes for %d blocks", wA->size, nblkA); return -1; }
+    if (wB->size != (m->is_float ? 128 : 32) * nblkB || wBrec->size != (m->is_float ? 4 : 1) * 3 * NB * NB) {
+        set_error("model: gru_b weight sizes inconsistent with the blob flavour"); return -1;
+    }
+    if (m->is_float) { set_error("model: float (DISABLE_DOT_PROD) blobs are not supported by this build yet"); return -1; }
+    m->nblkA = nblkA; m->nblkB = nblkB;
+
+    // ---------------- GRU_A: assign the 48 neuron groups to the 16 compute warps (LPT on block count) ----------------
+    // per 8-row group rg (0..143): list of (pos, weight ptr)
+    struct Blk { int pos; const unsigned char *w; };
+    std::vector<std::vector<Blk>> rowsA(3 * NGRP), rowsB(3 * NB / 8);
+    {
+        const int *p = idxA; const unsigned char *w = wA->data;
+        for (int rg = 0; rg < 3 * NGRP; rg++) { int nb = *p++; for (int j = 0; j < nb; j++) { rowsA[rg].push_back({*p++, w}); w += 32; } }
+        p = idxB; w = wB->data;
+        for (int rg = 0; rg < 3 * NB / 8; rg++) { int nb = *p++; for (int j = 0; j < nb; j++) { rowsB[rg].push_back({*p++, w}); w += 32; } }
+    }
+    std::vector<int> cost(NGRP), order(NGRP);
+    for (int g = 0; g < NGRP; g++) cost[g] = (int)(rowsA[g].size() + rowsA[NGRP + g].size() + rowsA[2 * NGRP + g].size());
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+    int grp[NWC][GPW]; int load[NWC] = {0}, fill[NWC] = {0};
+    for (int g : order) {
+        int best = -1;
+        for (int w = 0; w < NWC; w++) if (fill[w] < GPW && (best < 0 || load[w] < load[best])) best = w;
+        grp[best][fill[best]++] = g; load[best] += cost[g];
+    }
+
+    // ---------------- SMEM layout ----------------
+    SmemLayout &L = m->L;
+    auto padded = [](size_t n) { return (uint32_t)((n + 1) & ~size_t(1)); };
+    uint32_t nA_pad = 0, nB_pad = 0;
+    for (int w = 0; w < NWC; w++) for (int s = 0; s < GPW; s++) for (int q = 0; q < 3; q++) nA_pad += padded(rowsA[q * NGRP + grp[w][s]].size());
+    // GRU_B input GEMV: warp (rg, half) takes blocks [half*ceil(n/2) ...)
+    uint32_t dirB_h[NWB][2];
+    for (int rg = 0; rg < 6; rg++) {
+        size_t n = rowsB[rg].size(), h0 = (n + 1) / 2;
+        dirB_h[rg * 2][1] = padded(h0); dirB_h[rg * 2 + 1][1] = padded(n - h0);
+        nB_pad += dirB_h[rg * 2][1] + dirB_h[rg * 2 + 1][1];
+    }
+    uint32_t off = SM_IMAGE + IM_VAR;
+    auto take = [&](uint32_t bytes, uint32_t align = 16) { off = align_up(off, align); uint32_t o = off; off += bytes; return o; };
+    L.wA = take(nA_pad * 32, 128);
+    L.metaA = take(nA_pad * 2);
+    L.wB = take(nB_pad * 32, 128);
+    L.metaB = take(nB_pad * 2);
+    L.total_bytes = align_up(off, 128);
+    L.image_bytes = L.total_bytes - SM_IMAGE;
+    L.nblkA_padded = nA_pad; L.nblkB_padded = nB_pad;
+    if (!sample_kernel_smem_ok(L.total_bytes)) { set_error("model: %u bytes of shared memory needed, more than one SM offers", L.total_bytes); return -1; }
+
+    // ---------------- build the image ----------------
+    std::vector<uint8_t> img(L.image_bytes, 0);
+    const uint32_t oWA = L.wA - SM_IMAGE, oMA = L.metaA - SM_IMAGE, oWB = L.wB - SM_IMAGE, oMB = L.metaB - SM_IMAGE;
+    uint16_t *metaA = reinterpret_cast<uint16_t *>(&img[oMA]);
+    float *parA = reinterpret_cast<float *>(&img[IM_PARA]);
+    uint32_t *dirA = reinterpret_cast<uint32_t *>(&img[IM_DIRA]);
+    uint32_t *grpA = reinterpret_cast<uint32_t *>(&img[IM_GRPA]);
+    uint32_t blk = 0;
+    for (int w = 0; w < NWC; w++) for (int s = 0; s < GPW; s++) {
+        int g = grp[w][s];
+        grpA[w * GPW + s] = (uint32_t)g;
+        for (int q = 0; q < 3; q++) {
+            const auto &lst = rowsA[q * NGRP + g];
+            uint32_t np = padded(lst.size());
+            dirA[((w * GPW + s) * 3 + q) * 2 + 0] = blk;
+            dirA[((w * GPW + s) * 3 + q) * 2 + 1] = np;
+            for (size_t j = 0; j < lst.size(); j++) {
+                memcpy(&img[oWA + (size_t)(blk + j) * 32], lst[j].w, 32);
+                metaA[blk + j] = (uint16_t)((lst[j].pos / 4) * 128);
+            }
+            blk += np;    // padding blocks stay all-zero (weights 0, x row 0): contribute exactly 0
+            float *pp = &parA[((w * GPW + s) * 3 + q) * 16];
+            for (int i = 0; i < 8; i++) {
+                pp[i] = ga_subias[3 * NA + q * NA + 8 * g + i];       // recurrent su-bias (nnet.c:426)
+                pp[8 + i] = ga_diag[q * NA + 8 * g + i];
+            }
+        }
+    }
+    uint16_t *metaB = reinterpret_cast<uint16_t *>(&img[oMB]);
+    uint32_t *dirB = reinterpret_cast<uint32_t *>(&img[IM_DIRB]);
+    blk = 0;
+    for (int rg = 0; rg < 6; rg++) {
+        const auto &lst = rowsB[rg];
+        size_t h0 = (lst.size() + 1) / 2;
+        for (int half = 0; half < 2; half++) {
+            size_t b0 = half ? h0 : 0, b1 = half ? lst.size() : h0;
+            dirB[(rg * 2 + half) * 2 + 0] = blk;
+            dirB[(rg * 2 + half) * 2 + 1] = dirB_h[rg * 2 + half][1];
+            for (size_t j = b0; j < b1; j++) {
+                memcpy(&img[oWB + (size_t)(blk + (j - b0)) * 32], lst[j].w, 32);
+                metaB[blk + (j - b0)] = (uint16_t)((lst[j].pos / 4) * 128);
+            }
+            blk += dirB_h[rg * 2 + half][1];
+        }
+    }
+    memcpy(&img[IM_WBREC], wBrec->data, 3 * NB * NB);
+    {
+        float *pb = reinterpret_cast<float *>(&img[IM_PARB]);
+        for (int i = 0; i < 6 * NB; i++) pb[i] = gb_subias[i];          // nnet.c:346-360 (USE_SU_BIAS)
+        (void)gb_bias; (void)ga_bias;
+    }
+    memcpy(&img[IM_RCP], kRcpTable, sizeof(kRcpTable));
+    {
+        float *lg = reinterpret_cast<float *>(&img[IM_LOGIT]);
+        for (int i = 0; i < 256; i++) {                                   // lpcnet.c:188-191 (host libm, double log)
+            float prob = .025f + .95f * i / 255.f;
+            lg[i] = -log((1 - prob) / prob);
+        }
+        float *u2l = reinterpret_cast<float *>(&img[IM_U2L]);
+        for (int i = 0; i < 256; i++) {                                   // ulaw2lin, common.h:37-45 (double exp)
+            float u = (float)i, s, scale_1 = 32768.f / 255.f;
+            u = u - 128.f; s = u >= 0.f ? 1.f : -1.f; u = fabs(u);
+            u2l[i] = s * scale_1 * (exp(u / 128. * 5.5451774445f) - 1);
+        }
+        float *fw = reinterpret_cast<float *>(&img[IM_FCW]);
+        for (int i = 0; i < 256; i++) for (int j = 0; j < 32; j++) fw[i * FCW_ROW + j] = fc_w[i * 32 + j];
+        memcpy(&img[IM_FCB], fc_b, 512 * 4);
+        memcpy(&img[IM_FCF], fc_f, 512 * 4);
+    }
+
+    hm.embed_pitch = embed_pitch; hm.conv1_w = conv1_w; hm.conv1_b = conv1_b; hm.conv2_w = conv2_w; hm.conv2_b = conv2_b;
+    hm.dense1_w = dense1_w; hm.dense1_b = dense1_b; hm.dense2_w = dense2_w; hm.dense2_b = dense2_b;
+    hm.gad_w = gad_w; hm.gad_b = gad_b; hm.gbd_w = gbd_w; hm.gbd_b = gbd_b;
+    hm.emb_sig = emb_sig; hm.emb_pred = emb_pred; hm.emb_exc = emb_exc;
+    hm.img.swap(img);
+    // algorithmic bytes per synthesized sample
+    m->algo_bytes_sparse = 32L * nblkA + 4L * (3 * NGRP + nblkA);
+    m->algo_bytes_total = m->algo_bytes_sparse + 3 * NA * 4 /*diag*/ + 3 * NA * 4 /*su-bias*/ + 3 * 3 * NA * 4 /*3 embedding rows*/
+                        + 3 * NA * 4 /*gru_a_condition*/ + 32L * nblkB + 4L * (6 + nblkB) + 3 * NB * NB + 6 * NB * 4 + 3 * NB * 4
+                        + 8 * (2 * NB + 2 + 2) * 4 + 32;
+    return 0;
+}
+
+// Test hook (no CUDA needed): build the shared-memory image on the host and hand it out.
+int debug_build_image(const unsigned char *blob, int len, unsigned char *out, size_t cap, SmemLayout *L)
+{
+    DeviceModel m; HostModel hm;
+    if (build_host_model(&m, hm, blob, len, 1.0f) != 0) return -1;
+    *L = m.L;
+    if (hm.img.size() > cap) { set_error("debug image: buffer too small"); return -1; }
+    memcpy(out, hm.img.data(), hm.img.size());
+    return (int)hm.img.size();
+}
+
+int model_load(DeviceModel *m, const unsigned char *blob, int len, float lpc_gamma)
+{
+    HostModel hm;
+    if (build_host_model(m, hm, blob, len, lpc_gamma) != 0) return -1;
+    const std::vector<uint8_t> &img = hm.img;
+    const float *embed_pitch = hm.embed_pitch, *conv1_w = hm.conv1_w, *conv1_b = hm.conv1_b, *conv2_w = hm.conv2_w, *conv2_b = hm.conv2_b;
+    const float *dense1_w = hm.dense1_w, *dense1_b = hm.dense1_b, *dense2_w = hm.dense2_w, *dense2_b = hm.dense2_b;
+    const float *gad_w = hm.gad_w, *gad_b = hm.gad_b, *gbd_w = hm.gbd_w, *gbd_b = hm.gbd_b;
+    const float *emb_sig = hm.emb_sig, *emb_pred = hm.emb_pred, *emb_exc = hm.emb_exc;
+    // ---------------- device copies ----------------
+    bool ok = true;
+#define UP(field, src, count) ok = ok && ((m->field = to_device(src, (size_t)(count))) != nullptr);
+    UP(image, img.data(), img.size())
+    UP(emb_sig, emb_sig, 256 * 3 * NA) UP(emb_pred, emb_pred, 256 * 3 * NA) UP(emb_exc, emb_exc, 256 * 3 * NA)
+    UP(embed_pitch, embed_pitch, 256 * PITCH_EMBED)
+    UP(conv1_w, conv1_w, 3 * FRAME_IN * COND) UP(conv1_b, conv1_b, COND)
+    UP(conv2_w, conv2_w, 3 * COND * COND) UP(conv2_b, conv2_b, COND)
+    UP(dense1_w, dense1_w, COND * COND) UP(dense1_b, dense1_b, COND)
+    UP(dense2_w, dense2_w, COND * COND) UP(dense2_b, dense2_b, COND)
+    UP(gad_w, gad_w, COND * 3 * NA) UP(gad_b, gad_b, 3 * NA)
+    UP(gbd_w, gbd_w, COND * 3 * NB) UP(gbd_b, gbd_b, 3 * NB)
+    UP(rcp16, kRcpTable, 2048)
+    {
+        // DCT / FFT tables exactly as src/dump_lpcnet_tables.c:53,87-93 and kiss_fft.c:406-421 build them (host libm)
+        static const int factors[8] = {5, 64, 4, 16, 4, 4, 4, 1};
+        std::vector<float> dct(NB_BANDS * NB_BANDS), tw(2 * WINDOW_SIZE);
+        std::vector<int16_t> br(WINDOW_SIZE);
+        for (int i = 0; i < NB_BANDS; i++) for (int j = 0; j < NB_BANDS; j++) {
+            dct[i * NB_BANDS + j] = cos((i + .5) * j * M_PI / NB_BANDS);
+            if (j == 0) dct[i * NB_BANDS + j] *= sqrt(.5);
+        }
+        for (int i = 0; i < WINDOW_SIZE; i++) {
+            const double pi = 3.14159265358979323846264338327;
+            double phase = (-2 * pi / WINDOW_SIZE) * i;
+            tw[2 * i] = (float)cos(phase); tw[2 * i + 1] = (float)sin(phase);
+        }
+        // digit-reversal permutation of the 5x4x4x4 decomposition (compute_bitrev_table, kiss_fft.c:314-345)
+        struct Rec { static void go(int Fout, int16_t *f, int fstride, const int *fac) {
+            int p = fac[0], mm = fac[1];
+            if (mm == 1) { for (int j = 0; j < p; j++) { *f = (int16_t)(Fout + j); f += fstride; } }
+            else { for (int j = 0; j < p; j++) { go(Fout, f, fstride * p, fac + 2); f += fstride; Fout += mm; } }
+        } };
+        Rec::go(0, br.data(), 1, factors);
+        UP(dct, dct.data(), dct.size()) UP(twiddles, tw.data(), tw.size()) UP(bitrev, br.data(), br.size())
+        float gp[LPC_ORDER]; float gi = lpc_gamma;
+        for (int i = 0; i < LPC_ORDER; i++) { gp[i] = gi; gi *= lpc_gamma; }   // freq.c:299-308
+        UP(gamma_pow, gp, LPC_ORDER)
+        float pp[64];
+        for (int k = 0; k < 64; k++) pp[k] = pow(2.f, k / 21.) * 32;            // lpcnet_dec.c:124 (PITCH_MIN_PERIOD 32)
+        UP(pitch_pow, pp, 64)
+    }
+#undef UP
+    if (!ok) { set_error("model: device allocation/copy failed: %s", cudaGetErrorString(cudaGetLastError())); model_free(m); return -1; }
+
+    return 0;
+}
+
+void model_free(DeviceModel *m)
+{
+    void *ptrs[] = {m->image, m->emb_sig, m->emb_pred, m->emb_exc, m->embed_pitch, m->conv1_w, m->conv1_b, m->conv2_w, m->conv2_b,
+                    m->dense1_w, m->dense1_b, m->dense2_w, m->dense2_b, m->gad_w, m->gad_b, m->gbd_w, m->gbd_b, m->rcp16, m->dct,
+                    m->twiddles, m->bitrev, m->gamma_pow, m->pitch_pow, m->codebooks};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    memset(m, 0, sizeof(*m));
+}
+
+}  // namespace lpcnet_b200

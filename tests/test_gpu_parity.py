@@ -1,0 +1,187 @@
+"""GPU parity tests (-m gpu): the CUDA engine, called through the C ABI (ctypes), against
+  * the committed golden vectors produced by the untouched reference (tests/golden, make_golden.py), and
+  * the CPU oracle restatement (oracle/lpcnet_oracle.c) on the same seeded inputs.
+Bar: BIT-EXACT int16 PCM (integer GEMVs + op-for-op fp32 elementwise math), no tolerance anywhere.
+"""
+import hashlib
+import json
+import os
+import numpy as np
+import pytest
+import helpers as H
+from fixtures import make_feature_batch, make_packets
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import lpcnet_b200
+    from lpcnet_b200 import build
+    build.build()
+    assert lpcnet_b200.device_count() > 0, "GPU test selected but no CUDA device is visible"
+    return lpcnet_b200
+
+
+def _batch(eng, n):
+    return eng.Batch(n, H.blob("int8"), lpc_gamma=H.LPC_GAMMA, codebooks=H.codebooks())
+
+
+def _first_diff(a, b):
+    d = np.argwhere(a != b)
+    return None if d.size == 0 else tuple(d[0])
+
+
+def test_frame_network_bit_exact(eng):
+    """run_frame_network taps (gru_a/gru_b conditioning, weighted LPC) for 12 frames x 9 streams vs the oracle."""
+    n, T = 9, 12
+    f = make_feature_batch(range(20, 20 + n), T)
+    b = _batch(eng, n)
+    ga, gb, lpc = b.debug_frame_network(f)
+    L = H.oracle_lib()
+    for s in range(n):
+        st = L.oracle_state_create(H.oracle_model())
+        for t in range(T):
+            a = np.zeros(1152, np.float32); c = np.zeros(48, np.float32); l = np.zeros(16, np.float32)
+            L.oracle_frame_network(st, f[s, t].ctypes.data, a.ctypes.data, c.ctypes.data, l.ctypes.data)
+            np.testing.assert_array_equal(ga[s, t].view(np.uint32), a.view(np.uint32), err_msg="gru_a_condition s=%d t=%d" % (s, t))
+            np.testing.assert_array_equal(gb[s, t].view(np.uint32), c.view(np.uint32), err_msg="gru_b_condition s=%d t=%d" % (s, t))
+            np.testing.assert_array_equal(lpc[s, t].view(np.uint32), l.view(np.uint32), err_msg="lpc s=%d t=%d" % (s, t))
+        L.oracle_state_destroy(st)
+    b.close()
+
+
+def test_synthesis_matches_reference_golden(eng):
+    gold = np.load(os.path.join(H.GOLDEN, "synth_A.npz"))["pcm"]
+    b = _batch(eng, 4)
+    got = b.synthesize(make_feature_batch(range(4), 40))
+    assert (got[:, :320] == 0).all()
+    assert _first_diff(got, gold) is None, "first mismatch (stream, sample) = %s" % (_first_diff(got, gold),)
+    ms, launches = b.last_sample_kernel_ms()
+    assert ms > 0 and launches >= 5
+    b.close()
+
+
+def test_synthesis_matches_oracle_ragged_batch(eng):
+    """70 streams (two full CTAs + a 6-lane tail), 36-float feature stride, distinct features per stream."""
+    n, T = 70, 10
+    f20 = make_feature_batch(range(300, 300 + n), T)
+    f36 = np.zeros((n, T, 36), np.float32); f36[:, :, :20] = f20; f36[:, :, 20:] = 7.0    # padding must be ignored
+    b = _batch(eng, n)
+    got = b.synthesize(f36)
+    want = H.oracle_synth(f20, "int8")
+    assert _first_diff(got, want) is None, "first mismatch (stream, sample) = %s" % (_first_diff(got, want),)
+    b.close()
+
+
+def test_chunked_calls_equal_one_call_and_state_roundtrip(eng):
+    """Streaming use: 3+1+20+17 frames in four calls (crossing the silent warm-up and the internal 16-frame chunk)
+    must equal one 41-frame call; afterwards the device state equals the oracle's state."""
+    n, T = 5, 41
+    f = make_feature_batch(range(40, 40 + n), T)
+    b1, b2 = _batch(eng, n), _batch(eng, n)
+    one = b1.synthesize(f)
+    parts, t0 = [], 0
+    for k in (3, 1, 20, 17):
+        parts.append(b2.synthesize(f[:, t0:t0 + k]))
+        t0 += k
+    np.testing.assert_array_equal(np.concatenate(parts, axis=1), one)
+    np.testing.assert_array_equal(one, H.oracle_synth(f, "int8"))
+    L = H.oracle_lib()
+    st = L.oracle_state_create(H.oracle_model())
+    pcm = np.zeros(160, np.int16)
+    for t in range(T):
+        L.oracle_synthesize(st, f[2, t].ctypes.data, pcm.ctypes.data, 160)
+    ga = np.zeros(384, np.float32); gb = np.zeros(16, np.float32); ls = np.zeros(16, np.float32); misc = np.zeros(2, np.int32); rng = np.zeros(4, np.uint32)
+    L.oracle_get_state(st, ga.ctypes.data, gb.ctypes.data, ls.ctypes.data, misc.ctypes.data, rng.ctypes.data)
+    got = b2.get_state(2)
+    np.testing.assert_array_equal(got["gru_a"].view(np.uint32), ga.view(np.uint32))
+    np.testing.assert_array_equal(got["gru_b"].view(np.uint32), gb.view(np.uint32))
+    np.testing.assert_array_equal(got["last_sig"].view(np.uint32), ls.view(np.uint32))
+    assert got["last_exc"] == misc[0] and (got["rng"] == rng).all()
+    # reset returns to the fresh-state trajectory
+    b2.reset()
+    np.testing.assert_array_equal(b2.synthesize(f[:, :6]), one[:, :6 * 160])
+    b1.close(); b2.close(); L.oracle_state_destroy(st)
+
+
+def test_partial_frames(eng):
+    """N < 160 samples per call (the PLC uses 80): reference semantics = one feature vector per call, N samples."""
+    n, T = 3, 9
+    f = make_feature_batch(range(60, 60 + n), T)
+    b = _batch(eng, n)
+    got = b.synthesize(f, samples_per_frame=80)
+    L = H.oracle_lib()
+    for s in range(n):
+        st = L.oracle_state_create(H.oracle_model())
+        pcm = np.zeros(80, np.int16)
+        for t in range(T):
+            L.oracle_synthesize(st, f[s, t].ctypes.data, pcm.ctypes.data, 80)
+            np.testing.assert_array_equal(got[s, t * 80:(t + 1) * 80], pcm)
+        L.oracle_state_destroy(st)
+    b.close()
+
+
+def test_decode_matches_reference_golden(eng):
+    gold = np.load(os.path.join(H.GOLDEN, "decode_A.npz"))["pcm"]
+    b = _batch(eng, 3)
+    got = b.decode(np.stack([make_packets(s, 6) for s in range(3)]))
+    assert _first_diff(got, gold) is None, "first mismatch (stream, sample) = %s" % (_first_diff(got, gold),)
+    b.close()
+
+
+def test_reference_digests(eng):
+    """Longer runs pinned by sha256 of the reference's output (tests/golden/digests.json)."""
+    dig = json.load(open(os.path.join(H.GOLDEN, "digests.json")))
+    b = _batch(eng, 16)
+    got = b.synthesize(make_feature_batch(range(16), 150))
+    assert hashlib.sha256(got.tobytes()).hexdigest() == dig["synth_A_16x150"]
+    b.close()
+    b = _batch(eng, 8)
+    got = b.decode(np.stack([make_packets(s, 25) for s in range(8)]))
+    assert hashlib.sha256(got.tobytes()).hexdigest() == dig["decode_A_8x25"]
+    b.close()
+
+
+def test_drop_in_single_stream_api(eng):
+    """include/lpcnet.h used exactly like src/lpcnet_demo.c:202-219 (-synthesis) and :176-188 (-decode)."""
+    gold = np.load(os.path.join(H.GOLDEN, "synth_A.npz"))["pcm"]
+    L = eng.lib()
+    L.lpcnet_b200_set_default_model(H.blob("int8"), len(H.blob("int8")), H.LPC_GAMMA)
+    cb = H.codebooks()
+    L.lpcnet_b200_set_default_codebooks(cb.ctypes.data, cb.size)
+    net = eng.LPCNet()
+    f = make_feature_batch([1], 12)[0]
+    out = np.concatenate([net.synthesize(f[t]) for t in range(12)])
+    np.testing.assert_array_equal(out, gold[1, :12 * 160])
+    net.reset()
+    out2 = np.concatenate([net.synthesize(f[t]) for t in range(4)])
+    np.testing.assert_array_equal(out2, gold[1, :4 * 160])
+    net.load_model(H.blob("int8"))                      # lpcnet_load_model on a live state (lpcnet.c:202)
+    net.close()
+    gdec = np.load(os.path.join(H.GOLDEN, "decode_A.npz"))["pcm"]
+    dec = eng.LPCNetDecoder()
+    pk = make_packets(2, 3)
+    out = np.concatenate([dec.decode(pk[t]) for t in range(3)])
+    np.testing.assert_array_equal(out, gdec[2, :3 * 640])
+    dec.close()
+    with pytest.raises(eng.LPCNetB200Error):
+        eng.Batch(2, H.blob("int8")[:5000])              # malformed blob -> error, not a crash
+
+
+@pytest.mark.parametrize("n", [1024])
+def test_full_width_properties(eng, n):
+    """BASELINE-sized batch (>=1024 streams): size-independent checks — (i) replicated inputs give replicated
+    outputs in every CTA/lane position, (ii) a sample of streams equals the oracle, (iii) determinism across runs."""
+    T = 6
+    base = make_feature_batch(range(500, 508), T)
+    f = base[np.arange(n) % 8]
+    b = _batch(eng, n)
+    got = b.synthesize(f)
+    want = H.oracle_synth(base, "int8")
+    for s in range(n):
+        if not np.array_equal(got[s], want[s % 8]):
+            raise AssertionError("stream %d differs from its replica source %d at sample %s" % (s, s % 8, np.argwhere(got[s] != want[s % 8])[0]))
+    b.reset()
+    np.testing.assert_array_equal(b.synthesize(f), got)
+    b.close()

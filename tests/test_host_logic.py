@@ -1,0 +1,144 @@
+"""CPU tests (-m "not gpu") of the product's HOST logic: library loading, C-ABI surface, blob validation and the
+shared-memory image the per-sample kernel consumes (checked by replaying the kernel's block walk in numpy against
+a dense reconstruction of the model).  No compute entry point is called: without a GPU the engine must refuse."""
+import ctypes
+import os
+import re
+import numpy as np
+import pytest
+import helpers as H
+import lpcnet_b200
+from lpcnet_b200 import api
+
+ROOT = H.ROOT
+
+
+@pytest.fixture(scope="module")
+def L():
+    from lpcnet_b200 import build
+    build.build()
+    return api.lib()
+
+
+def _declared_symbols():
+    syms = []
+    for hdr in ("lpcnet.h", "lpcnet_b200.h"):
+        txt = open(os.path.join(ROOT, "include", hdr)).read()
+        txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+        syms += re.findall(r"LPCNET_EXPORT[^;(#]*?\b(lpcnet\w*)\s*\(", txt)
+    return sorted(set(syms))
+
+
+def test_library_exports_every_declared_symbol(L):
+    syms = _declared_symbols()
+    assert "lpcnet_synthesize" in syms and "lpcnet_decode" in syms and "lpcnet_b200_batch_synthesize" in syms
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(L, s), "missing export " + s
+
+
+def test_no_cpu_fallback_without_gpu(L):
+    if L.lpcnet_b200_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(api.LPCNetB200Error, match="no CUDA device"):
+        lpcnet_b200.Batch(4, H.blob("int8"))
+    assert not L.lpcnet_create()
+    assert not L.lpcnet_decoder_create()
+
+
+def _image(L, blob):
+    out = np.zeros(256 * 1024, np.uint8)
+    lay = np.zeros(16, np.uint32)
+    L.lpcnet_b200_debug_image.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    r = L.lpcnet_b200_debug_image(blob, len(blob), out.ctypes.data, out.size, lay.ctypes.data)
+    return r, out, lay
+
+
+def test_blob_validation(L):
+    b = H.blob("int8")
+    r, _, _ = _image(L, b)
+    assert r > 0
+    assert _image(L, b[:-100])[0] < 0                       # truncated record (parse_lpcnet_weights.c:40)
+    bad = bytearray(b); bad[12:16] = (10 ** 9).to_bytes(4, "little")   # size > block_size
+    assert _image(L, bytes(bad))[0] < 0
+    assert _image(L, b"")[0] < 0
+    assert _image(L, b[: 64 * 1000])[0] < 0                 # cut mid-way: arrays missing
+    assert b"float" in L.lpcnet_b200_last_error() or _image(L, H.blob("float"))[0] < 0   # float flavour: refused for now
+
+
+def test_smem_image_replays_to_the_dense_model(L):
+    """Walk the image exactly like the kernel (warp -> slot -> gate -> padded block list; (row group, K half) for
+    GRU_B) and check the integer GEMV it encodes equals the dense int8 matrices of the model for random u8 inputs."""
+    import gen_model
+    common, only8, _ = gen_model.make_model()
+    arrs = {n: a for n, _, a in common + only8}
+    r, img, lay = _image(L, H.blob("int8"))
+    wA, metaA, wB, metaB, image_bytes, total, nA, nB, SM_IMAGE, PARA, DIRA, GRPA, DIRB, WBREC, PARB, FCW = [int(v) for v in lay]
+    assert r == image_bytes and total <= 227 * 1024 and total == SM_IMAGE + image_bytes
+    img = img[:image_bytes]
+    rel = lambda o: o - SM_IMAGE
+
+    def dense_from_sparse(w8, idx, nrows, ncols):
+        M = np.zeros((nrows, ncols), np.int32); p = 0; wp = 0
+        for rg in range(nrows // 8):
+            nb = idx[p]; p += 1
+            for _ in range(nb):
+                pos = idx[p]; p += 1
+                M[rg * 8:rg * 8 + 8, pos:pos + 4] = w8[wp:wp + 32].reshape(8, 4); wp += 32
+        return M
+    MA = dense_from_sparse(arrs["sparse_gru_a_recurrent_weights"].astype(np.int32), arrs["sparse_gru_a_recurrent_weights_idx"], 1152, 384)
+    MB = dense_from_sparse(arrs["gru_b_weights"].astype(np.int32), arrs["gru_b_weights_idx"], 48, 384)
+    rng = np.random.default_rng(0)
+    x = rng.integers(0, 255, 384).astype(np.int32)
+    want_A, want_B = MA @ x, MB @ x
+
+    dirA = img[DIRA:DIRA + 16 * 3 * 3 * 2 * 4].view(np.uint32).reshape(16, 3, 3, 2)
+    grpA = img[GRPA:GRPA + 16 * 3 * 4].view(np.uint32).reshape(16, 3)
+    parA = img[PARA:PARA + 16 * 3 * 3 * 16 * 4].view(np.float32).reshape(16, 3, 3, 2, 8)
+    wAi = img[rel(wA):rel(wA) + nA * 32].view(np.int8).astype(np.int32).reshape(nA, 8, 4)
+    mA = img[rel(metaA):rel(metaA) + nA * 2].view(np.uint16)
+    assert sorted(grpA.reshape(-1).tolist()) == list(range(48))           # every neuron group owned exactly once
+    got = np.zeros(1152, np.int64)
+    loads = []
+    for w in range(16):
+        tot = 0
+        for sl in range(3):
+            g = int(grpA[w, sl])
+            for q in range(3):
+                b0, nb = int(dirA[w, sl, q, 0]), int(dirA[w, sl, q, 1])
+                assert nb % 2 == 0
+                tot += nb
+                for b in range(b0, b0 + nb):
+                    assert mA[b] % 128 == 0
+                    pos = int(mA[b]) // 128 * 4
+                    got[q * 384 + 8 * g:q * 384 + 8 * g + 8] += wAi[b] @ x[pos:pos + 4]
+                np.testing.assert_array_equal(parA[w, sl, q, 0], arrs["sparse_gru_a_subias"][1, q * 384 + 8 * g:q * 384 + 8 * g + 8])
+                np.testing.assert_array_equal(parA[w, sl, q, 1], arrs["sparse_gru_a_recurrent_weights_diag"][q * 384 + 8 * g:q * 384 + 8 * g + 8])
+        loads.append(tot)
+    np.testing.assert_array_equal(got, want_A)
+    assert max(loads) <= 1.15 * (sum(loads) / 16)                          # LPT balancing of the 16 compute warps
+
+    dirB = img[DIRB:DIRB + 12 * 2 * 4].view(np.uint32).reshape(6, 2, 2)
+    wBi = img[rel(wB):rel(wB) + nB * 32].view(np.int8).astype(np.int32).reshape(nB, 8, 4)
+    mB = img[rel(metaB):rel(metaB) + nB * 2].view(np.uint16)
+    gotB = np.zeros(48, np.int64)
+    for rg in range(6):
+        for half in range(2):
+            b0, nb = int(dirB[rg, half, 0]), int(dirB[rg, half, 1])
+            for b in range(b0, b0 + nb):
+                pos = int(mB[b]) // 128 * 4
+                gotB[rg * 8:rg * 8 + 8] += wBi[b] @ x[pos:pos + 4]
+    np.testing.assert_array_equal(gotB, want_B)
+    # GRU_B recurrent block layout [out/8][in/4][8][4] and su-biases
+    np.testing.assert_array_equal(img[WBREC:WBREC + 768].view(np.int8), arrs["gru_b_recurrent_weights"])
+    np.testing.assert_array_equal(img[PARB:PARB + 96 * 4].view(np.float32), arrs["gru_b_subias"].reshape(-1))
+    fcw = img[FCW:FCW + 256 * 33 * 4].view(np.float32).reshape(256, 33)
+    np.testing.assert_array_equal(fcw[:, :32], arrs["dual_fc_weights"].reshape(256, 32))
+
+
+def test_python_mirror_matches_reference_operator_names():
+    for name in ("LPCNet", "LPCNetDecoder", "Batch"):
+        assert hasattr(lpcnet_b200, name)
+    for m in ("load_model", "synthesize", "reset"):
+        assert hasattr(lpcnet_b200.LPCNet, m)
+    assert hasattr(lpcnet_b200.LPCNetDecoder, "decode")
