@@ -1,0 +1,315 @@
+#!/usr/bin/env python3
+"""bench.py — LPCNet synthesis throughput on B200 (driver contract: one JSON line on stdout from rank 0).
+
+  python bench.py --gpus N --steps K --warmup W            # this engine   (N>1: launched under torchrun, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K ...   # the reference's own CPU implementation on the host cores
+
+Metric (BASELINE.json): synthesized 16 kHz samples/s over batched independent streams.
+A "step" = one pass of the hot path over one batch of synthetic feature frames:
+  workload `config3_int8`: 4096 streams/GPU x FRAMES frames x 160 samples, int8 block-sparse GRU_A (BASELINE config 3,
+  the configuration the metric's ">= 1e8 samples/s/GPU at batch >= 1024 streams" target is quoted on).
+`value`  : inputs already resident in HBM, PCM left in HBM, CUDA events on the engine's stream, max over ranks.
+`e2e`    : the same step through the host-pointer C-ABI call (lpcnet_b200_batch_synthesize): pinned host features
+           -> H2D -> kernels -> D2H PCM, all inside the timed region.
+`roofline`: per-sample kernel (the dominant kernel), algorithmic bytes/sample x samples per launch / its measured
+           duration.  The weights are resident in SHARED MEMORY, so the algorithmic bytes are served by SMEM/L2, not HBM:
+           `frac` is reported against the measured HBM copy peak as the contract requires and additionally against the
+           nominal aggregate SMEM bandwidth at the SM clock observed under load (`frac_of_smem_peak`).
+`cpu_baseline`: the untouched reference compiled by oracle/Makefile (oracle/_ref, build T = -Ofast AVX2/FMA) timed on
+           this box's host cores on a bounded sample of the same workload (kind "reference"); falls back to the oracle
+           port (kind "port") only if the compiled reference did not travel.
+The oracle/reference are used here ONLY as the timed CPU baseline, never as the thing measured for `value`/`e2e`.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import numpy as np
+
+STREAMS_PER_GPU = 4096
+FRAMES = 10               # frames per step (1600 samples per stream per step)
+LPC_GAMMA = 0.9
+METRIC = "16 kHz samples/sec (batched independent streams), whole job"
+UNIT = "samples/s"
+
+
+def features_for(n, frames, first_stream=0):
+    """Distinct synthetic features per stream (seed 1000+s); 64 distinct trajectories tiled so set-up stays cheap."""
+    from fixtures import make_feature_batch
+    base = make_feature_batch(range(first_stream, first_stream + 64), frames)
+    return np.ascontiguousarray(base[np.arange(n) % 64])
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (profiling recipe's clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.lines, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        load = sorted(sm)[len(sm) // 2:]                      # upper half = samples taken under load
+        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(frames, nthreads, repeat=1):
+    """Times the reference's own CPU implementation (oracle/_ref build T, README flags restricted to AVX2/FMA) with one
+    independent stream per host thread.  Returns (samples_per_s, kind, cores, sample_description)."""
+    import helpers as H
+    blob = H.blob("int8")
+    feats = features_for(nthreads, frames)
+    pcm = np.zeros((nthreads, frames * 160), np.int16)
+    so = os.path.join(ROOT, "oracle", "_ref", "liblpcnet_ref_T.so")
+    if os.path.exists(so):
+        L = H.ref_lib("T")
+        best = None
+        for _ in range(repeat):
+            sec = L.ref_time_synthesis(blob, len(blob), feats.ctypes.data, 20, frames, nthreads, pcm.ctypes.data)
+            best = sec if best is None else min(best, sec)
+        kind = "reference"
+    else:
+        L = H.oracle_lib()
+        best = L.oracle_synthesize_batch(H.oracle_model("int8"), feats.ctypes.data, 20, nthreads, frames, nthreads, pcm.ctypes.data)
+        kind = "port"
+    samples = nthreads * max(0, frames - 2) * 160          # the first two frames are silent warm-up (no network evaluation)
+    return samples / best, kind, nthreads, "%d independent streams (1 per host thread) x %d frames, lpcnet_synthesize, int8 AVX2 path" % (nthreads, frames)
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    ncores = os.cpu_count() or 1
+    frames = 250                                            # ~0.15 s of CPU per thread-step at ~2.7e5 samples/s/core
+    for _ in range(args.warmup):
+        cpu_reference_run(40, ncores)
+    t0 = time.time()
+    vals = []
+    for _ in range(args.steps):
+        v, kind, cores, sample = cpu_reference_run(frames, ncores)
+        vals.append(v)
+    total_s = time.time() - t0
+    value = float(np.mean(vals))
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total_s / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8*s8->s32 (int8 DOT_PROD path) + f32", "data": "synthetic",
+        "config": {"workload": "config3_int8 on host CPU: one stream per host thread, reference src/ compiled -Ofast -mavx2 -mfma", "frames_per_step": frames,
+                   "streams": ncores},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="streams per GPU")
+    ap.add_argument("--frames", type=int, default=FRAMES, help="frames per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import helpers as H
+    import lpcnet_b200
+    from lpcnet_b200 import build
+    build.build()
+    if lpcnet_b200.device_count() <= 0:
+        raise SystemExit("bench: no CUDA device; this engine has no CPU fallback")
+    L = lpcnet_b200.lib()
+    n, F = args.streams, args.frames
+    blob = H.blob("int8")
+    batch = lpcnet_b200.Batch(n, blob, lpc_gamma=LPC_GAMMA, device=local)
+    algo_total, algo_sparse = batch.algorithmic_bytes()
+
+    feats = features_for(n, F, first_stream=64 * rank)
+    fbytes, pbytes = feats.nbytes, n * F * 160 * 2
+    d_feat = L.lpcnet_b200_device_alloc(fbytes)
+    d_pcm = L.lpcnet_b200_device_alloc(pbytes)
+    assert d_feat and d_pcm
+    L.lpcnet_b200_memcpy_h2d(d_feat, feats.ctypes.data, fbytes)
+    # pinned host buffers for the e2e leg
+    h_feat_p = L.lpcnet_b200_host_alloc(fbytes)
+    h_pcm_p = L.lpcnet_b200_host_alloc(pbytes)
+    ctypes.memmove(h_feat_p, feats.ctypes.data, fbytes)
+
+    def barrier():
+        batch.sync()
+        if dist is not None:
+            dist.barrier()
+
+    def step_device():
+        batch.synthesize_device(d_feat, F, 20, d_pcm)
+
+    def step_e2e():
+        if L.lpcnet_b200_batch_synthesize(batch._h, h_feat_p, F, 20, 160, h_pcm_p) != 0:
+            raise RuntimeError(L.lpcnet_b200_last_error())
+
+    # the first two frames after a reset are silent and skip the sample loop: consume them before anything is timed
+    batch.synthesize_device(d_feat, 2, 20, d_pcm)
+    for _ in range(args.warmup):
+        step_device()
+
+    # ---------------- timed: device-resident ----------------
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    wall0 = time.time()
+    step_ms, kern_ms, launches = [], [], 0
+    for _ in range(args.steps):
+        batch.flush_l2()                                     # evict L2 between timed iterations (outside the event bracket)
+        batch.timer_start()
+        step_device()
+        step_ms.append(batch.timer_stop())
+        ms, k = batch.last_sample_kernel_ms()
+        kern_ms.append(ms); launches += k
+    barrier()
+    wall = time.time() - wall0
+    clk = clocks.stop()
+    dev_s = sum(step_ms) * 1e-3
+    # ---------------- timed: end-to-end through the host-pointer C-ABI ----------------
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e2e_ms = []
+    for _ in range(args.steps):
+        batch.flush_l2(); batch.sync()
+        batch.timer_start()                                  # event on the engine's (idle) stream, then H2D -> kernels -> D2H
+        step_e2e()                                           # returns after the D2H copy has completed
+        e2e_ms.append(batch.timer_stop())
+    barrier()
+    e2e_s = sum(e2e_ms) * 1e-3
+
+    if dist is not None:
+        import torch
+        t = torch.tensor([dev_s, e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_s, e2e_s = float(t[0]), float(t[1])
+        # the one real exchange of the path: gather the PCM shards to rank 0 over NCCL (timed separately, device events)
+        pcm_t = torch.empty(n * F * 160, dtype=torch.int16, device="cuda")
+        outs = [torch.empty_like(pcm_t) for _ in range(world)] if rank == 0 else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier(); torch.cuda.synchronize()
+        e0.record()
+        dist.gather(pcm_t, outs, dst=0)
+        e1.record(); torch.cuda.synchronize()
+        gather_ms = e0.elapsed_time(e1)
+    else:
+        gather_ms = None
+
+    if rank == 0:
+        samples_step = world * n * F * 160
+        value = samples_step * args.steps / dev_s
+        e2e_value = samples_step * args.steps / e2e_s
+        peak, peak_src = measured_peaks()
+        kms = float(np.mean(kern_ms))                        # per-sample kernel duration per launch (one launch per step here)
+        samples_launch = n * F * 160
+        achieved = samples_launch * algo_total / (kms * 1e-3) / 1e9
+        sm_mhz = clk.get("sm_mhz") or 1965.0
+        smem_peak = 128.0 * 148 * sm_mhz * 1e6 / 1e9          # nominal 128 B/clk/SM at the clock observed under load
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8*s8->s32 (dp4a) + f32", "data": "synthetic",
+            "config": {"workload": "config3_int8: %d streams/GPU x %d frames x 160 samples per step, int8 block-sparse GRU_A, bit-exact vs reference build A" % (n, F),
+                       "streams_per_gpu": n, "frames_per_step": F, "samples_per_step": samples_step, "parallelism": "streams sharded across GPUs (dp%d), no data-path collective" % world,
+                       "l2": "256 MiB memset between timed steps (outside the event bracket)", "x_realtime_per_stream": value / world / n / 16000.0},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(fbytes), "d2h_bytes_per_step": int(pbytes), "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "kernel": "lpcnet_sample_kernel", "kernel_ms_per_launch": kms, "kernel_share_of_step": kms * args.steps / (dev_s * 1e3),
+                         "algorithmic_bytes_per_sample": algo_total, "sparse_gemv_bytes_per_sample": algo_sparse,
+                         "level_serving_the_bytes": "shared memory (weights resident per SM) + L2 (embedding rows)",
+                         "smem_peak_gbs_nominal": smem_peak, "frac_of_smem_peak": achieved / smem_peak,
+                         "sparse_gemv_achieved_gbs": samples_launch * algo_sparse / (kms * 1e-3) / 1e9,
+                         "sparse_gemv_frac_of_smem_peak": samples_launch * algo_sparse / (kms * 1e-3) / 1e9 / smem_peak},
+            "wall_s_timed_region": wall,
+        }
+        if gather_ms is not None:
+            out["pcm_gather"] = {"ms": gather_ms, "bytes_per_rank": int(pbytes), "backend": "nccl"}
+        if world == 1 and not args.no_cpu_baseline:
+            ncores = os.cpu_count() or 1
+            v, kind, cores, sample = cpu_reference_run(400, ncores)
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+        print(json.dumps(out), flush=True)
+
+    L.lpcnet_b200_device_free(d_feat); L.lpcnet_b200_device_free(d_pcm)
+    L.lpcnet_b200_host_free(h_feat_p); L.lpcnet_b200_host_free(h_pcm_p)
+    batch.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

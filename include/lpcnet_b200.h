@@ -75,6 +75,20 @@ LPCNET_EXPORT int lpcnet_b200_batch_decode_device(LPCNetB200Batch *b, const unsi
 /* Device time (ms, CUDA events on the engine's stream) the per-sample kernel took in the last synthesize/decode
  * call, summed over its launches; *launches receives how many engine kernels that call launched in total. */
 LPCNET_EXPORT float lpcnet_b200_batch_last_sample_kernel_ms(const LPCNetB200Batch *b, int *launches);
+/* CUDA-event stopwatch on the engine's stream, L2 eviction (256 MiB overwrite) and stream sync: what a benchmark
+ * needs to time the engine on the device without any other CUDA binding. */
+LPCNET_EXPORT int lpcnet_b200_batch_timer_start(LPCNetB200Batch *b);
+LPCNET_EXPORT float lpcnet_b200_batch_timer_stop(LPCNetB200Batch *b);     /* ms since timer_start, <0 on error */
+LPCNET_EXPORT int lpcnet_b200_batch_flush_l2(LPCNetB200Batch *b);
+LPCNET_EXPORT int lpcnet_b200_batch_sync(LPCNetB200Batch *b);
+/* Raw device / pinned-host memory for callers without their own CUDA binding. */
+LPCNET_EXPORT void *lpcnet_b200_device_alloc(size_t bytes);
+LPCNET_EXPORT void lpcnet_b200_device_free(void *p);
+LPCNET_EXPORT int lpcnet_b200_memcpy_h2d(void *dst, const void *src, size_t bytes);
+LPCNET_EXPORT int lpcnet_b200_memcpy_d2h(void *dst, const void *src, size_t bytes);
+LPCNET_EXPORT void *lpcnet_b200_host_alloc(size_t bytes);                 /* pinned */
+LPCNET_EXPORT void lpcnet_b200_host_free(void *p);
+
 /* Algorithmic bytes one synthesized sample of one stream must read: total and the
  * sparse-GEMV-only subset (GRU_A weights + indices). */
 LPCNET_EXPORT int lpcnet_b200_batch_algorithmic_bytes(const LPCNetB200Batch *b, long *total, long *sparse_gemv);
@@ -84,9 +98,15 @@ LPCNET_EXPORT int lpcnet_b200_batch_is_float(const LPCNetB200Batch *b);
  * misc[2]={last_exc, frame_count}, rng[4]. Any pointer may be NULL. */
 LPCNET_EXPORT int lpcnet_b200_batch_get_state(LPCNetB200Batch *b, int s, float *gru_a, float *gru_b, float *last_sig,
                                               int *misc, uint32_t *rng);
-/* Frame-network tap (tests): conditioning of the most recent frame for stream s: gru_a_condition[1152],
- * gru_b_condition[48], lpc[16]. */
-LPCNET_EXPORT int lpcnet_b200_batch_get_frame_taps(LPCNetB200Batch *b, int s, float *ga, float *gb, float *lpc);
+/* Frame-network tap (tests): run ONLY the 100 Hz kernels (reference run_frame_network, src/lpcnet.c:82-120) on
+ * host features [n][nframes<=16][feature_stride] and return gru_a_condition [n][nframes][1152], gru_b_condition
+ * [n][nframes][48] and the gamma-weighted LPC [n][nframes][16] each frame's sample loop would use. */
+LPCNET_EXPORT int lpcnet_b200_debug_frame_network(LPCNetB200Batch *b, const float *features, int nframes,
+                                                  int feature_stride, float *ga, float *gb, float *lpc);
+/* Test hook (host only, no CUDA): build the per-sample kernel's shared-memory image for a blob.  Returns the
+ * image size or <0; layout[16] receives the offsets documented in lpcnet_b200/csrc/batch_api.cu. */
+LPCNET_EXPORT int lpcnet_b200_debug_image(const unsigned char *blob, int len, unsigned char *out, size_t cap,
+                                          uint32_t *layout);
 
 /* Default model / codebooks for the lpcnet.h single-stream API (the reference compiles its model in; this
  * library loads it at run time).  Also settable through env LPCNET_B200_MODEL / LPCNET_B200_CODEBOOKS (file

@@ -41,6 +41,16 @@ def lib():
     L.lpcnet_b200_debug_frame_network.argtypes = [c_p, c_p, ctypes.c_int, ctypes.c_int, c_p, c_p, c_p]
     L.lpcnet_b200_set_default_model.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_float]
     L.lpcnet_b200_set_default_codebooks.argtypes = [c_p, ctypes.c_size_t]
+    L.lpcnet_b200_batch_timer_start.argtypes = [c_p]
+    L.lpcnet_b200_batch_timer_stop.restype = ctypes.c_float
+    L.lpcnet_b200_batch_timer_stop.argtypes = [c_p]
+    L.lpcnet_b200_batch_flush_l2.argtypes = [c_p]
+    L.lpcnet_b200_batch_sync.argtypes = [c_p]
+    L.lpcnet_b200_device_alloc.restype = c_p
+    L.lpcnet_b200_device_alloc.argtypes = [ctypes.c_size_t]
+    L.lpcnet_b200_device_free.argtypes = [c_p]
+    L.lpcnet_b200_memcpy_h2d.argtypes = [c_p, c_p, ctypes.c_size_t]
+    L.lpcnet_b200_memcpy_d2h.argtypes = [c_p, c_p, ctypes.c_size_t]
     L.lpcnet_b200_host_alloc.restype = c_p
     L.lpcnet_b200_host_alloc.argtypes = [ctypes.c_size_t]
     L.lpcnet_b200_host_free.argtypes = [c_p]
@@ -120,6 +130,24 @@ class Batch:
     def decode_device(self, d_packets_ptr, npackets, d_pcm_ptr, cuda_stream=None):
         if self._L.lpcnet_b200_batch_decode_device(self._h, d_packets_ptr, npackets, d_pcm_ptr, cuda_stream) != 0:
             raise LPCNetB200Error("lpcnet_b200_batch_decode_device: " + _err())
+
+    def timer_start(self):
+        if self._L.lpcnet_b200_batch_timer_start(self._h) != 0:
+            raise LPCNetB200Error(_err())
+
+    def timer_stop(self):
+        ms = self._L.lpcnet_b200_batch_timer_stop(self._h)
+        if ms < 0:
+            raise LPCNetB200Error(_err())
+        return float(ms)
+
+    def flush_l2(self):
+        if self._L.lpcnet_b200_batch_flush_l2(self._h) != 0:
+            raise LPCNetB200Error(_err())
+
+    def sync(self):
+        if self._L.lpcnet_b200_batch_sync(self._h) != 0:
+            raise LPCNetB200Error(_err())
 
     def last_sample_kernel_ms(self):
         k = ctypes.c_int(0)

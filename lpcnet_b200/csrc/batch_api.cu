@@ -31,8 +31,10 @@ struct LPCNetB200Batch {
     short *d_pcm; size_t d_pcm_cap;
     uint8_t *d_packets; size_t d_packets_cap;
     cudaStream_t stream;
-    cudaEvent_t ev0, ev1;
-    float last_ms; int last_launches;
+    cudaEvent_t ev0, ev1;                         // user timer (lpcnet_b200_batch_timer_*)
+    std::vector<cudaEvent_t> *kev;                // event pairs around every per-sample kernel launch of the last call
+    int kev_used;
+    int last_launches;
 };
 
 static int ensure(void **p, size_t *cap, size_t bytes)
@@ -112,7 +114,8 @@ LPCNetB200Batch *lpcnet_b200_batch_create(int n_streams, const unsigned char *bl
     if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", device); return nullptr; }
     LPCNetB200Batch *b = (LPCNetB200Batch *)calloc(1, sizeof(*b));
     b->device = device; b->n = n_streams;
-    if (model_load(&b->model, blob, blob_len, lpc_gamma) != 0) { free(b); return nullptr; }
+    b->kev = new std::vector<cudaEvent_t>();
+    if (model_load(&b->model, blob, blob_len, lpc_gamma) != 0) { delete b->kev; free(b); return nullptr; }
     const size_t n = n_streams;
     bool ok = true;
     auto al = [&](void **p, size_t bytes) { if (ok && cudaMalloc(p, bytes) != cudaSuccess) ok = false; };
@@ -138,6 +141,7 @@ void lpcnet_b200_batch_destroy(LPCNetB200Batch *b)
     void *ptrs[] = {b->hA, b->hB, b->last_sig, b->deemph, b->last_exc, b->rng, b->fs.conv1_state, b->fs.conv2_state, b->fs.lpc_carry,
                     b->fs.vq_mem, b->condA, b->condB, b->lpc_raw, b->d_features, b->d_pcm, b->d_packets};
     for (void *p : ptrs) if (p) cudaFree(p);
+    if (b->kev) { for (cudaEvent_t e : *b->kev) cudaEventDestroy(e); delete b->kev; }
     model_free(&b->model);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
@@ -169,7 +173,8 @@ static int synth_device(LPCNetB200Batch *b, const float *d_feat, long long strea
     if (frame_stride < NB_FEAT) { set_error("feature_stride must be >= 20"); return -1; }
     const int n = b->n;
     const long long pcm_stride = (long long)nframes * spf;
-    float total_ms = 0; int launches = 0;
+    int launches = 0;
+    b->kev_used = 0;
     for (int c0 = 0; c0 < nframes; c0 += CHUNK) {
         const int nf = nframes - c0 < CHUNK ? nframes - c0 : CHUNK;
         launch_frame_network(b->model, b->fs, d_feat + (size_t)c0 * frame_stride, stream_stride, frame_stride, n, nf,
@@ -194,20 +199,19 @@ static int synth_device(LPCNetB200Batch *b, const float *d_feat, long long strea
             p.pcm = d_pcm + (size_t)(c0 + silent) * spf;
             p.pcm_stream_stride = pcm_stride;
             p.n_streams = n; p.nframes = nf - silent; p.spf = spf;
-            if (time_it) CK(cudaEventRecord(b->ev0, st));
+            if (time_it) {      // event pair around the launch, resolved lazily by lpcnet_b200_batch_last_sample_kernel_ms (no sync here)
+                while ((int)b->kev->size() < b->kev_used + 2) { cudaEvent_t e; CK(cudaEventCreate(&e)); b->kev->push_back(e); }
+                CK(cudaEventRecord((*b->kev)[b->kev_used], st));
+            }
             CK(launch_sample_kernel(p, st));
             launches += 1;
-            if (time_it) {
-                CK(cudaEventRecord(b->ev1, st));
-                CK(cudaEventSynchronize(b->ev1));
-                float ms = 0; CK(cudaEventElapsedTime(&ms, b->ev0, b->ev1)); total_ms += ms;
-            }
+            if (time_it) { CK(cudaEventRecord((*b->kev)[b->kev_used + 1], st)); b->kev_used += 2; }
         }
         b->frame_count += nf;
         if (b->frame_count > 1000) b->frame_count = 1000;
     }
     CK(cudaGetLastError());
-    b->last_ms = total_ms; b->last_launches = launches;
+    b->last_launches = launches;
     return 0;
 }
 
@@ -282,8 +286,61 @@ float lpcnet_b200_batch_last_sample_kernel_ms(const LPCNetB200Batch *b, int *lau
 {
     if (!b) return 0.f;
     if (launches) *launches = b->last_launches;
-    return b->last_ms;
+    float total = 0.f;
+    for (int i = 0; i + 1 < b->kev_used; i += 2) {
+        float ms = 0.f;
+        if (cudaEventSynchronize((*b->kev)[i + 1]) != cudaSuccess) return -1.f;
+        if (cudaEventElapsedTime(&ms, (*b->kev)[i], (*b->kev)[i + 1]) != cudaSuccess) return -1.f;
+        total += ms;
+    }
+    return total;
 }
+
+// CUDA-event stopwatch on the engine's own stream (the stream every engine kernel is launched on when the caller
+// passes cuda_stream == NULL): start records an event, stop records another, synchronises and returns the ms between.
+int lpcnet_b200_batch_timer_start(LPCNetB200Batch *b)
+{
+    if (!b) { set_error("null batch"); return -1; }
+    CK(cudaSetDevice(b->device));
+    CK(cudaEventRecord(b->ev0, b->stream));
+    return 0;
+}
+float lpcnet_b200_batch_timer_stop(LPCNetB200Batch *b)
+{
+    if (!b) return -1.f;
+    float ms = 0.f;
+    if (cudaEventRecord(b->ev1, b->stream) != cudaSuccess || cudaEventSynchronize(b->ev1) != cudaSuccess ||
+        cudaEventElapsedTime(&ms, b->ev0, b->ev1) != cudaSuccess) { set_error("timer: %s", cudaGetErrorString(cudaGetLastError())); return -1.f; }
+    return ms;
+}
+// Evict L2 between timed iterations: overwrite a scratch buffer larger than the 126 MB L2 on the engine's stream.
+int lpcnet_b200_batch_flush_l2(LPCNetB200Batch *b)
+{
+    if (!b) { set_error("null batch"); return -1; }
+    static void *scratch = nullptr; static int scratch_dev = -1;
+    const size_t bytes = 256u << 20;
+    CK(cudaSetDevice(b->device));
+    if (!scratch || scratch_dev != b->device) { CK(cudaMalloc(&scratch, bytes)); scratch_dev = b->device; }
+    CK(cudaMemsetAsync(scratch, 0x5a, bytes, b->stream));
+    return 0;
+}
+int lpcnet_b200_batch_sync(LPCNetB200Batch *b)
+{
+    if (!b) { set_error("null batch"); return -1; }
+    CK(cudaSetDevice(b->device));
+    CK(cudaStreamSynchronize(b->stream));
+    return 0;
+}
+// Device memory helpers so that a plain-C / ctypes caller can keep inputs resident in HBM (no torch needed).
+void *lpcnet_b200_device_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { set_error("cudaMalloc(%zu) failed", bytes); return nullptr; }
+    return p;
+}
+void lpcnet_b200_device_free(void *p) { if (p) cudaFree(p); }
+int lpcnet_b200_memcpy_h2d(void *dst, const void *src, size_t bytes) { CK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice)); return 0; }
+int lpcnet_b200_memcpy_d2h(void *dst, const void *src, size_t bytes) { CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost)); return 0; }
 
 int lpcnet_b200_batch_algorithmic_bytes(const LPCNetB200Batch *b, long *total, long *sparse_gemv)
 {
@@ -307,20 +364,9 @@ int lpcnet_b200_batch_get_state(LPCNetB200Batch *b, int s, float *gru_a, float *
     return 0;
 }
 
-int lpcnet_b200_batch_get_frame_taps(LPCNetB200Batch *b, int s, float *ga, float *gb, float *lpc)
-{
-    // conditioning of the LAST frame of the most recent chunk; lpc = the weighted LPC that frame used
-    if (!b || s < 0 || s >= b->n) { set_error("bad stream index"); return -1; }
-    CK(cudaSetDevice(b->device));
-    CK(cudaStreamSynchronize(b->stream));
-    (void)ga; (void)gb; (void)lpc;
-    set_error("frame taps: use lpcnet_b200_debug_frame_network");
-    return -1;
-}
-
 // Test hook: run ONLY the frame-rate kernels on host features for a fresh batch state and return all taps.
 // ga [n][nframes][1152], gb [n][nframes][48], lpc [n][nframes][16] (gamma-weighted, i.e. what the sample loop uses)
-LPCNET_EXPORT int lpcnet_b200_debug_frame_network(LPCNetB200Batch *b, const float *features, int nframes, int feature_stride,
+int lpcnet_b200_debug_frame_network(LPCNetB200Batch *b, const float *features, int nframes, int feature_stride,
                                                   float *ga, float *gb, float *lpc)
 {
     if (!b) { set_error("null batch"); return -1; }
@@ -349,7 +395,7 @@ LPCNET_EXPORT int lpcnet_b200_debug_frame_network(LPCNetB200Batch *b, const floa
 
 // Test hook (host only, no CUDA): the shared-memory image and its run-time layout words
 // layout[8] = {wA, metaA, wB, metaB, image_bytes, total_bytes, nblkA_padded, nblkB_padded}; also returns SM_IMAGE in layout[8].
-LPCNET_EXPORT int lpcnet_b200_debug_image(const unsigned char *blob, int len, unsigned char *out, size_t cap, uint32_t *layout)
+int lpcnet_b200_debug_image(const unsigned char *blob, int len, unsigned char *out, size_t cap, uint32_t *layout)
 {
     SmemLayout L;
     int r = debug_build_image(blob, len, out, cap, &L);
@@ -362,12 +408,12 @@ LPCNET_EXPORT int lpcnet_b200_debug_image(const unsigned char *blob, int len, un
 }
 
 // Pinned host memory helpers for callers that want true async H2D/D2H (the benchmark's e2e leg).
-LPCNET_EXPORT void *lpcnet_b200_host_alloc(size_t bytes)
+void *lpcnet_b200_host_alloc(size_t bytes)
 {
     void *p = nullptr;
     if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { set_error("cudaHostAlloc(%zu) failed", bytes); return nullptr; }
     return p;
 }
-LPCNET_EXPORT void lpcnet_b200_host_free(void *p) { if (p) cudaFreeHost(p); }
+void lpcnet_b200_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 }  // extern "C"

@@ -151,7 +151,7 @@ def test_drop_in_single_stream_api(eng):
     cb = H.codebooks()
     L.lpcnet_b200_set_default_codebooks(cb.ctypes.data, cb.size)
     net = eng.LPCNet()
-    f = make_feature_batch([1], 12)[0]
+    f = make_feature_batch([1], 40)[0][:12]          # same generator call as the golden (features depend on the length)
     out = np.concatenate([net.synthesize(f[t]) for t in range(12)])
     np.testing.assert_array_equal(out, gold[1, :12 * 160])
     net.reset()
@@ -161,7 +161,7 @@ def test_drop_in_single_stream_api(eng):
     net.close()
     gdec = np.load(os.path.join(H.GOLDEN, "decode_A.npz"))["pcm"]
     dec = eng.LPCNetDecoder()
-    pk = make_packets(2, 3)
+    pk = make_packets(2, 6)[:3]
     out = np.concatenate([dec.decode(pk[t]) for t in range(3)])
     np.testing.assert_array_equal(out, gdec[2, :3 * 640])
     dec.close()

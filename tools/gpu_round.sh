@@ -1,0 +1,22 @@
+#!/bin/bash
+# One GPU session: parity tests, smoke, benchmark, ncu launch list, ncu full capture of the per-sample kernel.
+# usage: tools/gpu_round.sh <tag> [skip-tests]
+TAG=${1:-r01}
+mkdir -p gpurun_out
+set -x
+make -C oracle port >/dev/null
+if [ "$2" != "skip-tests" ]; then
+  timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+fi
+timeout 600 python bench.py --gpus 1 --steps 6 --warmup 3 > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err; tail -c 3000 gpurun_out/bench_${TAG}.json; tail -5 gpurun_out/bench_${TAG}.err
+timeout 600 python bench.py --impl reference --gpus 1 --steps 3 --warmup 1 > gpurun_out/bench_ref_${TAG}.json 2>/dev/null; tail -c 1500 gpurun_out/bench_ref_${TAG}.json
+# every launch with its device time (cold-cache, serialised: compare shares)
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_${TAG}.csv \
+    python bench.py --gpus 1 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch_${TAG}.log 2>&1
+tail -3 gpurun_out/ncu_launch_${TAG}.log
+# the per-sample kernel, full set, source view
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:lpcnet_sample -s 4 -c 1 -o gpurun_out/prof_${TAG} -f \
+    python bench.py --gpus 1 --steps 1 --warmup 3 --frames 3 --no-cpu-baseline > gpurun_out/ncu_full_${TAG}.log 2>&1
+tail -3 gpurun_out/ncu_full_${TAG}.log
+ls -la gpurun_out
