@@ -195,7 +195,12 @@ def main():
     feats = features_for(n, F, first_stream=64 * rank)
     fbytes, pbytes = feats.nbytes, n * F * 160 * 2
     d_feat = L.lpcnet_b200_device_alloc(fbytes)
-    d_pcm = L.lpcnet_b200_device_alloc(pbytes)
+    if dist is not None:                                      # under torchrun the PCM buffer is a torch tensor so NCCL can gather it
+        import torch
+        pcm_t = torch.empty((n, F * 160), dtype=torch.int16, device="cuda")
+        d_pcm = pcm_t.data_ptr()
+    else:
+        d_pcm = L.lpcnet_b200_device_alloc(pbytes)
     assert d_feat and d_pcm
     L.lpcnet_b200_memcpy_h2d(d_feat, feats.ctypes.data, fbytes)
     # pinned host buffers for the e2e leg
@@ -256,14 +261,15 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_s, e2e_s = float(t[0]), float(t[1])
         # the one real exchange of the path: gather the PCM shards to rank 0 over NCCL (timed separately, device events)
-        pcm_t = torch.empty(n * F * 160, dtype=torch.int16, device="cuda")
-        outs = [torch.empty_like(pcm_t) for _ in range(world)] if rank == 0 else None
+        from lpcnet_b200.sharding import gather_pcm
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         dist.barrier(); torch.cuda.synchronize()
         e0.record()
-        dist.gather(pcm_t, outs, dst=0)
+        full = gather_pcm(pcm_t, n * world, dist, dst=0)
         e1.record(); torch.cuda.synchronize()
         gather_ms = e0.elapsed_time(e1)
+        if rank == 0:
+            assert full.shape == (n * world, F * 160)
     else:
         gather_ms = None
 
@@ -304,7 +310,9 @@ def main():
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
         print(json.dumps(out), flush=True)
 
-    L.lpcnet_b200_device_free(d_feat); L.lpcnet_b200_device_free(d_pcm)
+    L.lpcnet_b200_device_free(d_feat)
+    if dist is None:
+        L.lpcnet_b200_device_free(d_pcm)
     L.lpcnet_b200_host_free(h_feat_p); L.lpcnet_b200_host_free(h_pcm_p)
     batch.close()
     if dist is not None:

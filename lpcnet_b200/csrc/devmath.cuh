@@ -18,9 +18,16 @@ __device__ __forceinline__ float rcp_emul(float x, const uint16_t *__restrict__ 
     uint32_t t = 0x3f000000u + ((uint32_t)tab16[(u >> 12) & 0x7FFu] << 11);
     return __uint_as_float(t - ((u & 0x7F800000u) - 0x3F800000u));
 }
+// same with the shared-memory table of the per-sample kernel: tab32[k] = T[k] + 0x3f800000 (no re-assembly needed)
+__device__ __forceinline__ float rcp_emul(float x, const uint32_t *__restrict__ tab32)
+{
+    uint32_t u = __float_as_uint(x);
+    return __uint_as_float(tab32[(u >> 12) & 0x7FFu] - (u & 0x7F800000u));
+}
 
 // tanh8_approx (vec_avx.h:393-411)
-__device__ __forceinline__ float tanh_approx(float x, const uint16_t *__restrict__ tab16)
+template <typename TAB>
+__device__ __forceinline__ float tanh_approx(float x, const TAB *__restrict__ tab16)
 {
     const float N0 = 952.52801514f, N1 = 96.39235687f, N2 = 0.60863042f;
     const float D0 = 952.72399902f, D1 = 413.36801147f, D2 = 11.88600922f;
@@ -34,7 +41,8 @@ __device__ __forceinline__ float tanh_approx(float x, const uint16_t *__restrict
 }
 
 // sigmoid8_approx (vec_avx.h:421-440)
-__device__ __forceinline__ float sigmoid_approx(float x, const uint16_t *__restrict__ tab16)
+template <typename TAB>
+__device__ __forceinline__ float sigmoid_approx(float x, const TAB *__restrict__ tab16)
 {
     const float N0 = 238.13200378f, N1 = 6.02452230f, N2 = 0.00950985f;
     const float D0 = 952.72399902f, D1 = 103.34200287f, D2 = 0.74287558f;

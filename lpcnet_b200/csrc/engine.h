@@ -38,17 +38,22 @@ constexpr int NWB = 12;                      // warps used by the GRU_B input GE
 // [SM_IMAGE, SM_IMAGE + image_bytes) is copied verbatim from the global "SMEM image" built at model-load time
 // (TMA bulk copies); [0, SM_IMAGE) is the mutable working set.
 constexpr uint32_t al128(uint32_t x) { return (x + 127u) & ~127u; }
+constexpr int GIN_ROW = 388;                                       // floats per stream in the gather tile: 384 + 4 pad => row stride 1552 B
+                                                                   // (= 16 mod 128): per-lane LDS.128 of a quarter-warp hit 8 disjoint 4-bank groups
 constexpr uint32_t SM_XS    = 0;                                   // 2 x XS_BYTES: double-buffered quantised GRU_A state
 constexpr uint32_t SM_XB    = SM_XS + 2 * XS_BYTES;                // 2 x [4 words][32]: quantised GRU_B state
-constexpr uint32_t SM_ACCB  = SM_XB + 2 * 4 * 32 * 4;              // int32 [2][48][32]: K-half partial sums of the GRU_B input GEMV
-constexpr uint32_t SM_HBS   = SM_ACCB + 2 * 3 * NB * 32 * 4;       // float [16][32]: GRU_B state for the sampler warp
-constexpr uint32_t SM_IDX   = SM_HBS + NB * 32 * 4;                // int32 [3][32]: last_sig_ulaw, pred_ulaw, last_exc
+constexpr uint32_t SM_GIN   = SM_XB + 2 * 4 * 32 * 4;              // float [32 streams][GIN_ROW]: cond + 3 embedding rows of ONE gate (z, r or h)
+constexpr uint32_t SM_ACCB  = SM_GIN;                              // int32 [2][48][32] K-half partial sums of the GRU_B input GEMV   } alias the gather tile:
+constexpr uint32_t SM_HBS   = SM_ACCB + 2 * 3 * NB * 32 * 4;       // float [16][32] GRU_B state for the sampler warp                  } live only between
+                                                                   //                                                                 } GRU_A and the next gather
+constexpr uint32_t SM_IDX   = SM_GIN + 32 * GIN_ROW * 4;           // int32 [3][32]: last_sig_ulaw, pred_ulaw, last_exc
 constexpr uint32_t SM_PCM   = SM_IDX + 3 * 32 * 4;                 // int16 [32][PCM_ROW]
 constexpr uint32_t SM_MBAR  = al128(SM_PCM + 32 * PCM_ROW * 2);    // 8-byte mbarrier of the image copy
 constexpr uint32_t SM_IMAGE = SM_MBAR + 128;
+static_assert(SM_HBS + NB * 32 * 4 <= SM_IDX, "GRU_B scratch must fit inside the gather tile it aliases");
 // image, fixed part (offsets relative to SM_IMAGE)
-constexpr uint32_t IM_RCP   = 0;                                   // u16 [2048] RCPPS table ((T-0x3f000000)>>11)
-constexpr uint32_t IM_LOGIT = IM_RCP + 2048 * 2;                   // float [256] sampling_logit_table
+constexpr uint32_t IM_RCP   = 0;                                   // u32 [2048] RCPPS table (T[k] + 0x3f800000: one IADD3 rebuilds the result)
+constexpr uint32_t IM_LOGIT = IM_RCP + 2048 * 4;                   // float [256] sampling_logit_table
 constexpr uint32_t IM_U2L   = IM_LOGIT + 256 * 4;                  // float [256] ulaw2lin
 constexpr uint32_t IM_FCW   = IM_U2L + 256 * 4;                    // float [256][FCW_ROW] dual_fc weights
 constexpr uint32_t IM_FCB   = IM_FCW + 256 * FCW_ROW * 4;          // float [2][256]

@@ -233,7 +233,10 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
         for (int i = 0; i < 6 * NB; i++) pb[i] = gb_subias[i];          // nnet.c:346-360 (USE_SU_BIAS)
         (void)gb_bias; (void)ga_bias;
     }
-    memcpy(&img[IM_RCP], kRcpTable, sizeof(kRcpTable));
+    {
+        uint32_t *r32 = reinterpret_cast<uint32_t *>(&img[IM_RCP]);
+        for (int k = 0; k < 2048; k++) r32[k] = 0x3f000000u + ((uint32_t)kRcpTable[k] << 11) + 0x3f800000u;
+    }
     {
         float *lg = reinterpret_cast<float *>(&img[IM_LOGIT]);
         for (int i = 0; i < 256; i++) {                                   // lpcnet.c:188-191 (host libm, double log)

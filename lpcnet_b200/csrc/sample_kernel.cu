@@ -26,7 +26,7 @@ namespace lpcnet_b200 {
 
 namespace {
 
-enum { BAR_IDX = 1, BAR_X = 2, BAR_ACCB = 3, BAR_HB = 4 };
+enum { BAR_IDX = 1, BAR_X = 2, BAR_ACCB = 3, BAR_HB = 4, BAR_GF = 5, BAR_GE = 6 };   // GF: gather tile full, GE: tile free again
 
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -60,22 +60,42 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 
-// 8 gathered conditioning inputs of one (gate, neuron group): cond + E_sig[a] + E_pred[b] + E_exc[c], left to right
-__device__ __forceinline__ void gather8(float g[8], const float *__restrict__ c, const float *__restrict__ e0,
-                                        const float *__restrict__ e1, const float *__restrict__ e2, int off)
+// Cooperative gather of ONE gate's GRU_A input for the CTA's 32 streams (compute_gru_a_input, nnet.c:484-491):
+//   G[s][k] = ((cond[s][k] + E_sig[a_s][k]) + E_pred[b_s][k]) + E_exc[c_s][k],   k in [0, 384)
+// Warp w serves streams 2w and 2w+1; its 32 lanes read consecutive float4 of the four rows (512 B contiguous per
+// instruction = 4 L1 lines, instead of 32 lines for a per-lane gather) and store the sums transposed-by-row into
+// the shared tile, from which every lane (== stream) later reads its own 8-neuron slices conflict-free.
+__device__ __forceinline__ void gather_gate(float *__restrict__ G, const float *__restrict__ cond_f, int n, int cta_s0,
+                                            const float *__restrict__ emb_sig, const float *__restrict__ emb_pred,
+                                            const float *__restrict__ emb_exc, const int *__restrict__ idx_s,
+                                            int gate, int warp, int lane)
 {
-    const float4 c0 = ldg4(c + off), c1 = ldg4(c + off + 4);
-    const float4 s0 = ldg4(e0 + off), s1 = ldg4(e0 + off + 4);
-    const float4 p0 = ldg4(e1 + off), p1 = ldg4(e1 + off + 4);
-    const float4 x0 = ldg4(e2 + off), x1 = ldg4(e2 + off + 4);
-    g[0] = __fadd_rn(__fadd_rn(__fadd_rn(c0.x, s0.x), p0.x), x0.x);
-    g[1] = __fadd_rn(__fadd_rn(__fadd_rn(c0.y, s0.y), p0.y), x0.y);
-    g[2] = __fadd_rn(__fadd_rn(__fadd_rn(c0.z, s0.z), p0.z), x0.z);
-    g[3] = __fadd_rn(__fadd_rn(__fadd_rn(c0.w, s0.w), p0.w), x0.w);
-    g[4] = __fadd_rn(__fadd_rn(__fadd_rn(c1.x, s1.x), p1.x), x1.x);
-    g[5] = __fadd_rn(__fadd_rn(__fadd_rn(c1.y, s1.y), p1.y), x1.y);
-    g[6] = __fadd_rn(__fadd_rn(__fadd_rn(c1.z, s1.z), p1.z), x1.z);
-    g[7] = __fadd_rn(__fadd_rn(__fadd_rn(c1.w, s1.w), p1.w), x1.w);
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int ss = 2 * warp + k;
+        const int sg = min(cta_s0 + ss, n - 1);
+        const float *c = cond_f + (size_t)sg * (3 * NA) + gate * NA + lane * 4;
+        const float *e0 = emb_sig + (size_t)idx_s[ss] * (3 * NA) + gate * NA + lane * 4;
+        const float *e1 = emb_pred + (size_t)idx_s[32 + ss] * (3 * NA) + gate * NA + lane * 4;
+        const float *e2 = emb_exc + (size_t)idx_s[64 + ss] * (3 * NA) + gate * NA + lane * 4;
+        float *g = G + ss * GIN_ROW + lane * 4;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const float4 a = ldg4(c + 128 * j), b = ldg4(e0 + 128 * j), d = ldg4(e1 + 128 * j), e = ldg4(e2 + 128 * j);
+            float4 r;
+            r.x = __fadd_rn(__fadd_rn(__fadd_rn(a.x, b.x), d.x), e.x);
+            r.y = __fadd_rn(__fadd_rn(__fadd_rn(a.y, b.y), d.y), e.y);
+            r.z = __fadd_rn(__fadd_rn(__fadd_rn(a.z, b.z), d.z), e.z);
+            r.w = __fadd_rn(__fadd_rn(__fadd_rn(a.w, b.w), d.w), e.w);
+            *reinterpret_cast<float4 *>(g + 128 * j) = r;
+        }
+    }
+}
+__device__ __forceinline__ void load_gin(float gin[8], const float *__restrict__ G, int lane, int g)
+{
+    const float4 a = *reinterpret_cast<const float4 *>(G + lane * GIN_ROW + 8 * g);
+    const float4 b = *reinterpret_cast<const float4 *>(G + lane * GIN_ROW + 8 * g + 4);
+    gin[0] = a.x; gin[1] = a.y; gin[2] = a.z; gin[3] = a.w; gin[4] = b.x; gin[5] = b.y; gin[6] = b.z; gin[7] = b.w;
 }
 
 // acc[r] += sum over `nb` (even) 8x4 blocks; weights broadcast from smem, activations one word per lane
@@ -130,12 +150,14 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
         }
     }
 
-    const uint16_t *rcp = reinterpret_cast<const uint16_t *>(smem + SM_IMAGE + IM_RCP);
+    const uint32_t *rcp = reinterpret_cast<const uint32_t *>(smem + SM_IMAGE + IM_RCP);
     uint8_t *xs = smem + SM_XS;
     uint32_t *xbw = reinterpret_cast<uint32_t *>(smem + SM_XB);
     int *accB = reinterpret_cast<int *>(smem + SM_ACCB);
     float *hBs = reinterpret_cast<float *>(smem + SM_HBS);
     int *idx_s = reinterpret_cast<int *>(smem + SM_IDX);
+    float *gin_tile = reinterpret_cast<float *>(smem + SM_GIN);
+    const int cta_s0 = blockIdx.x * STREAMS_PER_CTA;
     const int spf = P.spf;
 
     if (warp < NWC) {
@@ -174,42 +196,59 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
 
         int step = 0;
         for (int f = 0; f < P.nframes; f++) {
-            const float *condA = P.condA + ((size_t)f * n + s) * (3 * NA);
+            const float *condA_f = P.condA + (size_t)f * n * (3 * NA);
             const float *condBp = P.condB + ((size_t)f * n + s) * (3 * NB);
             const float cbz = __ldg(condBp + jb), cbr = __ldg(condBp + NB + jb), cbh = __ldg(condBp + 2 * NB + jb);
             for (int t = 0; t < spf; t++, step++) {
                 const int cur = step & 1, nxt = cur ^ 1;
                 bar_sync(BAR_IDX, SAMPLE_THREADS);                       // indices of this step are in idx_s
-                const float *e_sig = P.emb_sig + (size_t)idx_s[lane] * (3 * NA);
-                const float *e_pred = P.emb_pred + (size_t)idx_s[32 + lane] * (3 * NA);
-                const float *e_exc = P.emb_exc + (size_t)idx_s[64 + lane] * (3 * NA);
                 const uint8_t *xs_cur = xs + cur * XS_BYTES + lane * 4;
                 uint32_t *xs_nxt = reinterpret_cast<uint32_t *>(xs + nxt * XS_BYTES);
+                float rg[GPW][8];                                        // reset gate, then (in place) the candidate h~
 
-                // ---------------- GRU_A: the neuron groups this warp owns ----------------
+                // ---------------- GRU_A, gate by gate: cooperative gather -> tile -> owners consume ----------------
+                // reset gate r: rec = bias + diag*h + gin (nnet.c:431-435), + int8 GEMV, sigmoid
+                gather_gate(gin_tile, condA_f, n, cta_s0, P.emb_sig, P.emb_pred, P.emb_exc, idx_s, 1, warp, lane);
+                bar_sync(BAR_GF, NWC * 32);
+#pragma unroll
+                for (int sl = 0; sl < GPW; sl++) {
+                    const float *par = parA + sl * 3 * 16;
+                    const uint32_t *dir = dirA + sl * 3 * 2;
+                    float gin[8]; int acc[8];
+                    load_gin(gin, gin_tile, lane, grp[sl]);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) acc[i] = acc_init(__fadd_rn(__fadd_rn(par[16 + i], __fmul_rn(par[24 + i], h[sl][i])), gin[i]));
+                    gemv_blocks(acc, wA + (size_t)dir[2] * 32, metaA + dir[2], (int)dir[3], xs_cur);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) rg[sl][i] = sigmoid_approx(acc_finish(acc[i]), rcp);
+                }
+                bar_sync(BAR_GE, NWC * 32);
+                // candidate: rec = bias + diag*h (no input term, nnet.c:436-440); h~ = tanh(rec*r + gin_h) (:443-445)
+                gather_gate(gin_tile, condA_f, n, cta_s0, P.emb_sig, P.emb_pred, P.emb_exc, idx_s, 2, warp, lane);
+                bar_sync(BAR_GF, NWC * 32);
+#pragma unroll
+                for (int sl = 0; sl < GPW; sl++) {
+                    const float *par = parA + sl * 3 * 16;
+                    const uint32_t *dir = dirA + sl * 3 * 2;
+                    float gin[8]; int acc[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) acc[i] = acc_init(__fadd_rn(par[32 + i], __fmul_rn(par[40 + i], h[sl][i])));
+                    gemv_blocks(acc, wA + (size_t)dir[4] * 32, metaA + dir[4], (int)dir[5], xs_cur);
+                    load_gin(gin, gin_tile, lane, grp[sl]);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) rg[sl][i] = tanh_approx(__fadd_rn(__fmul_rn(acc_finish(acc[i]), rg[sl][i]), gin[i]), rcp);
+                }
+                bar_sync(BAR_GE, NWC * 32);
+                // update gate z, then h <- z*h + (1-z)*h~ (nnet.c:446-447) and the new quantised state
+                gather_gate(gin_tile, condA_f, n, cta_s0, P.emb_sig, P.emb_pred, P.emb_exc, idx_s, 0, warp, lane);
+                bar_sync(BAR_GF, NWC * 32);
 #pragma unroll
                 for (int sl = 0; sl < GPW; sl++) {
                     const int g = grp[sl];
                     const float *par = parA + sl * 3 * 16;
                     const uint32_t *dir = dirA + sl * 3 * 2;
-                    float gin[8], r[8], ht[8];
-                    int acc[8];
-                    // reset gate r: rec = bias + diag*h + gin (nnet.c:431-435), then the int8 GEMV, then sigmoid
-                    gather8(gin, condA, e_sig, e_pred, e_exc, NA + 8 * g);
-#pragma unroll
-                    for (int i = 0; i < 8; i++) acc[i] = acc_init(__fadd_rn(__fadd_rn(par[16 + i], __fmul_rn(par[24 + i], h[sl][i])), gin[i]));
-                    gemv_blocks(acc, wA + (size_t)dir[2] * 32, metaA + dir[2], (int)dir[3], xs_cur);
-#pragma unroll
-                    for (int i = 0; i < 8; i++) r[i] = sigmoid_approx(acc_finish(acc[i]), rcp);
-                    // candidate: rec = bias + diag*h (no input term, nnet.c:436-440); h~ = tanh(rec*r + gin_h) (:443-445)
-                    gather8(gin, condA, e_sig, e_pred, e_exc, 2 * NA + 8 * g);
-#pragma unroll
-                    for (int i = 0; i < 8; i++) acc[i] = acc_init(__fadd_rn(par[32 + i], __fmul_rn(par[40 + i], h[sl][i])));
-                    gemv_blocks(acc, wA + (size_t)dir[4] * 32, metaA + dir[4], (int)dir[5], xs_cur);
-#pragma unroll
-                    for (int i = 0; i < 8; i++) ht[i] = tanh_approx(__fadd_rn(__fmul_rn(acc_finish(acc[i]), r[i]), gin[i]), rcp);
-                    // update gate z (independent of r and h~; evaluated last to keep fewer values live)
-                    gather8(gin, condA, e_sig, e_pred, e_exc, 8 * g);
+                    float gin[8]; int acc[8];
+                    load_gin(gin, gin_tile, lane, g);
 #pragma unroll
                     for (int i = 0; i < 8; i++) acc[i] = acc_init(__fadd_rn(__fadd_rn(par[i], __fmul_rn(par[8 + i], h[sl][i])), gin[i]));
                     gemv_blocks(acc, wA + (size_t)dir[0] * 32, metaA + dir[0], (int)dir[1], xs_cur);
@@ -217,7 +256,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
                         const float z = sigmoid_approx(acc_finish(acc[i]), rcp);
-                        const float hn = __fadd_rn(__fmul_rn(z, h[sl][i]), __fmul_rn(__fsub_rn(1.f, z), ht[i]));   // nnet.c:446-447
+                        const float hn = __fadd_rn(__fmul_rn(z, h[sl][i]), __fmul_rn(__fsub_rn(1.f, z), rg[sl][i]));
                         h[sl][i] = hn;
                         q[i] = quant_u8(hn);
                     }

@@ -185,3 +185,28 @@ def test_full_width_properties(eng, n):
     b.reset()
     np.testing.assert_array_equal(b.synthesize(f), got)
     b.close()
+
+
+def test_untouched_reference_cli_links_and_runs(eng, tmp_path):
+    """The reference's own src/lpcnet_demo.c, compiled against the reference's own include/lpcnet.h and linked with
+    liblpcnet_b200.so (oracle/Makefile target `demo`, built where /root/reference exists), run exactly like the
+    reference CLI: `lpcnet_demo -synthesis features.f32 out.pcm` and `-decode packets out.pcm`."""
+    import subprocess
+    exe = os.path.join(H.ORACLE, "_ref", "lpcnet_demo_b200")
+    if not os.path.exists(exe):
+        pytest.skip("drop-in CLI was not prebuilt (needs /root/reference at build time)")
+    gold = np.load(os.path.join(H.GOLDEN, "synth_A.npz"))["pcm"]
+    f36 = np.zeros((40, 36), np.float32)
+    f36[:, :20] = make_feature_batch([0], 40)[0]
+    (tmp_path / "feat.f32").write_bytes(f36.tobytes())
+    os.symlink(os.path.join(H.gen_dir(), "model_int8.bin"), tmp_path / "weights_blob.bin")   # lpcnet_demo.c:160 loads this name
+    env = dict(os.environ, LPCNET_B200_LPC_GAMMA=str(H.LPC_GAMMA), LPCNET_B200_MODEL=os.path.join(H.gen_dir(), "model_int8.bin"),
+               LPCNET_B200_CODEBOOKS=os.path.join(H.gen_dir(), "codebooks.bin"))
+    subprocess.run([exe, "-synthesis", "feat.f32", "out.pcm"], cwd=tmp_path, env=env, check=True, timeout=300)
+    out = np.frombuffer((tmp_path / "out.pcm").read_bytes(), dtype=np.int16)
+    np.testing.assert_array_equal(out, gold[0])
+    gdec = np.load(os.path.join(H.GOLDEN, "decode_A.npz"))["pcm"]
+    (tmp_path / "pk.bin").write_bytes(make_packets(1, 6).tobytes())
+    subprocess.run([exe, "-decode", "pk.bin", "dec.pcm"], cwd=tmp_path, env=env, check=True, timeout=300)
+    out = np.frombuffer((tmp_path / "dec.pcm").read_bytes(), dtype=np.int16)
+    np.testing.assert_array_equal(out, gdec[1])
