@@ -104,7 +104,7 @@ LPCNET_EXPORT int lpcnet_b200_batch_get_state(LPCNetB200Batch *b, int s, float *
 LPCNET_EXPORT int lpcnet_b200_debug_frame_network(LPCNetB200Batch *b, const float *features, int nframes,
                                                   int feature_stride, float *ga, float *gb, float *lpc);
 /* Test hook (host only, no CUDA): build the per-sample kernel's shared-memory image for a blob.  Returns the
- * image size or <0; layout[16] receives the offsets documented in lpcnet_b200/csrc/batch_api.cu. */
+ * image size or <0; layout[24] receives the offsets documented in lpcnet_b200/csrc/batch_api.cu. */
 LPCNET_EXPORT int lpcnet_b200_debug_image(const unsigned char *blob, int len, unsigned char *out, size_t cap,
                                           uint32_t *layout);
 

@@ -190,7 +190,7 @@ static int synth_device(LPCNetB200Batch *b, const float *d_feat, long long strea
         if (nf > silent) {
             SampleParams p;
             p.L = b->model.L; p.image = b->model.image;
-            p.emb_sig = b->model.emb_sig; p.emb_pred = b->model.emb_pred; p.emb_exc = b->model.emb_exc;
+            p.emb_sig = b->model.emb_sig; p.emb_pred = b->model.emb_pred; p.emb_exc = b->model.emb_exc; p.fcw = b->model.fcw;
             p.condA = b->condA + (size_t)silent * n * 3 * NA;
             p.condB = b->condB + (size_t)silent * n * 3 * NB;
             p.lpc_raw = b->lpc_raw + (size_t)silent * n * LPC_ORDER;
@@ -403,7 +403,7 @@ int lpcnet_b200_debug_image(const unsigned char *blob, int len, unsigned char *o
     layout[0] = L.wA; layout[1] = L.metaA; layout[2] = L.wB; layout[3] = L.metaB; layout[4] = L.image_bytes; layout[5] = L.total_bytes;
     layout[6] = L.nblkA_padded; layout[7] = L.nblkB_padded; layout[8] = SM_IMAGE;
     layout[9] = IM_PARA; layout[10] = IM_DIRA; layout[11] = IM_GRPA; layout[12] = IM_DIRB; layout[13] = IM_WBREC; layout[14] = IM_PARB;
-    layout[15] = IM_FCW;
+    layout[15] = IM_FCW; layout[16] = NWC; layout[17] = GPW; layout[18] = FCW_SMEM_NODES; layout[19] = KPARTS;
     return r;
 }
 

@@ -21,16 +21,31 @@ constexpr int FEATURES_DELAY = 2;
 constexpr int WINDOW_SIZE = 320;
 constexpr int FREQ_SIZE = 161;
 
-// ---- per-sample kernel geometry ----
+// ---- per-sample kernel geometry (warp-specialised CTA) ----
 constexpr int STREAMS_PER_CTA = 32;          // lane == stream
-constexpr int NWC = 16;                      // compute warps: each owns NGRP/NWC neuron groups of GRU_A and one GRU_B neuron
+#ifndef LPCNET_NWC
+#define LPCNET_NWC 16
+#endif
+constexpr int NWC = LPCNET_NWC;              // compute warps (12, 16 or 24): each owns NGRP/NWC neuron groups of GRU_A, a (row group, K part) of the
+                                             // GRU_B input GEMV and up to ceil(16/NWC) GRU_B neurons.  24 warps x 2 groups keeps the per-thread
+                                             // working set small (h, S_h, S_z = 48 registers) so that 7 warps per scheduler hide the LDS latency
+#ifndef LPCNET_NWP
+#define LPCNET_NWP 7
+#endif
+constexpr int NWP = LPCNET_NWP;              // producer warps: cooperative gather of the GRU_A input rows.  The gather is latency-bound (L2 hits, ~1k cycles
+                                             // under load), so what matters is loads in flight: NWP warps x (registers/4) LDG.128 each
 constexpr int NGRP = NA / 8;                 // 48 groups of 8 neurons (one 8-row block group per gate)
-constexpr int GPW = NGRP / NWC;              // 3
-constexpr int SAMPLE_THREADS = (NWC + 1) * 32;   // + 1 sampler warp (tree sampler, LPC filter, u-law, de-emphasis)
+constexpr int GPW = NGRP / NWC;              // neuron groups per compute warp
+static_assert(NGRP % NWC == 0, "compute warps must divide the 48 neuron groups");
+constexpr int SAMPLE_THREADS = (NWC + NWP + 1) * 32;   // + 1 sampler warp (tree sampler, LPC filter, u-law, de-emphasis)
 constexpr int XS_BYTES = (NA / 4) * 32 * 4;  // quantised GRU_A state of 32 streams: [96 words][32 lanes]
-constexpr int FCW_ROW = 33;                  // dual_fc rows padded 32->33 floats (bank-conflict-free per-lane row gather)
-constexpr int PCM_ROW = 162;                 // int16 per stream in the PCM staging tile (81 words: odd => conflict-free)
-constexpr int NWB = 12;                      // warps used by the GRU_B input GEMV: (row-group 0..5) x (K half 0..1)
+constexpr int FCW_ROW = 36;                  // dual_fc rows kept in shared memory are padded 32->36 floats: 144 B stride = 16 mod 128, so the per-lane
+                                             // LDS.128 row reads of lanes on different nodes mostly land in different 4-bank groups
+constexpr int FCW_SMEM_NODES = 64;           // tree levels 0..5 (nodes 1..63) live in shared memory, levels 6,7 are read from global (L2)
+constexpr int KPARTS = (NWC >= 24) ? 4 : 2;  // K split of the GRU_B input GEMV
+constexpr int NWB = 6 * KPARTS;              // warps used by the GRU_B input GEMV: (row group 0..5) x (K part)
+static_assert(NWB <= NWC, "one (row group, K part) of GRU_B per compute warp");
+constexpr int NBW = (NB + NWC - 1) / NWC;    // GRU_B neurons finished per compute warp
 
 // ---- shared-memory map of the per-sample kernel ----
 // Everything whose size does not depend on the model's sparsity pattern sits at a COMPILE-TIME offset (keeps the
@@ -38,25 +53,26 @@ constexpr int NWB = 12;                      // warps used by the GRU_B input GE
 // [SM_IMAGE, SM_IMAGE + image_bytes) is copied verbatim from the global "SMEM image" built at model-load time
 // (TMA bulk copies); [0, SM_IMAGE) is the mutable working set.
 constexpr uint32_t al128(uint32_t x) { return (x + 127u) & ~127u; }
-constexpr int GIN_ROW = 388;                                       // floats per stream in the gather tile: 384 + 4 pad => row stride 1552 B
+constexpr int GIN_ROW = 388;                                       // floats per stream in a gather tile: 384 + 4 pad => row stride 1552 B
                                                                    // (= 16 mod 128): per-lane LDS.128 of a quarter-warp hit 8 disjoint 4-bank groups
-constexpr uint32_t SM_XS    = 0;                                   // 2 x XS_BYTES: double-buffered quantised GRU_A state
-constexpr uint32_t SM_XB    = SM_XS + 2 * XS_BYTES;                // 2 x [4 words][32]: quantised GRU_B state
-constexpr uint32_t SM_GIN   = SM_XB + 2 * 4 * 32 * 4;              // float [32 streams][GIN_ROW]: cond + 3 embedding rows of ONE gate (z, r or h)
-constexpr uint32_t SM_ACCB  = SM_GIN;                              // int32 [2][48][32] K-half partial sums of the GRU_B input GEMV   } alias the gather tile:
-constexpr uint32_t SM_HBS   = SM_ACCB + 2 * 3 * NB * 32 * 4;       // float [16][32] GRU_B state for the sampler warp                  } live only between
-                                                                   //                                                                 } GRU_A and the next gather
-constexpr uint32_t SM_IDX   = SM_GIN + 32 * GIN_ROW * 4;           // int32 [3][32]: last_sig_ulaw, pred_ulaw, last_exc
-constexpr uint32_t SM_PCM   = SM_IDX + 3 * 32 * 4;                 // int16 [32][PCM_ROW]
-constexpr uint32_t SM_MBAR  = al128(SM_PCM + 32 * PCM_ROW * 2);    // 8-byte mbarrier of the image copy
+constexpr uint32_t TILE_BYTES = 32 * GIN_ROW * 4;
+constexpr uint32_t SM_XS    = 0;                                   // 2 x quantised GRU_A state [96 words][32 lanes] (double-buffered)
+constexpr uint32_t SM_XB    = SM_XS + 2 * XS_BYTES;                    // 2 x [4 words][32]: quantised GRU_B state
+constexpr uint32_t SM_T0    = SM_XB + 2 * 4 * 32 * 4;              // gather tile 0: gate r, later gate z   (float [32 streams][GIN_ROW])
+constexpr uint32_t SM_T1    = SM_T0 + TILE_BYTES;                  // gather tile 1: gate h
+constexpr uint32_t SM_ACCB  = SM_T1;                               // int32 [KPARTS][48][32] partial sums of the GRU_B input GEMV     } alias tile 1:
+constexpr uint32_t SM_HBS   = SM_ACCB + KPARTS * 3 * NB * 32 * 4;       // float [16][32] GRU_B state for the sampler warp                  } live only between the
+                                                                   //                                                                 } h-gate and the next indices
+constexpr uint32_t SM_IDX   = SM_T1 + TILE_BYTES;                  // int32 [3][32]: last_sig_ulaw, pred_ulaw, last_exc
+constexpr uint32_t SM_MBAR  = al128(SM_IDX + 3 * 32 * 4);          // 8-byte mbarrier of the image copy
 constexpr uint32_t SM_IMAGE = SM_MBAR + 128;
 static_assert(SM_HBS + NB * 32 * 4 <= SM_IDX, "GRU_B scratch must fit inside the gather tile it aliases");
 // image, fixed part (offsets relative to SM_IMAGE)
-constexpr uint32_t IM_RCP   = 0;                                   // u32 [2048] RCPPS table (T[k] + 0x3f800000: one IADD3 rebuilds the result)
-constexpr uint32_t IM_LOGIT = IM_RCP + 2048 * 4;                   // float [256] sampling_logit_table
+constexpr uint32_t IM_RCP   = 0;                                   // u16 [2048] RCPPS table ((T[k] - 0x3f000000) >> 11)
+constexpr uint32_t IM_LOGIT = IM_RCP + 2048 * 2;                   // float [256] sampling_logit_table
 constexpr uint32_t IM_U2L   = IM_LOGIT + 256 * 4;                  // float [256] ulaw2lin
-constexpr uint32_t IM_FCW   = IM_U2L + 256 * 4;                    // float [256][FCW_ROW] dual_fc weights
-constexpr uint32_t IM_FCB   = IM_FCW + 256 * FCW_ROW * 4;          // float [2][256]
+constexpr uint32_t IM_FCW   = IM_U2L + 256 * 4;                    // float [FCW_SMEM_NODES][FCW_ROW] dual_fc weights of the upper tree levels
+constexpr uint32_t IM_FCB   = IM_FCW + FCW_SMEM_NODES * FCW_ROW * 4;   // float [2][256]
 constexpr uint32_t IM_FCF   = IM_FCB + 512 * 4;                    // float [2][256]
 constexpr uint32_t IM_PARA  = IM_FCF + 512 * 4;                    // float [NWC][GPW][3 gates][16] = recurrent su-bias[8], diag[8]
 constexpr uint32_t IM_DIRA  = IM_PARA + NWC * GPW * 3 * 16 * 4;    // uint32 [NWC][GPW][3][2] = {first block, padded (even) block count}
@@ -84,6 +100,7 @@ struct DeviceModel {
     uint8_t *image;                  // [L.image_bytes] global copy of the SMEM image
     // per-sample gathers (L2-resident): [256][3*NA] each
     float *emb_sig, *emb_pred, *emb_exc;
+    float *fcw;                      // dual_fc weights [256][32] (the lower tree levels are read from here)
     // frame network (fp32, reference layouts kept: column-major W[j*N+i], conv W[(k*in+i)*out+o])
     float *embed_pitch;              // [256][64]
     float *conv1_w, *conv1_b, *conv2_w, *conv2_b;
@@ -106,6 +123,7 @@ struct SampleParams {
     SmemLayout L;
     const uint8_t *image;
     const float *emb_sig, *emb_pred, *emb_exc;
+    const float *fcw;        // [256][32] dual_fc weights (levels 6,7 of the sampling tree)
     const float *condA;      // [nframes][n][3*NA]
     const float *condB;      // [nframes][n][3*NB]
     const float *lpc_raw;    // [nframes + 2][n][16]  (frame f uses entry f: the LPC of frame f-2)

@@ -97,7 +97,7 @@ uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 struct HostModel {               // everything model_load needs after parsing, before any CUDA call
     std::vector<uint8_t> img;
     const float *embed_pitch, *conv1_w, *conv1_b, *conv2_w, *conv2_b, *dense1_w, *dense1_b, *dense2_w, *dense2_b;
-    const float *gad_w, *gad_b, *gbd_w, *gbd_b, *emb_sig, *emb_pred, *emb_exc;
+    const float *gad_w, *gad_b, *gbd_w, *gbd_b, *emb_sig, *emb_pred, *emb_exc, *fc_w;
 };
 
 static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *blob, int len, float lpc_gamma)
@@ -164,19 +164,23 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
     auto padded = [](size_t n) { return (uint32_t)((n + 1) & ~size_t(1)); };
     uint32_t nA_pad = 0, nB_pad = 0;
     for (int w = 0; w < NWC; w++) for (int s = 0; s < GPW; s++) for (int q = 0; q < 3; q++) nA_pad += padded(rowsA[q * NGRP + grp[w][s]].size());
-    // GRU_B input GEMV: warp (rg, half) takes blocks [half*ceil(n/2) ...)
+    // GRU_B input GEMV: warp (rg, part) takes a contiguous KPARTS-th of the row group's block list
     uint32_t dirB_h[NWB][2];
+    auto part_lo = [](size_t n, int k) { return (n * k + KPARTS - 1) / KPARTS; };
     for (int rg = 0; rg < 6; rg++) {
-        size_t n = rowsB[rg].size(), h0 = (n + 1) / 2;
-        dirB_h[rg * 2][1] = padded(h0); dirB_h[rg * 2 + 1][1] = padded(n - h0);
-        nB_pad += dirB_h[rg * 2][1] + dirB_h[rg * 2 + 1][1];
+        size_t n = rowsB[rg].size();
+        for (int k = 0; k < KPARTS; k++) {
+            dirB_h[rg * KPARTS + k][1] = padded(part_lo(n, k + 1) - part_lo(n, k));
+            nB_pad += dirB_h[rg * KPARTS + k][1];
+        }
     }
     uint32_t off = SM_IMAGE + IM_VAR;
     auto take = [&](uint32_t bytes, uint32_t align = 16) { off = align_up(off, align); uint32_t o = off; off += bytes; return o; };
-    L.wA = take(nA_pad * 32, 128);
-    L.metaA = take(nA_pad * 2);
-    L.wB = take(nB_pad * 32, 128);
-    L.metaB = take(nB_pad * 2);
+    // +2 blocks / +4 meta entries of readable slack behind every array: the pipelined GEMV prefetches past the list end
+    L.wA = take((nA_pad + 2) * 32, 128);
+    L.metaA = take((nA_pad + 4) * 2);
+    L.wB = take((nB_pad + 2) * 32, 128);
+    L.metaB = take((nB_pad + 4) * 2);
     L.total_bytes = align_up(off, 128);
     L.image_bytes = L.total_bytes - SM_IMAGE;
     L.nblkA_padded = nA_pad; L.nblkB_padded = nB_pad;
@@ -215,16 +219,15 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
     blk = 0;
     for (int rg = 0; rg < 6; rg++) {
         const auto &lst = rowsB[rg];
-        size_t h0 = (lst.size() + 1) / 2;
-        for (int half = 0; half < 2; half++) {
-            size_t b0 = half ? h0 : 0, b1 = half ? lst.size() : h0;
-            dirB[(rg * 2 + half) * 2 + 0] = blk;
-            dirB[(rg * 2 + half) * 2 + 1] = dirB_h[rg * 2 + half][1];
+        for (int k = 0; k < KPARTS; k++) {
+            size_t b0 = part_lo(lst.size(), k), b1 = part_lo(lst.size(), k + 1);
+            dirB[(rg * KPARTS + k) * 2 + 0] = blk;
+            dirB[(rg * KPARTS + k) * 2 + 1] = dirB_h[rg * KPARTS + k][1];
             for (size_t j = b0; j < b1; j++) {
                 memcpy(&img[oWB + (size_t)(blk + (j - b0)) * 32], lst[j].w, 32);
                 metaB[blk + (j - b0)] = (uint16_t)((lst[j].pos / 4) * 128);
             }
-            blk += dirB_h[rg * 2 + half][1];
+            blk += dirB_h[rg * KPARTS + k][1];
         }
     }
     memcpy(&img[IM_WBREC], wBrec->data, 3 * NB * NB);
@@ -233,10 +236,7 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
         for (int i = 0; i < 6 * NB; i++) pb[i] = gb_subias[i];          // nnet.c:346-360 (USE_SU_BIAS)
         (void)gb_bias; (void)ga_bias;
     }
-    {
-        uint32_t *r32 = reinterpret_cast<uint32_t *>(&img[IM_RCP]);
-        for (int k = 0; k < 2048; k++) r32[k] = 0x3f000000u + ((uint32_t)kRcpTable[k] << 11) + 0x3f800000u;
-    }
+    memcpy(&img[IM_RCP], kRcpTable, sizeof(kRcpTable));
     {
         float *lg = reinterpret_cast<float *>(&img[IM_LOGIT]);
         for (int i = 0; i < 256; i++) {                                   // lpcnet.c:188-191 (host libm, double log)
@@ -250,7 +250,7 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
             u2l[i] = s * scale_1 * (exp(u / 128. * 5.5451774445f) - 1);
         }
         float *fw = reinterpret_cast<float *>(&img[IM_FCW]);
-        for (int i = 0; i < 256; i++) for (int j = 0; j < 32; j++) fw[i * FCW_ROW + j] = fc_w[i * 32 + j];
+        for (int i = 0; i < FCW_SMEM_NODES; i++) for (int j = 0; j < 32; j++) fw[i * FCW_ROW + j] = fc_w[i * 32 + j];
         memcpy(&img[IM_FCB], fc_b, 512 * 4);
         memcpy(&img[IM_FCF], fc_f, 512 * 4);
     }
@@ -258,7 +258,7 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
     hm.embed_pitch = embed_pitch; hm.conv1_w = conv1_w; hm.conv1_b = conv1_b; hm.conv2_w = conv2_w; hm.conv2_b = conv2_b;
     hm.dense1_w = dense1_w; hm.dense1_b = dense1_b; hm.dense2_w = dense2_w; hm.dense2_b = dense2_b;
     hm.gad_w = gad_w; hm.gad_b = gad_b; hm.gbd_w = gbd_w; hm.gbd_b = gbd_b;
-    hm.emb_sig = emb_sig; hm.emb_pred = emb_pred; hm.emb_exc = emb_exc;
+    hm.emb_sig = emb_sig; hm.emb_pred = emb_pred; hm.emb_exc = emb_exc; hm.fc_w = fc_w;
     hm.img.swap(img);
     // algorithmic bytes per synthesized sample
     m->algo_bytes_sparse = 32L * nblkA + 4L * (3 * NGRP + nblkA);
@@ -287,12 +287,13 @@ int model_load(DeviceModel *m, const unsigned char *blob, int len, float lpc_gam
     const float *embed_pitch = hm.embed_pitch, *conv1_w = hm.conv1_w, *conv1_b = hm.conv1_b, *conv2_w = hm.conv2_w, *conv2_b = hm.conv2_b;
     const float *dense1_w = hm.dense1_w, *dense1_b = hm.dense1_b, *dense2_w = hm.dense2_w, *dense2_b = hm.dense2_b;
     const float *gad_w = hm.gad_w, *gad_b = hm.gad_b, *gbd_w = hm.gbd_w, *gbd_b = hm.gbd_b;
-    const float *emb_sig = hm.emb_sig, *emb_pred = hm.emb_pred, *emb_exc = hm.emb_exc;
+    const float *emb_sig = hm.emb_sig, *emb_pred = hm.emb_pred, *emb_exc = hm.emb_exc, *fc_w = hm.fc_w;
     // ---------------- device copies ----------------
     bool ok = true;
 #define UP(field, src, count) ok = ok && ((m->field = to_device(src, (size_t)(count))) != nullptr);
     UP(image, img.data(), img.size())
     UP(emb_sig, emb_sig, 256 * 3 * NA) UP(emb_pred, emb_pred, 256 * 3 * NA) UP(emb_exc, emb_exc, 256 * 3 * NA)
+    UP(fcw, fc_w, 256 * 2 * NB)
     UP(embed_pitch, embed_pitch, 256 * PITCH_EMBED)
     UP(conv1_w, conv1_w, 3 * FRAME_IN * COND) UP(conv1_b, conv1_b, COND)
     UP(conv2_w, conv2_w, 3 * COND * COND) UP(conv2_b, conv2_b, COND)
@@ -338,7 +339,7 @@ int model_load(DeviceModel *m, const unsigned char *blob, int len, float lpc_gam
 
 void model_free(DeviceModel *m)
 {
-    void *ptrs[] = {m->image, m->emb_sig, m->emb_pred, m->emb_exc, m->embed_pitch, m->conv1_w, m->conv1_b, m->conv2_w, m->conv2_b,
+    void *ptrs[] = {m->image, m->fcw, m->emb_sig, m->emb_pred, m->emb_exc, m->embed_pitch, m->conv1_w, m->conv1_b, m->conv2_w, m->conv2_b,
                     m->dense1_w, m->dense1_b, m->dense2_w, m->dense2_b, m->gad_w, m->gad_b, m->gbd_w, m->gbd_b, m->rcp16, m->dct,
                     m->twiddles, m->bitrev, m->gamma_pow, m->pitch_pow, m->codebooks};
     for (void *p : ptrs) if (p) cudaFree(p);

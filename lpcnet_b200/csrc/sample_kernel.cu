@@ -1,4 +1,4 @@
-// sample_kernel.cu — the 16 kHz autoregressive loop as ONE persistent sm_100a kernel.
+// sample_kernel.cu — the 16 kHz autoregressive loop as ONE persistent, warp-specialised sm_100a kernel.
 //
 // Replaces (reference file:line):
 //   lpcnet_synthesize_tail_impl  src/lpcnet.c:235-271   (LPC prediction, u-law, de-emphasis, clamp/round)
@@ -9,15 +9,24 @@
 //   sample_mdense                src/nnet.c:163-214  +  kiss99_rand src/kiss99.c:59-81
 //   lin2ulaw / ulaw2lin          src/common.h:37-58
 //
-// Mapping (DESIGN.md "sample kernel"): one CTA = 32 independent streams, LANE == STREAM.  All 32 lanes of a warp
-// execute the same (warp-uniform) walk over the block-sparse weights, so every weight word is fetched from shared
-// memory ONCE per 32 streams (broadcast LDS.128) instead of once per stream, and no cross-lane reduction exists:
-// each lane finishes the 8 outputs of a block row group in its own registers with dp4a.u32.s32 (one dp4a == one
-// block row, integer-exact like maddubs+madd under the WeightClip pair constraint).  16 compute warps each own 3
-// neuron groups (8 neurons x {z,r,h}) of GRU_A — fp32 state lives in registers for the whole utterance, only the
-// quantised u8 state is exchanged through shared memory — plus one neuron of GRU_B.  A 17th warp runs the strictly
-// serial tail (tree sampler, LPC filter, u-law, de-emphasis) for its 32 streams.  Weights, su-biases, dual_fc and the
-// sampler tables are staged into shared memory once per launch by TMA bulk copies (cp.async.bulk + mbarrier).
+// One CTA = 32 independent streams, LANE == STREAM, one CTA per SM, NWC + 3 + 1 warps:
+//
+//   NWC compute warps own 48/NWC neuron groups (8 neurons x {z,r,h}) of GRU_A each (default 24 warps x 2 groups).  All 32 lanes walk the same
+//                     block-sparse weight list, so every 32-byte weight block is fetched from shared memory ONCE per
+//                     32 streams (broadcast LDS.128) and each lane finishes the 8 outputs of a row group in its own
+//                     registers with dp4a.u32.s32 — no cross-lane reduction.  fp32 state lives in registers for the
+//                     whole launch; only the quantised u8 state goes through shared memory.  The integer GEMV sums
+//                     S = W.q(h) do not depend on the sampled excitation, so they are computed FIRST (overlapping the
+//                     previous sample's sampler and this sample's gather) and the gathered input term is added when it
+//                     arrives:  acc = rne((bias + diag*h + gin)*16256) + S  is the same integer the reference gets.
+//    3 producer warps gather the GRU_A input term cond + E_sig[a] + E_pred[b] + E_exc[c] (compute_gru_a_input) for the 32
+//                     streams, one gate at a time, with 512-byte contiguous LDG.128 (4 L1 lines per request instead of
+//                     32 for a per-lane gather) into two [32][388] fp32 tiles that the compute lanes read conflict-free.
+//    1 sampler warp   runs the strictly serial tail (two KISS99 draws, 8-level sigmoid tree with sequential fp32 dot
+//                     products, ulaw2lin, order-16 LPC filter, de-emphasis, lin2ulaw) for its 32 streams.
+//
+// Weights, su-biases, the upper dual_fc levels and the sampler tables are staged into shared memory once per launch
+// by TMA bulk copies (cp.async.bulk + mbarrier).  Roles hand data over with named barriers (bar.arrive / bar.sync).
 #include <cstdint>
 #include "engine.h"
 #include "devmath.cuh"
@@ -26,11 +35,20 @@ namespace lpcnet_b200 {
 
 namespace {
 
-enum { BAR_IDX = 1, BAR_X = 2, BAR_ACCB = 3, BAR_HB = 4, BAR_GF = 5, BAR_GE = 6 };   // GF: gather tile full, GE: tile free again
+// named barriers: who arrives (A) / who waits (S) and the thread count each one is armed with
+enum {
+    BAR_IDX = 1,     // A sampler, S producers : indices of the next sample are in idx_s                 (32 + 96)
+    BAR_FULL0 = 2,   // A producers, S compute : tile 0 holds gate r (1st phase) / gate z (2nd phase)     (96 + 32 NWC)
+    BAR_FULL1 = 3,   // A producers, S compute : tile 1 holds gate h                                     (96 + 384)
+    BAR_EMPTY0 = 4,  // A compute, S producers : tile 0 (gate r) consumed, may be overwritten with gate z (384 + 96)
+    BAR_X = 5,       // S compute              : new quantised GRU_A state complete                       (384)
+    BAR_ACCB = 6,    // S compute              : GRU_B partial sums complete                              (384)
+    BAR_HB = 7       // A compute, S sampler   : GRU_B state of this sample is in hBs                     (384 + 32)
+};
+constexpr int CNT_IDX = 32 + NWP * 32, CNT_FULL = (NWP + NWC) * 32, CNT_C = NWC * 32, CNT_HB = NWC * 32 + 32;
 
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // ---- TMA bulk copy global -> shared, completion on an mbarrier ----
@@ -60,37 +78,60 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 
-// Cooperative gather of ONE gate's GRU_A input for the CTA's 32 streams (compute_gru_a_input, nnet.c:484-491):
-//   G[s][k] = ((cond[s][k] + E_sig[a_s][k]) + E_pred[b_s][k]) + E_exc[c_s][k],   k in [0, 384)
-// Warp w serves streams 2w and 2w+1; its 32 lanes read consecutive float4 of the four rows (512 B contiguous per
-// instruction = 4 L1 lines, instead of 32 lines for a per-lane gather) and store the sums transposed-by-row into
-// the shared tile, from which every lane (== stream) later reads its own 8-neuron slices conflict-free.
-__device__ __forceinline__ void gather_gate(float *__restrict__ G, const float *__restrict__ cond_f, int n, int cta_s0,
-                                            const float *__restrict__ emb_sig, const float *__restrict__ emb_pred,
-                                            const float *__restrict__ emb_exc, const int *__restrict__ idx_s,
-                                            int gate, int warp, int lane)
+// acc[r] += sum over `nb` 8x4 blocks; weights broadcast from smem (LDS.128), activations one word per lane.
+// Software-pipelined by hand: while block b is multiplied, the weights + activation word of block b+1 and the
+// meta entry of block b+2 are already in flight (LDS latency ~30 cycles would otherwise stall every 4 dp4a).
+// The prefetch runs up to two entries past the end of the list: the image keeps that slack readable
+// (next list / zero padding) and the values are never used.
+// shared-memory loads as volatile asm: keeps the compiler from sinking the prefetches of the pipelined GEMV down to
+// their first use (which would expose the ~30-cycle LDS latency once per 4 dp4a)
+__device__ __forceinline__ int4 lds128(uint32_t addr)
 {
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        const int ss = 2 * warp + k;
-        const int sg = min(cta_s0 + ss, n - 1);
-        const float *c = cond_f + (size_t)sg * (3 * NA) + gate * NA + lane * 4;
-        const float *e0 = emb_sig + (size_t)idx_s[ss] * (3 * NA) + gate * NA + lane * 4;
-        const float *e1 = emb_pred + (size_t)idx_s[32 + ss] * (3 * NA) + gate * NA + lane * 4;
-        const float *e2 = emb_exc + (size_t)idx_s[64 + ss] * (3 * NA) + gate * NA + lane * 4;
-        float *g = G + ss * GIN_ROW + lane * 4;
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            const float4 a = ldg4(c + 128 * j), b = ldg4(e0 + 128 * j), d = ldg4(e1 + 128 * j), e = ldg4(e2 + 128 * j);
-            float4 r;
-            r.x = __fadd_rn(__fadd_rn(__fadd_rn(a.x, b.x), d.x), e.x);
-            r.y = __fadd_rn(__fadd_rn(__fadd_rn(a.y, b.y), d.y), e.y);
-            r.z = __fadd_rn(__fadd_rn(__fadd_rn(a.z, b.z), d.z), e.z);
-            r.w = __fadd_rn(__fadd_rn(__fadd_rn(a.w, b.w), d.w), e.w);
-            *reinterpret_cast<float4 *>(g + 128 * j) = r;
-        }
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("{ .reg .u16 t; ld.shared.u16 t, [%1]; cvt.u32.u16 %0, t; }" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void mac_block(int acc[8], uint32_t x, const int4 &w0, const int4 &w1)
+{
+    acc[0] = dp4a_us(x, w0.x, acc[0]); acc[1] = dp4a_us(x, w0.y, acc[1]);
+    acc[2] = dp4a_us(x, w0.z, acc[2]); acc[3] = dp4a_us(x, w0.w, acc[3]);
+    acc[4] = dp4a_us(x, w1.x, acc[4]); acc[5] = dp4a_us(x, w1.y, acc[5]);
+    acc[6] = dp4a_us(x, w1.z, acc[6]); acc[7] = dp4a_us(x, w1.w, acc[7]);
+}
+// acc[r] += sum over `nb` (even) 8x4 blocks; weights broadcast from smem (LDS.128), activations one word per lane.
+// Software-pipelined by hand with two register sets: set B (block b+1) is loaded before set A (block b) is multiplied
+// and vice versa, meta entries two blocks ahead.  The prefetch runs up to four entries past the end of the list: the
+// image keeps that slack readable (next list / zero padding) and the values are never used.
+__device__ __forceinline__ void gemv_blocks(int acc[8], uint32_t w /* smem addr */, uint32_t meta /* smem addr */,
+                                            int nb /* even */, uint32_t xs_lane /* smem addr */)
+{
+    uint32_t mA = lds16(meta), mB = lds16(meta + 2);
+    uint32_t xA = lds32(xs_lane + mA);
+    int4 a0 = lds128(w), a1 = lds128(w + 16);
+    for (int b = 0; b < nb; b += 2) {
+        const uint32_t xB = lds32(xs_lane + mB);
+        const int4 b0 = lds128(w + 32), b1 = lds128(w + 48);
+        mA = lds16(meta + 4); mB = lds16(meta + 6);
+        mac_block(acc, xA, a0, a1);
+        xA = lds32(xs_lane + mA);
+        a0 = lds128(w + 64); a1 = lds128(w + 80);
+        mac_block(acc, xB, b0, b1);
+        w += 64; meta += 4;
     }
 }
+
 __device__ __forceinline__ void load_gin(float gin[8], const float *__restrict__ G, int lane, int g)
 {
     const float4 a = *reinterpret_cast<const float4 *>(G + lane * GIN_ROW + 8 * g);
@@ -98,27 +139,41 @@ __device__ __forceinline__ void load_gin(float gin[8], const float *__restrict__
     gin[0] = a.x; gin[1] = a.y; gin[2] = a.z; gin[3] = a.w; gin[4] = b.x; gin[5] = b.y; gin[6] = b.z; gin[7] = b.w;
 }
 
-// acc[r] += sum over `nb` (even) 8x4 blocks; weights broadcast from smem, activations one word per lane
-__device__ __forceinline__ void gemv_blocks(int acc[8], const uint8_t *__restrict__ w, const uint16_t *__restrict__ meta,
-                                            int nb, const uint8_t *__restrict__ xs_lane)
+// Producer warps: ONE gate's input term for all 32 streams of the CTA,
+//   G[s][k] = ((cond[s][k] + E_sig[a_s][k]) + E_pred[b_s][k]) + E_exc[c_s][k]        (nnet.c:484-491, left to right)
+// cut into 96 units (stream, third-of-the-row): one unit = 128 columns = one 512-byte LDG.128 per source row.
+// Producer p takes units p, p+NWP, ...; B units (4B independent LDG.128 per lane) are in flight at a time.
+template <int B>
+__device__ __forceinline__ void gather_slice(float *__restrict__ G, const float *__restrict__ cond_f, int n, int cta_s0,
+                                             const float *__restrict__ emb_sig, const float *__restrict__ emb_pred,
+                                             const float *__restrict__ emb_exc, const int *__restrict__ idx_s,
+                                             int gate, int p, int lane)
 {
-    for (int b = 0; b < nb; b += 2) {
-        const uint32_t m = *reinterpret_cast<const uint32_t *>(meta + b);
-        const uint32_t x0 = *reinterpret_cast<const uint32_t *>(xs_lane + (m & 0xFFFFu));
-        const uint32_t x1 = *reinterpret_cast<const uint32_t *>(xs_lane + (m >> 16));
-        const int4 wa = *reinterpret_cast<const int4 *>(w);
-        const int4 wb = *reinterpret_cast<const int4 *>(w + 16);
-        const int4 wc = *reinterpret_cast<const int4 *>(w + 32);
-        const int4 wd = *reinterpret_cast<const int4 *>(w + 48);
-        acc[0] = dp4a_us(x0, wa.x, acc[0]); acc[1] = dp4a_us(x0, wa.y, acc[1]);
-        acc[2] = dp4a_us(x0, wa.z, acc[2]); acc[3] = dp4a_us(x0, wa.w, acc[3]);
-        acc[4] = dp4a_us(x0, wb.x, acc[4]); acc[5] = dp4a_us(x0, wb.y, acc[5]);
-        acc[6] = dp4a_us(x0, wb.z, acc[6]); acc[7] = dp4a_us(x0, wb.w, acc[7]);
-        acc[0] = dp4a_us(x1, wc.x, acc[0]); acc[1] = dp4a_us(x1, wc.y, acc[1]);
-        acc[2] = dp4a_us(x1, wc.z, acc[2]); acc[3] = dp4a_us(x1, wc.w, acc[3]);
-        acc[4] = dp4a_us(x1, wd.x, acc[4]); acc[5] = dp4a_us(x1, wd.y, acc[5]);
-        acc[6] = dp4a_us(x1, wd.z, acc[6]); acc[7] = dp4a_us(x1, wd.w, acc[7]);
-        w += 64;
+    constexpr int UNITS = STREAMS_PER_CTA * 3;
+    for (int u0 = p; u0 < UNITS; u0 += B * NWP) {
+        float4 a[B], b[B], d[B], e[B];
+#pragma unroll
+        for (int j = 0; j < B; j++) {
+            const int u = min(u0 + j * NWP, UNITS - 1);
+            const int ss = u / 3, col = gate * NA + (u % 3) * 128 + lane * 4;
+            const int sg = min(cta_s0 + ss, n - 1);
+            a[j] = ldg4(cond_f + (size_t)sg * (3 * NA) + col);
+            b[j] = ldg4(emb_sig + (size_t)idx_s[ss] * (3 * NA) + col);
+            d[j] = ldg4(emb_pred + (size_t)idx_s[32 + ss] * (3 * NA) + col);
+            e[j] = ldg4(emb_exc + (size_t)idx_s[64 + ss] * (3 * NA) + col);
+        }
+#pragma unroll
+        for (int j = 0; j < B; j++) {
+            const int u = u0 + j * NWP;
+            if (u < UNITS) {
+                float4 r;
+                r.x = __fadd_rn(__fadd_rn(__fadd_rn(a[j].x, b[j].x), d[j].x), e[j].x);
+                r.y = __fadd_rn(__fadd_rn(__fadd_rn(a[j].y, b[j].y), d[j].y), e[j].y);
+                r.z = __fadd_rn(__fadd_rn(__fadd_rn(a[j].z, b[j].z), d[j].z), e[j].z);
+                r.w = __fadd_rn(__fadd_rn(__fadd_rn(a[j].w, b[j].w), d[j].w), e[j].w);
+                *reinterpret_cast<float4 *>(G + (u / 3) * GIN_ROW + (u % 3) * 128 + lane * 4) = r;
+            }
+        }
     }
 }
 
@@ -130,7 +185,8 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
     const SmemLayout &L = P.L;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = P.n_streams;
-    const int s_raw = blockIdx.x * STREAMS_PER_CTA + lane;
+    const int cta_s0 = blockIdx.x * STREAMS_PER_CTA;
+    const int s_raw = cta_s0 + lane;
     const bool live = s_raw < n;
     const int s = live ? s_raw : n - 1;          // dead lanes shadow the last stream (all loads valid), stores masked
 
@@ -150,14 +206,14 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
         }
     }
 
-    const uint32_t *rcp = reinterpret_cast<const uint32_t *>(smem + SM_IMAGE + IM_RCP);
+    const uint16_t *rcp = reinterpret_cast<const uint16_t *>(smem + SM_IMAGE + IM_RCP);
     uint8_t *xs = smem + SM_XS;
     uint32_t *xbw = reinterpret_cast<uint32_t *>(smem + SM_XB);
     int *accB = reinterpret_cast<int *>(smem + SM_ACCB);
     float *hBs = reinterpret_cast<float *>(smem + SM_HBS);
     int *idx_s = reinterpret_cast<int *>(smem + SM_IDX);
-    float *gin_tile = reinterpret_cast<float *>(smem + SM_GIN);
-    const int cta_s0 = blockIdx.x * STREAMS_PER_CTA;
+    float *tile0 = reinterpret_cast<float *>(smem + SM_T0);
+    float *tile1 = reinterpret_cast<float *>(smem + SM_T1);
     const int spf = P.spf;
 
     if (warp < NWC) {
@@ -166,13 +222,15 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
         const uint32_t *grpA = reinterpret_cast<const uint32_t *>(smem + SM_IMAGE + IM_GRPA);
         const uint32_t *dirA = reinterpret_cast<const uint32_t *>(smem + SM_IMAGE + IM_DIRA) + warp * GPW * 3 * 2;
         const float *parA = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_PARA) + warp * GPW * 3 * 16;
-        const uint16_t *metaA = reinterpret_cast<const uint16_t *>(smem + L.metaA);
-        const uint8_t *wA = smem + L.wA;
+        const uint32_t metaA = smem_u32(smem + L.metaA);
+        const uint32_t wA = smem_u32(smem + L.wA);
         const uint32_t *dirB = reinterpret_cast<const uint32_t *>(smem + SM_IMAGE + IM_DIRB);
-        const uint16_t *metaB = reinterpret_cast<const uint16_t *>(smem + L.metaB);
-        const uint8_t *wB = smem + L.wB;
+        const uint32_t metaB = smem_u32(smem + L.metaB);
+        const uint32_t wB = smem_u32(smem + L.wB);
         const float *parB = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_PARB);
         const uint8_t *wBrec = smem + SM_IMAGE + IM_WBREC;
+        const uint32_t xs_lane0 = smem_u32(xs + lane * 4);
+        uint32_t *xs_w0 = reinterpret_cast<uint32_t *>(xs);
 
         int grp[GPW];
         float h[GPW][8];
@@ -182,125 +240,147 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
 #pragma unroll
             for (int i = 0; i < 8; i++) h[sl][i] = P.hA[(size_t)(8 * grp[sl] + i) * n + s];
         }
-        const int jb = warp;                               // the GRU_B neuron this warp finishes (NB == NWC)
-        float hb = P.hB[(size_t)jb * n + s];
-        // quantised copies of the restored state: xs[0] <- q(hA), xb[0] <- q(hB)
+        // GRU_B neurons finished by this warp: jb = warp + k*NWC < NB
+        float hb[NBW];
+#pragma unroll
+        for (int k = 0; k < NBW; k++) hb[k] = P.hB[(size_t)min(warp + k * NWC, NB - 1) * n + s];
+        // quantised copies of the restored state: xs <- q(hA), xb[0] <- q(hB)
 #pragma unroll
         for (int sl = 0; sl < GPW; sl++) {
-            uint32_t w0 = quant_u8(h[sl][0]) | (quant_u8(h[sl][1]) << 8) | (quant_u8(h[sl][2]) << 16) | (quant_u8(h[sl][3]) << 24);
-            uint32_t w1 = quant_u8(h[sl][4]) | (quant_u8(h[sl][5]) << 8) | (quant_u8(h[sl][6]) << 16) | (quant_u8(h[sl][7]) << 24);
-            reinterpret_cast<uint32_t *>(xs)[(2 * grp[sl]) * 32 + lane] = w0;
-            reinterpret_cast<uint32_t *>(xs)[(2 * grp[sl] + 1) * 32 + lane] = w1;
+            xs_w0[(2 * grp[sl]) * 32 + lane] = quant_u8(h[sl][0]) | (quant_u8(h[sl][1]) << 8) | (quant_u8(h[sl][2]) << 16) | (quant_u8(h[sl][3]) << 24);
+            xs_w0[(2 * grp[sl] + 1) * 32 + lane] = quant_u8(h[sl][4]) | (quant_u8(h[sl][5]) << 8) | (quant_u8(h[sl][6]) << 16) | (quant_u8(h[sl][7]) << 24);
         }
-        reinterpret_cast<uint8_t *>(xbw)[((jb >> 2) * 32 + lane) * 4 + (jb & 3)] = (uint8_t)quant_u8(hb);
+#pragma unroll
+        for (int k = 0; k < NBW; k++) {
+            const int jb = warp + k * NWC;
+            if (jb < NB) reinterpret_cast<uint8_t *>(xbw)[((jb >> 2) * 32 + lane) * 4 + (jb & 3)] = (uint8_t)quant_u8(hb[k]);
+        }
+        bar_sync(BAR_X, CNT_C);                                          // restored quantised state visible to all compute warps
 
         int step = 0;
         for (int f = 0; f < P.nframes; f++) {
-            const float *condA_f = P.condA + (size_t)f * n * (3 * NA);
             const float *condBp = P.condB + ((size_t)f * n + s) * (3 * NB);
-            const float cbz = __ldg(condBp + jb), cbr = __ldg(condBp + NB + jb), cbh = __ldg(condBp + 2 * NB + jb);
+            float cbz[NBW], cbr[NBW], cbh[NBW];
+#pragma unroll
+            for (int k = 0; k < NBW; k++) {
+                const int jb = min(warp + k * NWC, NB - 1);
+                cbz[k] = __ldg(condBp + jb); cbr[k] = __ldg(condBp + NB + jb); cbh[k] = __ldg(condBp + 2 * NB + jb);
+            }
             for (int t = 0; t < spf; t++, step++) {
-                const int cur = step & 1, nxt = cur ^ 1;
-                bar_sync(BAR_IDX, SAMPLE_THREADS);                       // indices of this step are in idx_s
-                const uint8_t *xs_cur = xs + cur * XS_BYTES + lane * 4;
-                uint32_t *xs_nxt = reinterpret_cast<uint32_t *>(xs + nxt * XS_BYTES);
-                float rg[GPW][8];                                        // reset gate, then (in place) the candidate h~
-
-                // ---------------- GRU_A, gate by gate: cooperative gather -> tile -> owners consume ----------------
-                // reset gate r: rec = bias + diag*h + gin (nnet.c:431-435), + int8 GEMV, sigmoid
-                gather_gate(gin_tile, condA_f, n, cta_s0, P.emb_sig, P.emb_pred, P.emb_exc, idx_s, 1, warp, lane);
-                bar_sync(BAR_GF, NWC * 32);
+                const int cur = step & 1, nxt = cur ^ 1;                 // double buffers of the quantised states
+                const uint32_t xs_lane = xs_lane0 + cur * XS_BYTES;
+                uint32_t *xs_w = xs_w0 + nxt * (XS_BYTES / 4);
+                int Sh[GPW][8];                                          // candidate-gate GEMV sums; later (bit pattern) rec_h * r, then h~
+                // ---- A: candidate-gate GEMV  S_h = W_h . q(h)   (needs only the previous state: overlaps sampler + gather) ----
+#pragma unroll
+                for (int sl = 0; sl < GPW; sl++) {
+                    const uint32_t *dir = dirA + sl * 3 * 2;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) Sh[sl][i] = 0;
+                    gemv_blocks(Sh[sl], wA + dir[4] * 32, metaA + dir[4] * 2, (int)dir[5], xs_lane);
+                }
+                // ---- B: reset gate r (nnet.c:431-435): GEMV first, then the gathered input term from tile 0 ----
 #pragma unroll
                 for (int sl = 0; sl < GPW; sl++) {
                     const float *par = parA + sl * 3 * 16;
                     const uint32_t *dir = dirA + sl * 3 * 2;
-                    float gin[8]; int acc[8];
-                    load_gin(gin, gin_tile, lane, grp[sl]);
+                    int Sr[8];
 #pragma unroll
-                    for (int i = 0; i < 8; i++) acc[i] = acc_init(__fadd_rn(__fadd_rn(par[16 + i], __fmul_rn(par[24 + i], h[sl][i])), gin[i]));
-                    gemv_blocks(acc, wA + (size_t)dir[2] * 32, metaA + dir[2], (int)dir[3], xs_cur);
+                    for (int i = 0; i < 8; i++) Sr[i] = 0;
+                    gemv_blocks(Sr, wA + dir[2] * 32, metaA + dir[2] * 2, (int)dir[3], xs_lane);
+                    if (sl == 0) bar_sync(BAR_FULL0, CNT_FULL);          // gate r of all 32 streams is in tile 0
+                    float gin[8];
+                    load_gin(gin, tile0, lane, grp[sl]);
 #pragma unroll
-                    for (int i = 0; i < 8; i++) rg[sl][i] = sigmoid_approx(acc_finish(acc[i]), rcp);
+                    for (int i = 0; i < 8; i++) {
+                        const int acc = acc_init(__fadd_rn(__fadd_rn(par[16 + i], __fmul_rn(par[24 + i], h[sl][i])), gin[i])) + Sr[i];
+                        const float r = sigmoid_approx(acc_finish(acc), rcp);
+                        // candidate pre-activation: rec_h = bias + diag*h (+ GEMV), no input term (nnet.c:436-440); keep rec_h * r
+                        const int acch = acc_init(__fadd_rn(par[32 + i], __fmul_rn(par[40 + i], h[sl][i]))) + Sh[sl][i];
+                        Sh[sl][i] = __float_as_int(__fmul_rn(acc_finish(acch), r));
+                    }
                 }
-                bar_sync(BAR_GE, NWC * 32);
-                // candidate: rec = bias + diag*h (no input term, nnet.c:436-440); h~ = tanh(rec*r + gin_h) (:443-445)
-                gather_gate(gin_tile, condA_f, n, cta_s0, P.emb_sig, P.emb_pred, P.emb_exc, idx_s, 2, warp, lane);
-                bar_sync(BAR_GF, NWC * 32);
+                bar_arrive(BAR_EMPTY0, CNT_FULL);                        // tile 0 may now receive gate z
+                // ---- C: h~ = tanh(rec_h*r + gin_h) from tile 1 (nnet.c:443-445) ----
+                bar_sync(BAR_FULL1, CNT_FULL);                           // gate h is in tile 1
 #pragma unroll
                 for (int sl = 0; sl < GPW; sl++) {
-                    const float *par = parA + sl * 3 * 16;
-                    const uint32_t *dir = dirA + sl * 3 * 2;
-                    float gin[8]; int acc[8];
+                    float gin[8];
+                    load_gin(gin, tile1, lane, grp[sl]);
 #pragma unroll
-                    for (int i = 0; i < 8; i++) acc[i] = acc_init(__fadd_rn(par[32 + i], __fmul_rn(par[40 + i], h[sl][i])));
-                    gemv_blocks(acc, wA + (size_t)dir[4] * 32, metaA + dir[4], (int)dir[5], xs_cur);
-                    load_gin(gin, gin_tile, lane, grp[sl]);
-#pragma unroll
-                    for (int i = 0; i < 8; i++) rg[sl][i] = tanh_approx(__fadd_rn(__fmul_rn(acc_finish(acc[i]), rg[sl][i]), gin[i]), rcp);
+                    for (int i = 0; i < 8; i++)
+                        Sh[sl][i] = __float_as_int(tanh_approx(__fadd_rn(__int_as_float(Sh[sl][i]), gin[i]), rcp));
                 }
-                bar_sync(BAR_GE, NWC * 32);
-                // update gate z, then h <- z*h + (1-z)*h~ (nnet.c:446-447) and the new quantised state
-                gather_gate(gin_tile, condA_f, n, cta_s0, P.emb_sig, P.emb_pred, P.emb_exc, idx_s, 0, warp, lane);
-                bar_sync(BAR_GF, NWC * 32);
+                // ---- D: update gate z (GEMV + input term from tile 0, 2nd phase), h <- z*h + (1-z)*h~ (nnet.c:446-447), new state ----
 #pragma unroll
                 for (int sl = 0; sl < GPW; sl++) {
                     const int g = grp[sl];
                     const float *par = parA + sl * 3 * 16;
                     const uint32_t *dir = dirA + sl * 3 * 2;
-                    float gin[8]; int acc[8];
-                    load_gin(gin, gin_tile, lane, g);
+                    int Sz[8];
 #pragma unroll
-                    for (int i = 0; i < 8; i++) acc[i] = acc_init(__fadd_rn(__fadd_rn(par[i], __fmul_rn(par[8 + i], h[sl][i])), gin[i]));
-                    gemv_blocks(acc, wA + (size_t)dir[0] * 32, metaA + dir[0], (int)dir[1], xs_cur);
+                    for (int i = 0; i < 8; i++) Sz[i] = 0;
+                    gemv_blocks(Sz, wA + dir[0] * 32, metaA + dir[0] * 2, (int)dir[1], xs_lane);
+                    if (sl == 0) bar_sync(BAR_FULL0, CNT_FULL);          // gate z of all 32 streams is in tile 0
+                    float gin[8];
+                    load_gin(gin, tile0, lane, g);
                     uint32_t q[8];
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
-                        const float z = sigmoid_approx(acc_finish(acc[i]), rcp);
-                        const float hn = __fadd_rn(__fmul_rn(z, h[sl][i]), __fmul_rn(__fsub_rn(1.f, z), rg[sl][i]));
+                        const int acc = acc_init(__fadd_rn(__fadd_rn(par[i], __fmul_rn(par[8 + i], h[sl][i])), gin[i])) + Sz[i];
+                        const float z = sigmoid_approx(acc_finish(acc), rcp);
+                        const float hn = __fadd_rn(__fmul_rn(z, h[sl][i]), __fmul_rn(__fsub_rn(1.f, z), __int_as_float(Sh[sl][i])));
                         h[sl][i] = hn;
                         q[i] = quant_u8(hn);
                     }
-                    xs_nxt[(2 * g) * 32 + lane] = q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24);
-                    xs_nxt[(2 * g + 1) * 32 + lane] = q[4] | (q[5] << 8) | (q[6] << 16) | (q[7] << 24);
+                    xs_w[(2 * g) * 32 + lane] = q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24);     // other buffer: readers of the old state are unaffected
+                    xs_w[(2 * g + 1) * 32 + lane] = q[4] | (q[5] << 8) | (q[6] << 16) | (q[7] << 24);
                 }
-                bar_sync(BAR_X, NWC * 32);                               // new quantised GRU_A state complete
+                bar_sync(BAR_X, CNT_C);                                  // new quantised GRU_A state complete (tile 1 is dead: accB/hBs may use it)
 
-                // ---------------- GRU_B input GEMV (48 x 384 int8): warp = (row group, K half) ----------------
+                // ---------------- E: GRU_B input GEMV (48 x 384 int8): warp = (row group, K part) ----------------
                 if (warp < NWB) {
                     int acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                     const uint32_t b0 = dirB[warp * 2], nb = dirB[warp * 2 + 1];
-                    gemv_blocks(acc, wB + (size_t)b0 * 32, metaB + b0, (int)nb, xs + nxt * XS_BYTES + lane * 4);
-                    const int rg = warp >> 1, half = warp & 1;
+                    gemv_blocks(acc, wB + b0 * 32, metaB + b0 * 2, (int)nb, xs_lane0 + nxt * XS_BYTES);
+                    const int rgp = warp / KPARTS, part = warp % KPARTS;
 #pragma unroll
-                    for (int i = 0; i < 8; i++) accB[(half * 3 * NB + rg * 8 + i) * 32 + lane] = acc[i];
+                    for (int i = 0; i < 8; i++) accB[(part * 3 * NB + rgp * 8 + i) * 32 + lane] = acc[i];
                 }
-                bar_sync(BAR_ACCB, NWC * 32);
-
-                // ---------------- GRU_B finish: this warp's neuron jb (nnet.c:346-371) ----------------
+                bar_sync(BAR_ACCB, CNT_C);
+                // ---------------- GRU_B finish (nnet.c:346-371): neurons warp, warp + NWC, ... ----------------
                 {
                     const uint32_t *xbc = xbw + cur * 4 * 32;
-                    const uint32_t x0 = xbc[lane], x1 = xbc[32 + lane], x2 = xbc[64 + lane], x3 = xbc[96 + lane];
-                    // su-biases and recurrent weight words of rows jb, 16+jb, 32+jb; W_rec layout [out/8][in/4][8][4] (dump_lpcnet.py:58-59)
-                    int az = acc_init(__fadd_rn(parB[jb], cbz)) + accB[jb * 32 + lane] + accB[(3 * NB + jb) * 32 + lane];
-                    int ar = acc_init(__fadd_rn(parB[NB + jb], cbr)) + accB[(NB + jb) * 32 + lane] + accB[(3 * NB + NB + jb) * 32 + lane];
-                    int ah = acc_init(__fadd_rn(parB[2 * NB + jb], cbh)) + accB[(2 * NB + jb) * 32 + lane] + accB[(3 * NB + 2 * NB + jb) * 32 + lane];
-                    int rz = acc_init(parB[3 * NB + jb]), rr = acc_init(parB[4 * NB + jb]), rh = acc_init(parB[5 * NB + jb]);
-                    const uint32_t xw[4] = {x0, x1, x2, x3};
+                    const uint32_t xw[4] = {xbc[lane], xbc[32 + lane], xbc[64 + lane], xbc[96 + lane]};
+                    uint8_t *xbn = reinterpret_cast<uint8_t *>(xbw + nxt * 4 * 32);
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        rz = dp4a_us(xw[k], *reinterpret_cast<const int *>(wBrec + (((jb >> 3) * 4 + k) * 8 + (jb & 7)) * 4), rz);
-                        rr = dp4a_us(xw[k], *reinterpret_cast<const int *>(wBrec + ((((NB + jb) >> 3) * 4 + k) * 8 + ((NB + jb) & 7)) * 4), rr);
-                        rh = dp4a_us(xw[k], *reinterpret_cast<const int *>(wBrec + ((((2 * NB + jb) >> 3) * 4 + k) * 8 + ((2 * NB + jb) & 7)) * 4), rh);
+                    for (int k2 = 0; k2 < NBW; k2++) {
+                        const int jb = warp + k2 * NWC;
+                        if (jb >= NB) break;
+                        int az = acc_init(__fadd_rn(parB[jb], cbz[k2])), ar = acc_init(__fadd_rn(parB[NB + jb], cbr[k2])), ah = acc_init(__fadd_rn(parB[2 * NB + jb], cbh[k2]));
+#pragma unroll
+                        for (int kp = 0; kp < KPARTS; kp++) {
+                            az += accB[(kp * 3 * NB + jb) * 32 + lane];
+                            ar += accB[(kp * 3 * NB + NB + jb) * 32 + lane];
+                            ah += accB[(kp * 3 * NB + 2 * NB + jb) * 32 + lane];
+                        }
+                        int rz = acc_init(parB[3 * NB + jb]), rr = acc_init(parB[4 * NB + jb]), rh = acc_init(parB[5 * NB + jb]);
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {    // W_rec layout [out/8][in/4][8][4] (dump_lpcnet.py:58-59)
+                            rz = dp4a_us(xw[k], *reinterpret_cast<const int *>(wBrec + (((jb >> 3) * 4 + k) * 8 + (jb & 7)) * 4), rz);
+                            rr = dp4a_us(xw[k], *reinterpret_cast<const int *>(wBrec + ((((NB + jb) >> 3) * 4 + k) * 8 + ((NB + jb) & 7)) * 4), rr);
+                            rh = dp4a_us(xw[k], *reinterpret_cast<const int *>(wBrec + ((((2 * NB + jb) >> 3) * 4 + k) * 8 + ((2 * NB + jb) & 7)) * 4), rh);
+                        }
+                        const float zz = sigmoid_approx(__fadd_rn(acc_finish(az), acc_finish(rz)), rcp);
+                        const float rrr = sigmoid_approx(__fadd_rn(acc_finish(ar), acc_finish(rr)), rcp);
+                        const float hh = tanh_approx(__fadd_rn(acc_finish(ah), __fmul_rn(acc_finish(rh), rrr)), rcp);
+                        hb[k2] = __fadd_rn(__fmul_rn(zz, hb[k2]), __fmul_rn(__fsub_rn(1.f, zz), hh));
+                        hBs[jb * 32 + lane] = hb[k2];
+                        xbn[((jb >> 2) * 32 + lane) * 4 + (jb & 3)] = (uint8_t)quant_u8(hb[k2]);
                     }
-                    const float zz = sigmoid_approx(__fadd_rn(acc_finish(az), acc_finish(rz)), rcp);
-                    const float rrr = sigmoid_approx(__fadd_rn(acc_finish(ar), acc_finish(rr)), rcp);
-                    const float hh = tanh_approx(__fadd_rn(acc_finish(ah), __fmul_rn(acc_finish(rh), rrr)), rcp);
-                    hb = __fadd_rn(__fmul_rn(zz, hb), __fmul_rn(__fsub_rn(1.f, zz), hh));
-                    hBs[jb * 32 + lane] = hb;
-                    reinterpret_cast<uint8_t *>(xbw + nxt * 4 * 32)[((jb >> 2) * 32 + lane) * 4 + (jb & 3)] = (uint8_t)quant_u8(hb);
                 }
                 __threadfence_block();
-                bar_arrive(BAR_HB, SAMPLE_THREADS);                      // GRU_B state of this step is in hBs
+                bar_arrive(BAR_HB, CNT_HB);                              // GRU_B state of this sample is in hBs
             }
         }
         // ---- save the recurrent state ----
@@ -309,7 +389,27 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
             for (int sl = 0; sl < GPW; sl++)
 #pragma unroll
                 for (int i = 0; i < 8; i++) P.hA[(size_t)(8 * grp[sl] + i) * n + s] = h[sl][i];
-            P.hB[(size_t)jb * n + s] = hb;
+#pragma unroll
+            for (int k = 0; k < NBW; k++) if (warp + k * NWC < NB) P.hB[(size_t)(warp + k * NWC) * n + s] = hb[k];
+        }
+    } else if (warp < NWC + NWP) {
+        // =====================================================  producer warps  =====================================================
+        const int p = warp - NWC;
+        for (int f = 0; f < P.nframes; f++) {
+            const float *condA_f = P.condA + (size_t)f * n * (3 * NA);
+            for (int t = 0; t < spf; t++) {
+                bar_sync(BAR_IDX, CNT_IDX);                              // indices of this sample are in idx_s
+                gather_slice<3>(tile0, condA_f, n, cta_s0, P.emb_sig, P.emb_pred, P.emb_exc, idx_s, 1, p, lane);   // gate r
+                __threadfence_block();
+                bar_arrive(BAR_FULL0, CNT_FULL);
+                gather_slice<3>(tile1, condA_f, n, cta_s0, P.emb_sig, P.emb_pred, P.emb_exc, idx_s, 2, p, lane);   // gate h
+                __threadfence_block();
+                bar_arrive(BAR_FULL1, CNT_FULL);
+                bar_sync(BAR_EMPTY0, CNT_FULL);                          // gate r consumed
+                gather_slice<3>(tile0, condA_f, n, cta_s0, P.emb_sig, P.emb_pred, P.emb_exc, idx_s, 0, p, lane);   // gate z
+                __threadfence_block();
+                bar_arrive(BAR_FULL0, CNT_FULL);
+            }
         }
     } else {
         // =====================================================  sampler warp  =====================================================
@@ -319,7 +419,6 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
         const float *fcw = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_FCW);
         const float *fcb = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_FCB);
         const float *fcf = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_FCF);
-        short *pcm_s = reinterpret_cast<short *>(smem + SM_PCM);
 
         float ls[LPC_ORDER], lpc[LPC_ORDER];
 #pragma unroll
@@ -328,6 +427,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
         int last_exc = P.last_exc[s];
         Kiss99 rng;
         rng.z = P.rng[s]; rng.w = P.rng[(size_t)n + s]; rng.jsr = P.rng[2 * (size_t)n + s]; rng.jcong = P.rng[3 * (size_t)n + s];
+        short *pcm_out = P.pcm + (size_t)s * P.pcm_stream_stride;
 
         for (int f = 0; f < P.nframes; f++) {
             {   // frame f uses the LPC computed from the features of frame f-2 (lpcnet.c:110-112), weighted by gamma^i (freq.c:299-308)
@@ -346,7 +446,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
                 idx_s[32 + lane] = lin2ulaw(pred);
                 idx_s[64 + lane] = last_exc;
                 __threadfence_block();
-                bar_arrive(BAR_IDX, SAMPLE_THREADS);
+                bar_arrive(BAR_IDX, CNT_IDX);
                 // thresholds (nnet.c:178-184): two RNG words -> 8 logits; does not depend on the network
                 float thr[8];
                 {
@@ -354,7 +454,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
                     thr[0] = logit[r0 & 0xFF]; thr[1] = logit[(r0 >> 8) & 0xFF]; thr[2] = logit[(r0 >> 16) & 0xFF]; thr[3] = logit[r0 >> 24];
                     thr[4] = logit[r1 & 0xFF]; thr[5] = logit[(r1 >> 8) & 0xFF]; thr[6] = logit[(r1 >> 16) & 0xFF]; thr[7] = logit[r1 >> 24];
                 }
-                bar_sync(BAR_HB, SAMPLE_THREADS);                        // wait for GRU_B
+                bar_sync(BAR_HB, CNT_HB);                                // wait for GRU_B
                 float hbv[NB];
 #pragma unroll
                 for (int j = 0; j < NB; j++) hbv[j] = hBs[j * 32 + lane];
@@ -362,12 +462,33 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
 #pragma unroll
                 for (int b = 0; b < 8; b++) {                            // sample_mdense, nnet.c:186-211
                     const int i = (1 << b) | val;
-                    const float *wr = fcw + i * FCW_ROW;
                     float sum1 = fcb[i], sum2 = fcb[256 + i];
+                    // two sequential 16-term chains (one per channel), fed 8 weights at a time to keep the live set small
+                    if (b < 6) {                                         // nodes < 64: weights in shared memory (rows padded to 36 floats)
+                        const float *wr = fcw + i * FCW_ROW;
 #pragma unroll
-                    for (int j = 0; j < NB; j++) {
-                        sum1 = __fadd_rn(sum1, __fmul_rn(wr[j], hbv[j]));
-                        sum2 = __fadd_rn(sum2, __fmul_rn(wr[NB + j], hbv[j]));
+                        for (int j0 = 0; j0 < NB; j0 += 8) {
+                            const float4 a0 = *reinterpret_cast<const float4 *>(wr + j0), a1 = *reinterpret_cast<const float4 *>(wr + j0 + 4);
+                            const float4 c0 = *reinterpret_cast<const float4 *>(wr + NB + j0), c1 = *reinterpret_cast<const float4 *>(wr + NB + j0 + 4);
+                            const float wa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, wc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                sum1 = __fadd_rn(sum1, __fmul_rn(wa[j], hbv[j0 + j]));
+                                sum2 = __fadd_rn(sum2, __fmul_rn(wc[j], hbv[j0 + j]));
+                            }
+                        }
+                    } else {                                             // lower levels: one 128-byte row per lane from global (L2-resident)
+                        const float *wr = P.fcw + i * 32;
+#pragma unroll
+                        for (int j0 = 0; j0 < NB; j0 += 8) {
+                            const float4 a0 = ldg4(wr + j0), a1 = ldg4(wr + j0 + 4), c0 = ldg4(wr + NB + j0), c1 = ldg4(wr + NB + j0 + 4);
+                            const float wa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, wc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                sum1 = __fadd_rn(sum1, __fmul_rn(wa[j], hbv[j0 + j]));
+                                sum2 = __fadd_rn(sum2, __fmul_rn(wc[j], hbv[j0 + j]));
+                            }
+                        }
                     }
                     sum1 = __fmul_rn(fcf[i], tanh_approx(sum1, rcp));
                     sum2 = __fmul_rn(fcf[256 + i], tanh_approx(sum2, rcp));
@@ -384,17 +505,8 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
                 deemph = pcm;
                 if (pcm < -32767) pcm = -32767;
                 if (pcm > 32767) pcm = 32767;
-                pcm_s[lane * PCM_ROW + t] = (short)__double2int_rd(0.5 + (double)pcm);   // (int)floor(.5 + pcm)
+                if (live) pcm_out[(size_t)f * spf + t] = (short)__double2int_rd(0.5 + (double)pcm);   // (int)floor(.5 + pcm)
             }
-            // ---- flush the frame's PCM tile: 32 streams x spf samples, coalesced along time ----
-            __syncwarp();
-            for (int ss = 0; ss < STREAMS_PER_CTA; ss++) {
-                const int sg = blockIdx.x * STREAMS_PER_CTA + ss;
-                if (sg >= n) break;
-                short *dst = P.pcm + (size_t)sg * P.pcm_stream_stride + (size_t)f * spf;
-                for (int t = lane; t < spf; t += 32) dst[t] = pcm_s[ss * PCM_ROW + t];
-            }
-            __syncwarp();
         }
         if (live) {
 #pragma unroll

@@ -48,7 +48,7 @@ def test_no_cpu_fallback_without_gpu(L):
 
 def _image(L, blob):
     out = np.zeros(256 * 1024, np.uint8)
-    lay = np.zeros(16, np.uint32)
+    lay = np.zeros(24, np.uint32)
     L.lpcnet_b200_debug_image.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
     r = L.lpcnet_b200_debug_image(blob, len(blob), out.ctypes.data, out.size, lay.ctypes.data)
     return r, out, lay
@@ -73,7 +73,7 @@ def test_smem_image_replays_to_the_dense_model(L):
     common, only8, _ = gen_model.make_model()
     arrs = {n: a for n, _, a in common + only8}
     r, img, lay = _image(L, H.blob("int8"))
-    wA, metaA, wB, metaB, image_bytes, total, nA, nB, SM_IMAGE, PARA, DIRA, GRPA, DIRB, WBREC, PARB, FCW = [int(v) for v in lay]
+    wA, metaA, wB, metaB, image_bytes, total, nA, nB, SM_IMAGE, PARA, DIRA, GRPA, DIRB, WBREC, PARB, FCW, NWC, GPW, FCN, KP = [int(v) for v in lay[:20]]
     assert r == image_bytes and total <= 227 * 1024 and total == SM_IMAGE + image_bytes
     img = img[:image_bytes]
     rel = lambda o: o - SM_IMAGE
@@ -92,17 +92,17 @@ def test_smem_image_replays_to_the_dense_model(L):
     x = rng.integers(0, 255, 384).astype(np.int32)
     want_A, want_B = MA @ x, MB @ x
 
-    dirA = img[DIRA:DIRA + 16 * 3 * 3 * 2 * 4].view(np.uint32).reshape(16, 3, 3, 2)
-    grpA = img[GRPA:GRPA + 16 * 3 * 4].view(np.uint32).reshape(16, 3)
-    parA = img[PARA:PARA + 16 * 3 * 3 * 16 * 4].view(np.float32).reshape(16, 3, 3, 2, 8)
+    dirA = img[DIRA:DIRA + NWC * GPW * 3 * 2 * 4].view(np.uint32).reshape(NWC, GPW, 3, 2)
+    grpA = img[GRPA:GRPA + NWC * GPW * 4].view(np.uint32).reshape(NWC, GPW)
+    parA = img[PARA:PARA + NWC * GPW * 3 * 16 * 4].view(np.float32).reshape(NWC, GPW, 3, 2, 8)
     wAi = img[rel(wA):rel(wA) + nA * 32].view(np.int8).astype(np.int32).reshape(nA, 8, 4)
     mA = img[rel(metaA):rel(metaA) + nA * 2].view(np.uint16)
     assert sorted(grpA.reshape(-1).tolist()) == list(range(48))           # every neuron group owned exactly once
     got = np.zeros(1152, np.int64)
     loads = []
-    for w in range(16):
+    for w in range(NWC):
         tot = 0
-        for sl in range(3):
+        for sl in range(GPW):
             g = int(grpA[w, sl])
             for q in range(3):
                 b0, nb = int(dirA[w, sl, q, 0]), int(dirA[w, sl, q, 1])
@@ -116,14 +116,14 @@ def test_smem_image_replays_to_the_dense_model(L):
                 np.testing.assert_array_equal(parA[w, sl, q, 1], arrs["sparse_gru_a_recurrent_weights_diag"][q * 384 + 8 * g:q * 384 + 8 * g + 8])
         loads.append(tot)
     np.testing.assert_array_equal(got, want_A)
-    assert max(loads) <= 1.15 * (sum(loads) / 16)                          # LPT balancing of the 16 compute warps
+    assert max(loads) <= 1.15 * (sum(loads) / NWC)                         # LPT balancing of the compute warps
 
-    dirB = img[DIRB:DIRB + 12 * 2 * 4].view(np.uint32).reshape(6, 2, 2)
+    dirB = img[DIRB:DIRB + 6 * KP * 2 * 4].view(np.uint32).reshape(6, KP, 2)
     wBi = img[rel(wB):rel(wB) + nB * 32].view(np.int8).astype(np.int32).reshape(nB, 8, 4)
     mB = img[rel(metaB):rel(metaB) + nB * 2].view(np.uint16)
     gotB = np.zeros(48, np.int64)
     for rg in range(6):
-        for half in range(2):
+        for half in range(KP):
             b0, nb = int(dirB[rg, half, 0]), int(dirB[rg, half, 1])
             for b in range(b0, b0 + nb):
                 pos = int(mB[b]) // 128 * 4
@@ -132,8 +132,8 @@ def test_smem_image_replays_to_the_dense_model(L):
     # GRU_B recurrent block layout [out/8][in/4][8][4] and su-biases
     np.testing.assert_array_equal(img[WBREC:WBREC + 768].view(np.int8), arrs["gru_b_recurrent_weights"])
     np.testing.assert_array_equal(img[PARB:PARB + 96 * 4].view(np.float32), arrs["gru_b_subias"].reshape(-1))
-    fcw = img[FCW:FCW + 256 * 33 * 4].view(np.float32).reshape(256, 33)
-    np.testing.assert_array_equal(fcw[:, :32], arrs["dual_fc_weights"].reshape(256, 32))
+    fcw = img[FCW:FCW + FCN * 36 * 4].view(np.float32).reshape(FCN, 36)
+    np.testing.assert_array_equal(fcw[:, :32], arrs["dual_fc_weights"].reshape(256, 32)[:FCN])
 
 
 def test_python_mirror_matches_reference_operator_names():
