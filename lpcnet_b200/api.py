@@ -3,7 +3,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "liblpcnet_b200.so")
+_SO = os.environ.get("LPCNET_B200_SO") or os.path.join(_HERE, "liblpcnet_b200.so")   # env override: tuning variants only
 c_p = ctypes.c_void_p
 
 

@@ -22,6 +22,26 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(name, defines):
+    """Tuning aid: build lpcnet_b200/variants/lib_<name>.so with extra -D flags (e.g. LPCNET_NWC=12)."""
+    vdir = os.path.join(HERE, "variants")
+    os.makedirs(os.path.join(vdir, "obj_" + name), exist_ok=True)
+    objs = []
+    for s in SOURCES:
+        o = os.path.join(vdir, "obj_" + name, s.replace(".cu", ".o"))
+        cmd = [NVCC] + FLAGS + ["-D%s" % d for d in defines] + ["-c", os.path.join(CSRC, s), "-o", o]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("nvcc failed on " + s)
+        if s == "sample_kernel.cu":
+            print(name, [l.strip() for l in r.stderr.splitlines() if "registers" in l or "spill" in l][-2:])
+        objs.append(o)
+    so = os.path.join(vdir, "lib_%s.so" % name)
+    subprocess.check_call([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", so] + objs + ["-lcudart"])
+    return so
+
+
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return SO

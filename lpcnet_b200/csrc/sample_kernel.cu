@@ -31,6 +31,10 @@
 #include "engine.h"
 #include "devmath.cuh"
 
+#ifndef LPCNET_GB
+#define LPCNET_GB 3      // units (4 LDG.128 each) a producer lane keeps in flight
+#endif
+
 namespace lpcnet_b200 {
 
 namespace {
@@ -117,15 +121,15 @@ __device__ __forceinline__ void mac_block(int acc[8], uint32_t x, const int4 &w0
 __device__ __forceinline__ void gemv_blocks(int acc[8], uint32_t w /* smem addr */, uint32_t meta /* smem addr */,
                                             int nb /* even */, uint32_t xs_lane /* smem addr */)
 {
-    uint32_t mA = lds16(meta), mB = lds16(meta + 2);
-    uint32_t xA = lds32(xs_lane + mA);
+    uint32_t mAB = lds32(meta);                          // two u16 row offsets per word (lists start on even block indices)
+    uint32_t xA = lds32(xs_lane + (mAB & 0xFFFFu));
     int4 a0 = lds128(w), a1 = lds128(w + 16);
     for (int b = 0; b < nb; b += 2) {
-        const uint32_t xB = lds32(xs_lane + mB);
+        const uint32_t xB = lds32(xs_lane + (mAB >> 16));
         const int4 b0 = lds128(w + 32), b1 = lds128(w + 48);
-        mA = lds16(meta + 4); mB = lds16(meta + 6);
+        mAB = lds32(meta + 4);
         mac_block(acc, xA, a0, a1);
-        xA = lds32(xs_lane + mA);
+        xA = lds32(xs_lane + (mAB & 0xFFFFu));
         a0 = lds128(w + 64); a1 = lds128(w + 80);
         mac_block(acc, xB, b0, b1);
         w += 64; meta += 4;
@@ -399,14 +403,14 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
             const float *condA_f = P.condA + (size_t)f * n * (3 * NA);
             for (int t = 0; t < spf; t++) {
                 bar_sync(BAR_IDX, CNT_IDX);                              // indices of this sample are in idx_s
-                gather_slice<3>(tile0, condA_f, n, cta_s0, P.emb_sig, P.emb_pred, P.emb_exc, idx_s, 1, p, lane);   // gate r
+                gather_slice<LPCNET_GB>(tile0, condA_f, n, cta_s0, P.emb_sig, P.emb_pred, P.emb_exc, idx_s, 1, p, lane);   // gate r
                 __threadfence_block();
                 bar_arrive(BAR_FULL0, CNT_FULL);
-                gather_slice<3>(tile1, condA_f, n, cta_s0, P.emb_sig, P.emb_pred, P.emb_exc, idx_s, 2, p, lane);   // gate h
+                gather_slice<LPCNET_GB>(tile1, condA_f, n, cta_s0, P.emb_sig, P.emb_pred, P.emb_exc, idx_s, 2, p, lane);   // gate h
                 __threadfence_block();
                 bar_arrive(BAR_FULL1, CNT_FULL);
                 bar_sync(BAR_EMPTY0, CNT_FULL);                          // gate r consumed
-                gather_slice<3>(tile0, condA_f, n, cta_s0, P.emb_sig, P.emb_pred, P.emb_exc, idx_s, 0, p, lane);   // gate z
+                gather_slice<LPCNET_GB>(tile0, condA_f, n, cta_s0, P.emb_sig, P.emb_pred, P.emb_exc, idx_s, 0, p, lane);   // gate z
                 __threadfence_block();
                 bar_arrive(BAR_FULL0, CNT_FULL);
             }
