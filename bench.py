@@ -94,6 +94,17 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(load)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic_per_sample():
+    """DRAM bytes per synthesized sample of the per-sample kernel, from the most recent committed `ncu --set full`
+    capture (profiles/*_traffic.json, written by tools/ncu_summary.py).  None if no capture is committed."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    if not files:
+        return None, None
+    d = json.load(open(files[-1]))
+    return float(d["dram_bytes"]) / float(d["samples_in_launch"]), os.path.basename(files[-1])
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -263,6 +274,7 @@ def main():
         # the one real exchange of the path: gather the PCM shards to rank 0 over NCCL (timed separately, device events)
         from lpcnet_b200.sharding import gather_pcm
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gather_pcm(pcm_t, n * world, dist, dst=0)                # untimed: first collective sets up the NCCL channels
         dist.barrier(); torch.cuda.synchronize()
         e0.record()
         full = gather_pcm(pcm_t, n * world, dist, dst=0)
@@ -283,6 +295,7 @@ def main():
         achieved = samples_launch * algo_total / (kms * 1e-3) / 1e9
         sm_mhz = clk.get("sm_mhz") or 1965.0
         smem_peak = 128.0 * 148 * sm_mhz * 1e6 / 1e9          # nominal 128 B/clk/SM at the clock observed under load
+        tps, tsrc = ncu_traffic_per_sample()
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -293,7 +306,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(fbytes), "d2h_bytes_per_step": int(pbytes), "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": int(launches),
             "clocks": clk,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": (tps * samples_launch if tps is not None else None), "traffic_source": tsrc,
                          "peak_source": peak_src, "kernel": "lpcnet_sample_kernel", "kernel_ms_per_launch": kms, "kernel_share_of_step": kms * args.steps / (dev_s * 1e3),
                          "algorithmic_bytes_per_sample": algo_total, "sparse_gemv_bytes_per_sample": algo_sparse,
                          "level_serving_the_bytes": "shared memory (weights resident per SM) + L2 (embedding rows)",

@@ -203,7 +203,7 @@ static int synth_device(LPCNetB200Batch *b, const float *d_feat, long long strea
                 while ((int)b->kev->size() < b->kev_used + 2) { cudaEvent_t e; CK(cudaEventCreate(&e)); b->kev->push_back(e); }
                 CK(cudaEventRecord((*b->kev)[b->kev_used], st));
             }
-            CK(launch_sample_kernel(p, st));
+            CK(b->model.is_float ? launch_sample_kernel_f32(p, st) : launch_sample_kernel(p, st));
             launches += 1;
             if (time_it) { CK(cudaEventRecord((*b->kev)[b->kev_used + 1], st)); b->kev_used += 2; }
         }
@@ -401,7 +401,7 @@ int lpcnet_b200_debug_image(const unsigned char *blob, int len, unsigned char *o
     int r = debug_build_image(blob, len, out, cap, &L);
     if (r < 0) return r;
     layout[0] = L.wA; layout[1] = L.metaA; layout[2] = L.wB; layout[3] = L.metaB; layout[4] = L.image_bytes; layout[5] = L.total_bytes;
-    layout[6] = L.nblkA_padded; layout[7] = L.nblkB_padded; layout[8] = SM_IMAGE;
+    layout[6] = L.nblkA_padded; layout[7] = L.nblkB_padded; layout[8] = L.sm_image;
     layout[9] = IM_PARA; layout[10] = IM_DIRA; layout[11] = IM_GRPA; layout[12] = IM_DIRB; layout[13] = IM_WBREC; layout[14] = IM_PARB;
     layout[15] = IM_FCW; layout[16] = NWC; layout[17] = GPW; layout[18] = FCW_SMEM_NODES; layout[19] = KPARTS;
     return r;

@@ -82,11 +82,39 @@ constexpr uint32_t IM_WBREC = IM_DIRB + NWB * 2 * 4;               // int8 [6][4
 constexpr uint32_t IM_PARB  = IM_WBREC + 3 * NB * NB;              // float [96]: input-side su-bias[48], recurrent-side su-bias[48]
 constexpr uint32_t IM_VAR   = al128(IM_PARB + 6 * NB * 4);         // start of the variable-size arrays
 
+// ---- shared-memory map of the FLOAT-flavour per-sample kernel (sample_kernel_f32.cu) ----
+// fp32 GRU_A state tile instead of the u8 one, no gather tiles (per-lane gather), fp16 weights (64 B per block),
+// the whole dual_fc table read from global memory.
+constexpr uint32_t F_XS    = 0;                                    // float [384][32]: GRU_A state of the 32 streams (single buffer)
+constexpr uint32_t F_HB    = F_XS + NA * 32 * 4;                   // float [2][16][32]: GRU_B state (double-buffered)
+constexpr uint32_t F_ACCB  = F_HB + 2 * NB * 32 * 4;                   // float [48][32]: GRU_B input-side pre-activations
+constexpr uint32_t F_IDX   = F_ACCB + 3 * NB * 32 * 4;             // int32 [3][32]
+constexpr uint32_t F_MBAR  = al128(F_IDX + 3 * 32 * 4);
+constexpr uint32_t F_IMAGE = F_MBAR + 128;
+constexpr uint32_t FI_RCP   = 0;                                   // u16 [2048]
+constexpr uint32_t FI_LOGIT = FI_RCP + 2048 * 2;
+constexpr uint32_t FI_U2L   = FI_LOGIT + 256 * 4;
+constexpr uint32_t FI_FCB   = FI_U2L + 256 * 4;
+constexpr uint32_t FI_FCF   = FI_FCB + 512 * 4;
+constexpr uint32_t FI_PARA  = FI_FCF + 512 * 4;                    // float [NWC][GPW][3][16] = recurrent bias[8], diag[8]
+constexpr uint32_t FI_DIRA  = FI_PARA + NWC * GPW * 3 * 16 * 4;
+constexpr uint32_t FI_GRPA  = FI_DIRA + NWC * GPW * 3 * 2 * 4;
+constexpr uint32_t FI_DIRB  = FI_GRPA + NWC * GPW * 4;             // uint32 [6*KPARTS][2] (only part 0 of each row group is non-empty)
+constexpr uint32_t FI_PARB  = FI_DIRB + NWB * 2 * 4;               // float [96]: input-side bias[48], recurrent-side bias[48]
+constexpr uint32_t FI_VAR   = al128(FI_PARB + 6 * NB * 4);
+
+// offsets used by the (flavour-agnostic) image builder
+struct ImageMap { uint32_t sm_image, rcp, logit, u2l, fcw, fcb, fcf, parA, dirA, grpA, dirB, wBrec, parB, var; };
+constexpr ImageMap MAP_INT8 = {SM_IMAGE, IM_RCP, IM_LOGIT, IM_U2L, IM_FCW, IM_FCB, IM_FCF, IM_PARA, IM_DIRA, IM_GRPA, IM_DIRB, IM_WBREC, IM_PARB, IM_VAR};
+constexpr ImageMap MAP_F32  = {F_IMAGE, FI_RCP, FI_LOGIT, FI_U2L, 0xFFFFFFFFu, FI_FCB, FI_FCF, FI_PARA, FI_DIRA, FI_GRPA, FI_DIRB, 0xFFFFFFFFu, FI_PARB, FI_VAR};
+
 struct SmemLayout {          // run-time part; offsets are absolute (from the start of dynamic shared memory)
     uint32_t wA;        // int8 GRU_A blocks, 32 B each = [8 out][4 in], ordered (warp, slot, gate, block)
     uint32_t metaA;     // u16 per block: byte offset of the x word-row ((pos/4)*128)
     uint32_t wB;        // int8 GRU_B input blocks, ordered (row group, K half, block)
     uint32_t metaB;     // u16 per block
+    uint32_t wBrecF;    // float flavour only: fp32 [16 in][48 out] GRU_B recurrent weights
+    uint32_t sm_image;  // where the image starts (SM_IMAGE for int8, F_IMAGE for the float flavour)
     uint32_t image_bytes;
     uint32_t total_bytes;
     uint32_t nblkA_padded, nblkB_padded;
@@ -158,6 +186,7 @@ void launch_frame_network(const DeviceModel &m, const FrameState &fs, const floa
 void launch_decode_packets(const DeviceModel &m, const FrameState &fs, const uint8_t *d_packets, int n, int npackets,
                            float *d_features /* [n][4*npackets][20] */, cudaStream_t st);
 cudaError_t launch_sample_kernel(const SampleParams &p, cudaStream_t st);
+cudaError_t launch_sample_kernel_f32(const SampleParams &p, cudaStream_t st);
 int sample_kernel_smem_ok(uint32_t bytes);
 
 }  // namespace lpcnet_b200

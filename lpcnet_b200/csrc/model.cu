@@ -14,6 +14,7 @@
 #include <numeric>
 #include <string>
 #include <vector>
+#include <cuda_fp16.h>
 #include "engine.h"
 
 namespace lpcnet_b200 {
@@ -135,7 +136,20 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
     if (wB->size != (m->is_float ? 128 : 32) * nblkB || wBrec->size != (m->is_float ? 4 : 1) * 3 * NB * NB) {
         set_error("model: gru_b weight sizes inconsistent with the blob flavour"); return -1;
     }
-    if (m->is_float) { set_error("model: float (DISABLE_DOT_PROD) blobs are not supported by this build yet"); return -1; }
+    const int src_blk = m->is_float ? 128 : 32;      // bytes per 8x4 block in the blob
+    const int img_blk = m->is_float ? 64 : 32;       // bytes per block in shared memory (float flavour: fp16 storage)
+    if (m->is_float) {
+        // The float flavour keeps the recurrent weights in shared memory as fp16 (BASELINE config 2): only lossless when
+        // every weight is exactly representable (true for the k/128 weights of quantisation-aware models, lpcnet.py:118-126).
+        auto fp16_exact = [](const unsigned char *d, int bytes) {
+            const float *f = reinterpret_cast<const float *>(d);
+            for (int i = 0; i < bytes / 4; i++) if (__half2float(__float2half_rn(f[i])) != f[i]) return false;
+            return true;
+        };
+        if (!fp16_exact(wA->data, wA->size) || !fp16_exact(wB->data, wB->size)) {
+            set_error("model: float blob whose recurrent weights are not fp16-exact; the fp32-weight variant is not built"); return -1;
+        }
+    }
     m->nblkA = nblkA; m->nblkB = nblkB;
 
     // ---------------- GRU_A: assign the 48 neuron groups to the 16 compute warps (LPT on block count) ----------------
@@ -144,9 +158,9 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
     std::vector<std::vector<Blk>> rowsA(3 * NGRP), rowsB(3 * NB / 8);
     {
         const int *p = idxA; const unsigned char *w = wA->data;
-        for (int rg = 0; rg < 3 * NGRP; rg++) { int nb = *p++; for (int j = 0; j < nb; j++) { rowsA[rg].push_back({*p++, w}); w += 32; } }
+        for (int rg = 0; rg < 3 * NGRP; rg++) { int nb = *p++; for (int j = 0; j < nb; j++) { rowsA[rg].push_back({*p++, w}); w += src_blk; } }
         p = idxB; w = wB->data;
-        for (int rg = 0; rg < 3 * NB / 8; rg++) { int nb = *p++; for (int j = 0; j < nb; j++) { rowsB[rg].push_back({*p++, w}); w += 32; } }
+        for (int rg = 0; rg < 3 * NB / 8; rg++) { int nb = *p++; for (int j = 0; j < nb; j++) { rowsB[rg].push_back({*p++, w}); w += src_blk; } }
     }
     std::vector<int> cost(NGRP), order(NGRP);
     for (int g = 0; g < NGRP; g++) cost[g] = (int)(rowsA[g].size() + rowsA[NGRP + g].size() + rowsA[2 * NGRP + g].size());
@@ -166,7 +180,8 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
     for (int w = 0; w < NWC; w++) for (int s = 0; s < GPW; s++) for (int q = 0; q < 3; q++) nA_pad += padded(rowsA[q * NGRP + grp[w][s]].size());
     // GRU_B input GEMV: warp (rg, part) takes a contiguous KPARTS-th of the row group's block list
     uint32_t dirB_h[NWB][2];
-    auto part_lo = [](size_t n, int k) { return (n * k + KPARTS - 1) / KPARTS; };
+    const bool is_float = m->is_float != 0;
+    auto part_lo = [is_float](size_t n, int k) { return is_float ? (k == 0 ? (size_t)0 : n) : (n * k + KPARTS - 1) / KPARTS; };
     for (int rg = 0; rg < 6; rg++) {
         size_t n = rowsB[rg].size();
         for (int k = 0; k < KPARTS; k++) {
@@ -174,25 +189,34 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
             nB_pad += dirB_h[rg * KPARTS + k][1];
         }
     }
-    uint32_t off = SM_IMAGE + IM_VAR;
+    const ImageMap M = is_float ? MAP_F32 : MAP_INT8;
+    uint32_t off = M.sm_image + M.var;
     auto take = [&](uint32_t bytes, uint32_t align = 16) { off = align_up(off, align); uint32_t o = off; off += bytes; return o; };
     // +2 blocks / +4 meta entries of readable slack behind every array: the pipelined GEMV prefetches past the list end
-    L.wA = take((nA_pad + 2) * 32, 128);
+    L.wA = take((nA_pad + 2) * img_blk, 128);
     L.metaA = take((nA_pad + 4) * 2);
-    L.wB = take((nB_pad + 2) * 32, 128);
+    L.wB = take((nB_pad + 2) * img_blk, 128);
     L.metaB = take((nB_pad + 4) * 2);
+    L.wBrecF = is_float ? take(3 * NB * NB * 4, 16) : 0;
     L.total_bytes = align_up(off, 128);
-    L.image_bytes = L.total_bytes - SM_IMAGE;
+    L.sm_image = M.sm_image;
+    L.image_bytes = L.total_bytes - M.sm_image;
     L.nblkA_padded = nA_pad; L.nblkB_padded = nB_pad;
     if (!sample_kernel_smem_ok(L.total_bytes)) { set_error("model: %u bytes of shared memory needed, more than one SM offers", L.total_bytes); return -1; }
 
     // ---------------- build the image ----------------
     std::vector<uint8_t> img(L.image_bytes, 0);
-    const uint32_t oWA = L.wA - SM_IMAGE, oMA = L.metaA - SM_IMAGE, oWB = L.wB - SM_IMAGE, oMB = L.metaB - SM_IMAGE;
+    auto put_block = [is_float](uint8_t *dst, const unsigned char *src) {
+        if (!is_float) { memcpy(dst, src, 32); return; }
+        const float *f = reinterpret_cast<const float *>(src);          // [4 in][8 out] fp32 -> fp16, same order
+        __half *h = reinterpret_cast<__half *>(dst);
+        for (int i = 0; i < 32; i++) h[i] = __float2half_rn(f[i]);
+    };
+    const uint32_t oWA = L.wA - M.sm_image, oMA = L.metaA - M.sm_image, oWB = L.wB - M.sm_image, oMB = L.metaB - M.sm_image;
     uint16_t *metaA = reinterpret_cast<uint16_t *>(&img[oMA]);
-    float *parA = reinterpret_cast<float *>(&img[IM_PARA]);
-    uint32_t *dirA = reinterpret_cast<uint32_t *>(&img[IM_DIRA]);
-    uint32_t *grpA = reinterpret_cast<uint32_t *>(&img[IM_GRPA]);
+    float *parA = reinterpret_cast<float *>(&img[M.parA]);
+    uint32_t *dirA = reinterpret_cast<uint32_t *>(&img[M.dirA]);
+    uint32_t *grpA = reinterpret_cast<uint32_t *>(&img[M.grpA]);
     uint32_t blk = 0;
     for (int w = 0; w < NWC; w++) for (int s = 0; s < GPW; s++) {
         int g = grp[w][s];
@@ -203,19 +227,19 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
             dirA[((w * GPW + s) * 3 + q) * 2 + 0] = blk;
             dirA[((w * GPW + s) * 3 + q) * 2 + 1] = np;
             for (size_t j = 0; j < lst.size(); j++) {
-                memcpy(&img[oWA + (size_t)(blk + j) * 32], lst[j].w, 32);
-                metaA[blk + j] = (uint16_t)((lst[j].pos / 4) * 128);
+                put_block(&img[oWA + (size_t)(blk + j) * img_blk], lst[j].w);
+                metaA[blk + j] = (uint16_t)(is_float ? lst[j].pos * 128 : (lst[j].pos / 4) * 128);
             }
             blk += np;    // padding blocks stay all-zero (weights 0, x row 0): contribute exactly 0
             float *pp = &parA[((w * GPW + s) * 3 + q) * 16];
             for (int i = 0; i < 8; i++) {
-                pp[i] = ga_subias[3 * NA + q * NA + 8 * g + i];       // recurrent su-bias (nnet.c:426)
+                pp[i] = (is_float ? ga_bias : ga_subias)[3 * NA + q * NA + 8 * g + i];   // recurrent (su-)bias (nnet.c:425-430)
                 pp[8 + i] = ga_diag[q * NA + 8 * g + i];
             }
         }
     }
     uint16_t *metaB = reinterpret_cast<uint16_t *>(&img[oMB]);
-    uint32_t *dirB = reinterpret_cast<uint32_t *>(&img[IM_DIRB]);
+    uint32_t *dirB = reinterpret_cast<uint32_t *>(&img[M.dirB]);
     blk = 0;
     for (int rg = 0; rg < 6; rg++) {
         const auto &lst = rowsB[rg];
@@ -224,35 +248,37 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
             dirB[(rg * KPARTS + k) * 2 + 0] = blk;
             dirB[(rg * KPARTS + k) * 2 + 1] = dirB_h[rg * KPARTS + k][1];
             for (size_t j = b0; j < b1; j++) {
-                memcpy(&img[oWB + (size_t)(blk + (j - b0)) * 32], lst[j].w, 32);
-                metaB[blk + (j - b0)] = (uint16_t)((lst[j].pos / 4) * 128);
+                put_block(&img[oWB + (size_t)(blk + (j - b0)) * img_blk], lst[j].w);
+                metaB[blk + (j - b0)] = (uint16_t)(is_float ? lst[j].pos * 128 : (lst[j].pos / 4) * 128);
             }
             blk += dirB_h[rg * KPARTS + k][1];
         }
     }
-    memcpy(&img[IM_WBREC], wBrec->data, 3 * NB * NB);
+    if (is_float) memcpy(&img[L.wBrecF - M.sm_image], wBrec->data, 3 * NB * NB * 4);    // float [in 16][out 48] (sgemv_accum16 layout)
+    else memcpy(&img[M.wBrec], wBrec->data, 3 * NB * NB);
     {
-        float *pb = reinterpret_cast<float *>(&img[IM_PARB]);
-        for (int i = 0; i < 6 * NB; i++) pb[i] = gb_subias[i];          // nnet.c:346-360 (USE_SU_BIAS)
-        (void)gb_bias; (void)ga_bias;
+        float *pb = reinterpret_cast<float *>(&img[M.parB]);
+        for (int i = 0; i < 6 * NB; i++) pb[i] = (is_float ? gb_bias : gb_subias)[i];   // nnet.c:346-360 (USE_SU_BIAS only with DOT_PROD)
     }
-    memcpy(&img[IM_RCP], kRcpTable, sizeof(kRcpTable));
+    memcpy(&img[M.rcp], kRcpTable, sizeof(kRcpTable));
     {
-        float *lg = reinterpret_cast<float *>(&img[IM_LOGIT]);
+        float *lg = reinterpret_cast<float *>(&img[M.logit]);
         for (int i = 0; i < 256; i++) {                                   // lpcnet.c:188-191 (host libm, double log)
             float prob = .025f + .95f * i / 255.f;
             lg[i] = -log((1 - prob) / prob);
         }
-        float *u2l = reinterpret_cast<float *>(&img[IM_U2L]);
+        float *u2l = reinterpret_cast<float *>(&img[M.u2l]);
         for (int i = 0; i < 256; i++) {                                   // ulaw2lin, common.h:37-45 (double exp)
             float u = (float)i, s, scale_1 = 32768.f / 255.f;
             u = u - 128.f; s = u >= 0.f ? 1.f : -1.f; u = fabs(u);
             u2l[i] = s * scale_1 * (exp(u / 128. * 5.5451774445f) - 1);
         }
-        float *fw = reinterpret_cast<float *>(&img[IM_FCW]);
-        for (int i = 0; i < FCW_SMEM_NODES; i++) for (int j = 0; j < 32; j++) fw[i * FCW_ROW + j] = fc_w[i * 32 + j];
-        memcpy(&img[IM_FCB], fc_b, 512 * 4);
-        memcpy(&img[IM_FCF], fc_f, 512 * 4);
+        if (!is_float) {
+            float *fw = reinterpret_cast<float *>(&img[M.fcw]);
+            for (int i = 0; i < FCW_SMEM_NODES; i++) for (int j = 0; j < 32; j++) fw[i * FCW_ROW + j] = fc_w[i * 32 + j];
+        }
+        memcpy(&img[M.fcb], fc_b, 512 * 4);
+        memcpy(&img[M.fcf], fc_f, 512 * 4);
     }
 
     hm.embed_pitch = embed_pitch; hm.conv1_w = conv1_w; hm.conv1_b = conv1_b; hm.conv2_w = conv2_w; hm.conv2_b = conv2_b;

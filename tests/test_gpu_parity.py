@@ -169,7 +169,7 @@ def test_drop_in_single_stream_api(eng):
         eng.Batch(2, H.blob("int8")[:5000])              # malformed blob -> error, not a crash
 
 
-@pytest.mark.parametrize("n", [1024])
+@pytest.mark.parametrize("n", [1024, 4096])
 def test_full_width_properties(eng, n):
     """BASELINE-sized batch (>=1024 streams): size-independent checks — (i) replicated inputs give replicated
     outputs in every CTA/lane position, (ii) a sample of streams equals the oracle, (iii) determinism across runs."""
@@ -210,3 +210,57 @@ def test_untouched_reference_cli_links_and_runs(eng, tmp_path):
     subprocess.run([exe, "-decode", "pk.bin", "dec.pcm"], cwd=tmp_path, env=env, check=True, timeout=300)
     out = np.frombuffer((tmp_path / "dec.pcm").read_bytes(), dtype=np.int16)
     np.testing.assert_array_equal(out, gdec[1])
+
+
+def test_decode_full_width_properties(eng):
+    """BASELINE config 5 width (1024 streams, lpcnet_decode path): replicated packet streams must give replicated PCM
+    in every CTA / lane position, equal to the oracle's decode of the 8 source streams."""
+    n, P = 1024, 3
+    base = np.stack([make_packets(700 + s, P) for s in range(8)])
+    pk = base[np.arange(n) % 8]
+    b = _batch(eng, n)
+    got = b.decode(pk)
+    want = H.oracle_decode(base, "int8")
+    for s in range(n):
+        if not np.array_equal(got[s], want[s % 8]):
+            raise AssertionError("stream %d differs from its replica source %d at sample %s" % (s, s % 8, np.argwhere(got[s] != want[s % 8])[0]))
+    b.close()
+
+
+def test_device_pointer_api_matches_host_api(eng):
+    """lpcnet_b200_batch_synthesize_device (inputs resident in HBM, the benchmark's `value` path) == host-pointer call."""
+    import ctypes
+    n, T = 40, 7
+    f = make_feature_batch(range(900, 900 + n), T)
+    L = eng.lib()
+    b1, b2 = _batch(eng, n), _batch(eng, n)
+    want = b1.synthesize(f)
+    d_f = L.lpcnet_b200_device_alloc(f.nbytes); d_p = L.lpcnet_b200_device_alloc(want.nbytes)
+    L.lpcnet_b200_memcpy_h2d(d_f, f.ctypes.data, f.nbytes)
+    b2.synthesize_device(d_f, T, 20, d_p)
+    got = np.zeros_like(want)
+    L.lpcnet_b200_memcpy_d2h(got.ctypes.data, d_p, want.nbytes)
+    np.testing.assert_array_equal(got, want)
+    L.lpcnet_b200_device_free(d_f); L.lpcnet_b200_device_free(d_p)
+    b1.close(); b2.close()
+
+
+def test_float_flavour_matches_reference_golden(eng):
+    """BASELINE config 2 arithmetic: the DISABLE_DOT_PROD (float) model flavour with fp16-stored recurrent weights must
+    reproduce the reference's float build (pinned oracle build B) bit for bit — order-sensitive FMA chains included."""
+    gold = np.load(os.path.join(H.GOLDEN, "synth_B.npz"))["pcm"]
+    b = eng.Batch(4, H.blob("float"), lpc_gamma=H.LPC_GAMMA)
+    got = b.synthesize(make_feature_batch(range(4), 40))
+    assert _first_diff(got, gold) is None, "first mismatch (stream, sample) = %s" % (_first_diff(got, gold),)
+    b.close()
+    n, T = 37, 9                                       # ragged batch vs the oracle's float path
+    f = make_feature_batch(range(1200, 1200 + n), T)
+    b = eng.Batch(n, H.blob("float"), lpc_gamma=H.LPC_GAMMA)
+    got = b.synthesize(f)
+    want = H.oracle_synth(f, "float")
+    assert _first_diff(got, want) is None, "first mismatch (stream, sample) = %s" % (_first_diff(got, want),)
+    dig = json.load(open(os.path.join(H.GOLDEN, "digests.json")))
+    b.close()
+    b = eng.Batch(16, H.blob("float"), lpc_gamma=H.LPC_GAMMA)
+    assert hashlib.sha256(b.synthesize(make_feature_batch(range(16), 150)).tobytes()).hexdigest() == dig["synth_B_16x150"]
+    b.close()

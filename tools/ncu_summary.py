@@ -33,6 +33,15 @@ if os.path.exists(rep):
         for key in KEYS:
             if key in d:
                 lines.append("| %s | %s | %s |" % (key, d[key], u[key]))
+        if k == 0 and "lpcnet_sample_kernel" in d.get("Kernel Name", ""):
+            def num(key):
+                v = float(d[key].replace(",", "")); unit = u[key].lower()
+                return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1)
+            grid = int(float(d["launch__grid_size"].replace(",", "")))
+            frames = int(os.environ.get("NCU_FRAMES", "3"))
+            json.dump({"dram_bytes": num("dram__bytes_read.sum") + num("dram__bytes_write.sum"), "grid": grid, "frames": frames,
+                       "samples_in_launch": 4096 * frames * 160, "note": "ncu --set full capture of lpcnet_sample_kernel at 4096 streams x %d frames" % frames},
+                      open(os.path.join(out, "%s_traffic.json" % tag), "w"), indent=1)
         st = sorted(((float(d[h].replace(",", "")), h[len(STALL):-len("_per_issue_active.ratio")]) for h in hdr
                      if h.startswith(STALL) and h.endswith("_per_issue_active.ratio") and d[h]), reverse=True)
         lines += ["", "warp stall reasons (warps stalled per issue-active cycle): " + ", ".join("%s %.2f" % (n, v) for v, n in st[:8]), ""]
