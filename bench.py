@@ -171,7 +171,9 @@ def main():
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="streams per GPU")
+    ap.add_argument("--workload", default="config3_int8", choices=["config3_int8", "config2_float", "config5_decode"],
+                    help="BASELINE config to run; the default (and the driver's) line is config3_int8")
+    ap.add_argument("--streams", type=int, default=0, help="streams per GPU (default: 4096 / 256 / 1024 by workload)")
     ap.add_argument("--frames", type=int, default=FRAMES, help="frames per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -198,12 +200,21 @@ def main():
     if lpcnet_b200.device_count() <= 0:
         raise SystemExit("bench: no CUDA device; this engine has no CPU fallback")
     L = lpcnet_b200.lib()
-    n, F = args.streams, args.frames
-    blob = H.blob("int8")
-    batch = lpcnet_b200.Batch(n, blob, lpc_gamma=LPC_GAMMA, device=local)
+    n = args.streams or {"config3_int8": STREAMS_PER_GPU, "config2_float": 256, "config5_decode": 1024}[args.workload]
+    F = args.frames
+    decode = args.workload == "config5_decode"
+    if decode:
+        F = max(4, F // 4 * 4)                              # whole packets: 4 frames each
+    blob = H.blob("float" if args.workload == "config2_float" else "int8")
+    batch = lpcnet_b200.Batch(n, blob, lpc_gamma=LPC_GAMMA, device=local, codebooks=H.codebooks() if decode else None)
     algo_total, algo_sparse = batch.algorithmic_bytes()
 
-    feats = features_for(n, F, first_stream=64 * rank)
+    if decode:
+        from fixtures import make_packets
+        base = np.stack([make_packets(2000 + 64 * rank + k, F // 4) for k in range(64)])
+        feats = np.ascontiguousarray(base[np.arange(n) % 64])          # "features" = packets [n][F/4][8] uint8
+    else:
+        feats = features_for(n, F, first_stream=64 * rank)
     fbytes, pbytes = feats.nbytes, n * F * 160 * 2
     d_feat = L.lpcnet_b200_device_alloc(fbytes)
     if dist is not None:                                      # under torchrun the PCM buffer is a torch tensor so NCCL can gather it
@@ -225,14 +236,19 @@ def main():
             dist.barrier()
 
     def step_device():
-        batch.synthesize_device(d_feat, F, 20, d_pcm)
+        if decode:
+            batch.decode_device(d_feat, F // 4, d_pcm)
+        else:
+            batch.synthesize_device(d_feat, F, 20, d_pcm)
 
     def step_e2e():
-        if L.lpcnet_b200_batch_synthesize(batch._h, h_feat_p, F, 20, 160, h_pcm_p) != 0:
+        r = (L.lpcnet_b200_batch_decode(batch._h, h_feat_p, F // 4, h_pcm_p) if decode
+             else L.lpcnet_b200_batch_synthesize(batch._h, h_feat_p, F, 20, 160, h_pcm_p))
+        if r != 0:
             raise RuntimeError(L.lpcnet_b200_last_error())
 
     # the first two frames after a reset are silent and skip the sample loop: consume them before anything is timed
-    batch.synthesize_device(d_feat, 2, 20, d_pcm)
+    step_device()
     for _ in range(args.warmup):
         step_device()
 
@@ -299,8 +315,10 @@ def main():
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8*s8->s32 (dp4a) + f32", "data": "synthetic",
-            "config": {"workload": "config3_int8: %d streams/GPU x %d frames x 160 samples per step, int8 block-sparse GRU_A, bit-exact vs reference build A" % (n, F),
+            "dtype": "f32 (fp16-stored weights)" if args.workload == "config2_float" else "u8*s8->s32 (dp4a) + f32", "data": "synthetic",
+            "config": {"workload": {"config3_int8": "config3_int8: %d streams/GPU x %d frames x 160 samples per step, int8 block-sparse GRU_A, bit-exact vs reference build A",
+                                    "config2_float": "config2_float: %d streams/GPU x %d frames x 160 samples per step, float GRU arithmetic with fp16-stored weights, bit-exact vs reference build B",
+                                    "config5_decode": "config5_decode: %d streams/GPU x %d frames (8-byte packets -> lpcnet_decode), int8, synthetic VQ codebooks"}[args.workload] % (n, F),
                        "streams_per_gpu": n, "frames_per_step": F, "samples_per_step": samples_step, "parallelism": "streams sharded across GPUs (dp%d), no data-path collective" % world,
                        "l2": "256 MiB memset between timed steps (outside the event bracket)", "x_realtime_per_stream": value / world / n / 16000.0},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(fbytes), "d2h_bytes_per_step": int(pbytes), "ms_per_step": 1e3 * e2e_s / args.steps},
@@ -308,7 +326,7 @@ def main():
             "clocks": clk,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (tps * samples_launch if tps is not None else None), "traffic_source": tsrc,
-                         "peak_source": peak_src, "kernel": "lpcnet_sample_kernel", "kernel_ms_per_launch": kms, "kernel_share_of_step": kms * args.steps / (dev_s * 1e3),
+                         "peak_source": peak_src, "kernel": "lpcnet_sample_kernel_f32" if args.workload == "config2_float" else "lpcnet_sample_kernel", "kernel_ms_per_launch": kms, "kernel_share_of_step": kms * args.steps / (dev_s * 1e3),
                          "algorithmic_bytes_per_sample": algo_total, "sparse_gemv_bytes_per_sample": algo_sparse,
                          "level_serving_the_bytes": "shared memory (weights resident per SM) + L2 (embedding rows)",
                          "smem_peak_gbs_nominal": smem_peak, "frac_of_smem_peak": achieved / smem_peak,

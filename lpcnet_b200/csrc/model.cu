@@ -287,10 +287,13 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
     hm.emb_sig = emb_sig; hm.emb_pred = emb_pred; hm.emb_exc = emb_exc; hm.fc_w = fc_w;
     hm.img.swap(img);
     // algorithmic bytes per synthesized sample
-    m->algo_bytes_sparse = 32L * nblkA + 4L * (3 * NGRP + nblkA);
-    m->algo_bytes_total = m->algo_bytes_sparse + 3 * NA * 4 /*diag*/ + 3 * NA * 4 /*su-bias*/ + 3 * 3 * NA * 4 /*3 embedding rows*/
-                        + 3 * NA * 4 /*gru_a_condition*/ + 32L * nblkB + 4L * (6 + nblkB) + 3 * NB * NB + 6 * NB * 4 + 3 * NB * 4
-                        + 8 * (2 * NB + 2 + 2) * 4 + 32;
+    {   // float flavour: weights are read as fp16 (64 B per block); recurrent GRU_B weights as stored
+        const long bb = is_float ? 64 : 32, wrec = is_float ? 3L * NB * NB * 4 : 3L * NB * NB;
+        m->algo_bytes_sparse = bb * nblkA + 4L * (3 * NGRP + nblkA);
+        m->algo_bytes_total = m->algo_bytes_sparse + 3 * NA * 4 /*diag*/ + 3 * NA * 4 /*bias*/ + 3 * 3 * NA * 4 /*3 embedding rows*/
+                            + 3 * NA * 4 /*gru_a_condition*/ + bb * nblkB + 4L * (6 + nblkB) + wrec + 6 * NB * 4 + 3 * NB * 4
+                            + 8 * (2 * NB + 2 + 2) * 4 + 32;
+    }
     return 0;
 }
 

@@ -20,3 +20,11 @@ timeout 1500 ncu --set full --clock-control none --import-source on -k regex:lpc
     python bench.py --gpus 1 --steps 1 --warmup 3 --frames 3 --no-cpu-baseline > gpurun_out/ncu_full_${TAG}.log 2>&1
 tail -3 gpurun_out/ncu_full_${TAG}.log
 ls -la gpurun_out
+for W in config2_float config5_decode; do
+  timeout 600 python bench.py --gpus 1 --steps 4 --warmup 3 --workload $W --no-cpu-baseline > gpurun_out/bench_${W}_${TAG}.json 2>gpurun_out/bench_${W}_${TAG}.err
+  python - <<PY
+import json
+d=json.loads(open("gpurun_out/bench_${W}_${TAG}.json").read().strip().splitlines()[-1])
+print("$W", {k:d[k] for k in ("value","ms_per_step")}, "e2e", d["e2e"]["value"], d["config"]["workload"][:60])
+PY
+done
