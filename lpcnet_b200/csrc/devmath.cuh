@@ -21,8 +21,10 @@ __device__ __forceinline__ float rcp_emul(float x, const uint16_t *__restrict__ 
 // same with the shared-memory table of the per-sample kernel: tab32[k] = T[k] + 0x3f800000 (no re-assembly needed)
 __device__ __forceinline__ float rcp_emul(float x, const uint32_t *__restrict__ tab32)
 {
-    uint32_t u = __float_as_uint(x);
-    return __uint_as_float(tab32[(u >> 12) & 0x7FFu] - (u & 0x7F800000u));
+    const uint32_t u = __float_as_uint(x);
+    // byte offset of entry (u >> 12) & 0x7FF, formed with one shift + one mask
+    const uint32_t t = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(tab32) + ((u >> 10) & 0x1FFCu));
+    return __uint_as_float(t - (u & 0x7F800000u));
 }
 
 // tanh8_approx (vec_avx.h:393-411)

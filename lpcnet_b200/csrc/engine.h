@@ -68,8 +68,8 @@ constexpr uint32_t SM_MBAR  = al128(SM_IDX + 3 * 32 * 4);          // 8-byte mba
 constexpr uint32_t SM_IMAGE = SM_MBAR + 128;
 static_assert(SM_HBS + NB * 32 * 4 <= SM_IDX, "GRU_B scratch must fit inside the gather tile it aliases");
 // image, fixed part (offsets relative to SM_IMAGE)
-constexpr uint32_t IM_RCP   = 0;                                   // u16 [2048] RCPPS table ((T[k] - 0x3f000000) >> 11)
-constexpr uint32_t IM_LOGIT = IM_RCP + 2048 * 2;                   // float [256] sampling_logit_table
+constexpr uint32_t IM_RCP   = 0;                                   // u32 [2048] RCPPS table, pre-biased: T[k] + 0x3f800000 (one IADD rebuilds the result)
+constexpr uint32_t IM_LOGIT = IM_RCP + 2048 * 4;                   // float [256] sampling_logit_table
 constexpr uint32_t IM_U2L   = IM_LOGIT + 256 * 4;                  // float [256] ulaw2lin
 constexpr uint32_t IM_FCW   = IM_U2L + 256 * 4;                    // float [FCW_SMEM_NODES][FCW_ROW] dual_fc weights of the upper tree levels
 constexpr uint32_t IM_FCB   = IM_FCW + FCW_SMEM_NODES * FCW_ROW * 4;   // float [2][256]

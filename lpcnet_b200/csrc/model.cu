@@ -260,7 +260,11 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
         float *pb = reinterpret_cast<float *>(&img[M.parB]);
         for (int i = 0; i < 6 * NB; i++) pb[i] = (is_float ? gb_bias : gb_subias)[i];   // nnet.c:346-360 (USE_SU_BIAS only with DOT_PROD)
     }
-    memcpy(&img[M.rcp], kRcpTable, sizeof(kRcpTable));
+    if (is_float) memcpy(&img[M.rcp], kRcpTable, sizeof(kRcpTable));
+    else {
+        uint32_t *r32 = reinterpret_cast<uint32_t *>(&img[M.rcp]);
+        for (int k = 0; k < 2048; k++) r32[k] = 0x3f000000u + ((uint32_t)kRcpTable[k] << 11) + 0x3f800000u;
+    }
     {
         float *lg = reinterpret_cast<float *>(&img[M.logit]);
         for (int i = 0; i < 256; i++) {                                   // lpcnet.c:188-191 (host libm, double log)

@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
         }
     }
 
-    const uint16_t *rcp = reinterpret_cast<const uint16_t *>(smem + SM_IMAGE + IM_RCP);
+    const uint32_t *rcp = reinterpret_cast<const uint32_t *>(smem + SM_IMAGE + IM_RCP);
     uint8_t *xs = smem + SM_XS;
     uint32_t *xbw = reinterpret_cast<uint32_t *>(smem + SM_XB);
     int *accB = reinterpret_cast<int *>(smem + SM_ACCB);
