@@ -150,3 +150,14 @@ def test_decode_packet_matches_reference():
         L.oracle_decode_packet(st, fo.ctypes.data, pk[t].ctypes.data)
         np.testing.assert_array_equal(fr.view(np.uint32), fo.view(np.uint32))
     L.oracle_state_destroy(st)
+
+
+def test_rcpps_table_closed_form():
+    """The captured Intel RCPPS table (tests/golden/rcpps_table.bin, compiled into the engine) is exactly
+    T[k] = rint(2^25 / (2k + 4097)) * 2^-13 for the 2048 mantissa bins — evidence that it is a property of the
+    instruction, not of one machine."""
+    t = H.rcp_table().astype(np.int64)
+    k = np.arange(2048, dtype=np.int64)
+    m13 = (2 ** 25 + (2 * k + 4097) // 2) // (2 * k + 4097)            # rint(2^25 / d), d odd => no ties
+    want = (np.float32(1.0) * (m13.astype(np.float64) / 8192.0)).astype(np.float32).view(np.uint32).astype(np.int64)
+    np.testing.assert_array_equal(t, want)
