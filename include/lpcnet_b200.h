@@ -58,7 +58,7 @@ LPCNET_EXPORT int lpcnet_b200_batch_set_codebooks(LPCNetB200Batch *b, const floa
 /* == lpcnet_synthesize() per stream, `nframes` times ==
  * features: [n_streams][nframes][feature_stride] floats (first 20 of each frame used; stride 20 or 36 typical)
  * pcm     : [n_streams][nframes*samples_per_frame] int16
- * samples_per_frame is the reference's N argument (160 in the demo/decoder; any 1..160). */
+ * samples_per_frame is the reference's N argument (160 in the demo/decoder; any N >= 1 like the reference). */
 LPCNET_EXPORT int lpcnet_b200_batch_synthesize(LPCNetB200Batch *b, const float *features, int nframes,
                                                int feature_stride, int samples_per_frame, short *pcm);
 LPCNET_EXPORT int lpcnet_b200_batch_synthesize_device(LPCNetB200Batch *b, const float *d_features, int nframes,

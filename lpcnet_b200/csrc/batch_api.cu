@@ -169,7 +169,7 @@ static int synth_device(LPCNetB200Batch *b, const float *d_feat, long long strea
 {
     if (!b) { set_error("null batch"); return -1; }
     if (nframes <= 0) return 0;
-    if (spf < 1 || spf > FRAME_SIZE) { set_error("samples_per_frame must be in 1..160"); return -1; }
+    if (spf < 1 || spf > 65536) { set_error("samples_per_frame must be in 1..65536"); return -1; }
     if (frame_stride < NB_FEAT) { set_error("feature_stride must be >= 20"); return -1; }
     const int n = b->n;
     const long long pcm_stride = (long long)nframes * spf;

@@ -351,12 +351,25 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
 #pragma unroll
                     for (int i = 0; i < 8; i++) accB[(part * 3 * NB + rgp * 8 + i) * 32 + lane] = acc[i];
                 }
-                bar_sync(BAR_ACCB, CNT_C);
                 // ---------------- GRU_B finish (nnet.c:346-371): neurons warp, warp + NWC, ... ----------------
                 {
                     const uint32_t *xbc = xbw + cur * 4 * 32;
                     const uint32_t xw[4] = {xbc[lane], xbc[32 + lane], xbc[64 + lane], xbc[96 + lane]};
                     uint8_t *xbn = reinterpret_cast<uint8_t *>(xbw + nxt * 4 * 32);
+                    // recurrent side first: it only needs the previous GRU_B state, so it runs while other warps finish their partial sums
+                    int rz[NBW], rr[NBW], rh[NBW];
+#pragma unroll
+                    for (int k2 = 0; k2 < NBW; k2++) {
+                        const int jb = min(warp + k2 * NWC, NB - 1);
+                        rz[k2] = acc_init(parB[3 * NB + jb]); rr[k2] = acc_init(parB[4 * NB + jb]); rh[k2] = acc_init(parB[5 * NB + jb]);
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {    // W_rec layout [out/8][in/4][8][4] (dump_lpcnet.py:58-59)
+                            rz[k2] = dp4a_us(xw[k], *reinterpret_cast<const int *>(wBrec + (((jb >> 3) * 4 + k) * 8 + (jb & 7)) * 4), rz[k2]);
+                            rr[k2] = dp4a_us(xw[k], *reinterpret_cast<const int *>(wBrec + ((((NB + jb) >> 3) * 4 + k) * 8 + ((NB + jb) & 7)) * 4), rr[k2]);
+                            rh[k2] = dp4a_us(xw[k], *reinterpret_cast<const int *>(wBrec + ((((2 * NB + jb) >> 3) * 4 + k) * 8 + ((2 * NB + jb) & 7)) * 4), rh[k2]);
+                        }
+                    }
+                    bar_sync(BAR_ACCB, CNT_C);                           // all K-part partial sums are in accB
 #pragma unroll
                     for (int k2 = 0; k2 < NBW; k2++) {
                         const int jb = warp + k2 * NWC;
@@ -368,16 +381,9 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
                             ar += accB[(kp * 3 * NB + NB + jb) * 32 + lane];
                             ah += accB[(kp * 3 * NB + 2 * NB + jb) * 32 + lane];
                         }
-                        int rz = acc_init(parB[3 * NB + jb]), rr = acc_init(parB[4 * NB + jb]), rh = acc_init(parB[5 * NB + jb]);
-#pragma unroll
-                        for (int k = 0; k < 4; k++) {    // W_rec layout [out/8][in/4][8][4] (dump_lpcnet.py:58-59)
-                            rz = dp4a_us(xw[k], *reinterpret_cast<const int *>(wBrec + (((jb >> 3) * 4 + k) * 8 + (jb & 7)) * 4), rz);
-                            rr = dp4a_us(xw[k], *reinterpret_cast<const int *>(wBrec + ((((NB + jb) >> 3) * 4 + k) * 8 + ((NB + jb) & 7)) * 4), rr);
-                            rh = dp4a_us(xw[k], *reinterpret_cast<const int *>(wBrec + ((((2 * NB + jb) >> 3) * 4 + k) * 8 + ((2 * NB + jb) & 7)) * 4), rh);
-                        }
-                        const float zz = sigmoid_approx(__fadd_rn(acc_finish(az), acc_finish(rz)), rcp);
-                        const float rrr = sigmoid_approx(__fadd_rn(acc_finish(ar), acc_finish(rr)), rcp);
-                        const float hh = tanh_approx(__fadd_rn(acc_finish(ah), __fmul_rn(acc_finish(rh), rrr)), rcp);
+                        const float zz = sigmoid_approx(__fadd_rn(acc_finish(az), acc_finish(rz[k2])), rcp);
+                        const float rrr = sigmoid_approx(__fadd_rn(acc_finish(ar), acc_finish(rr[k2])), rcp);
+                        const float hh = tanh_approx(__fadd_rn(acc_finish(ah), __fmul_rn(acc_finish(rh[k2]), rrr)), rcp);
                         hb[k2] = __fadd_rn(__fmul_rn(zz, hb[k2]), __fmul_rn(__fsub_rn(1.f, zz), hh));
                         hBs[jb * 32 + lane] = hb[k2];
                         xbn[((jb >> 2) * 32 + lane) * 4 + (jb & 3)] = (uint8_t)quant_u8(hb[k2]);

@@ -105,19 +105,20 @@ def test_chunked_calls_equal_one_call_and_state_roundtrip(eng):
     b1.close(); b2.close(); L.oracle_state_destroy(st)
 
 
-def test_partial_frames(eng):
-    """N < 160 samples per call (the PLC uses 80): reference semantics = one feature vector per call, N samples."""
+@pytest.mark.parametrize("N", [80, 1, 250])
+def test_other_samples_per_call(eng, N):
+    """N != 160 samples per call (the PLC uses 80; the reference loop takes any N): one feature vector per call."""
     n, T = 3, 9
     f = make_feature_batch(range(60, 60 + n), T)
     b = _batch(eng, n)
-    got = b.synthesize(f, samples_per_frame=80)
+    got = b.synthesize(f, samples_per_frame=N)
     L = H.oracle_lib()
     for s in range(n):
         st = L.oracle_state_create(H.oracle_model())
-        pcm = np.zeros(80, np.int16)
+        pcm = np.zeros(N, np.int16)
         for t in range(T):
-            L.oracle_synthesize(st, f[s, t].ctypes.data, pcm.ctypes.data, 80)
-            np.testing.assert_array_equal(got[s, t * 80:(t + 1) * 80], pcm)
+            L.oracle_synthesize(st, f[s, t].ctypes.data, pcm.ctypes.data, N)
+            np.testing.assert_array_equal(got[s, t * N:(t + 1) * N], pcm)
         L.oracle_state_destroy(st)
     b.close()
 
