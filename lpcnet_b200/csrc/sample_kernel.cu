@@ -145,38 +145,33 @@ __device__ __forceinline__ void load_gin(float gin[8], const float *__restrict__
 
 // Producer warps: ONE gate's input term for all 32 streams of the CTA,
 //   G[s][k] = ((cond[s][k] + E_sig[a_s][k]) + E_pred[b_s][k]) + E_exc[c_s][k]        (nnet.c:484-491, left to right)
-// cut into 96 units (stream, third-of-the-row): one unit = 128 columns = one 512-byte LDG.128 per source row.
-// Producer p takes units p, p+NWP, ...; B units (4B independent LDG.128 per lane) are in flight at a time.
-template <int B>
+// Producer p serves streams p, p+NWP, ...: per stream the four row pointers are formed once and the 384 columns of the
+// gate are covered by three 512-byte LDG.128 per row (4 L1 lines per request), i.e. 12 independent loads in flight per
+// lane, then 12 fp32 adds and three 512-byte conflict-free STS.128 into the [32][388] tile.
 __device__ __forceinline__ void gather_slice(float *__restrict__ G, const float *__restrict__ cond_f, int n, int cta_s0,
                                              const float *__restrict__ emb_sig, const float *__restrict__ emb_pred,
                                              const float *__restrict__ emb_exc, const int *__restrict__ idx_s,
                                              int gate, int p, int lane)
 {
-    constexpr int UNITS = STREAMS_PER_CTA * 3;
-    for (int u0 = p; u0 < UNITS; u0 += B * NWP) {
-        float4 a[B], b[B], d[B], e[B];
+    const int col = gate * NA + lane * 4;
+    for (int ss = p; ss < STREAMS_PER_CTA; ss += NWP) {
+        const int sg = min(cta_s0 + ss, n - 1);
+        const float *c = cond_f + (size_t)sg * (3 * NA) + col;
+        const float *e0 = emb_sig + idx_s[ss] * (3 * NA) + col;
+        const float *e1 = emb_pred + idx_s[32 + ss] * (3 * NA) + col;
+        const float *e2 = emb_exc + idx_s[64 + ss] * (3 * NA) + col;
+        float4 a[3], b[3], d[3], e[3];
 #pragma unroll
-        for (int j = 0; j < B; j++) {
-            const int u = min(u0 + j * NWP, UNITS - 1);
-            const int ss = u / 3, col = gate * NA + (u % 3) * 128 + lane * 4;
-            const int sg = min(cta_s0 + ss, n - 1);
-            a[j] = ldg4(cond_f + (size_t)sg * (3 * NA) + col);
-            b[j] = ldg4(emb_sig + (size_t)idx_s[ss] * (3 * NA) + col);
-            d[j] = ldg4(emb_pred + (size_t)idx_s[32 + ss] * (3 * NA) + col);
-            e[j] = ldg4(emb_exc + (size_t)idx_s[64 + ss] * (3 * NA) + col);
-        }
+        for (int j = 0; j < 3; j++) { a[j] = ldg4(c + 128 * j); b[j] = ldg4(e0 + 128 * j); d[j] = ldg4(e1 + 128 * j); e[j] = ldg4(e2 + 128 * j); }
+        float *g = G + ss * GIN_ROW + lane * 4;
 #pragma unroll
-        for (int j = 0; j < B; j++) {
-            const int u = u0 + j * NWP;
-            if (u < UNITS) {
-                float4 r;
-                r.x = __fadd_rn(__fadd_rn(__fadd_rn(a[j].x, b[j].x), d[j].x), e[j].x);
-                r.y = __fadd_rn(__fadd_rn(__fadd_rn(a[j].y, b[j].y), d[j].y), e[j].y);
-                r.z = __fadd_rn(__fadd_rn(__fadd_rn(a[j].z, b[j].z), d[j].z), e[j].z);
-                r.w = __fadd_rn(__fadd_rn(__fadd_rn(a[j].w, b[j].w), d[j].w), e[j].w);
-                *reinterpret_cast<float4 *>(G + (u / 3) * GIN_ROW + (u % 3) * 128 + lane * 4) = r;
-            }
+        for (int j = 0; j < 3; j++) {
+            float4 r;
+            r.x = __fadd_rn(__fadd_rn(__fadd_rn(a[j].x, b[j].x), d[j].x), e[j].x);
+            r.y = __fadd_rn(__fadd_rn(__fadd_rn(a[j].y, b[j].y), d[j].y), e[j].y);
+            r.z = __fadd_rn(__fadd_rn(__fadd_rn(a[j].z, b[j].z), d[j].z), e[j].z);
+            r.w = __fadd_rn(__fadd_rn(__fadd_rn(a[j].w, b[j].w), d[j].w), e[j].w);
+            *reinterpret_cast<float4 *>(g + 128 * j) = r;
         }
     }
 }
@@ -409,14 +404,14 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
             const float *condA_f = P.condA + (size_t)f * n * (3 * NA);
             for (int t = 0; t < spf; t++) {
                 bar_sync(BAR_IDX, CNT_IDX);                              // indices of this sample are in idx_s
-                gather_slice<LPCNET_GB>(tile0, condA_f, n, cta_s0, P.emb_sig, P.emb_pred, P.emb_exc, idx_s, 1, p, lane);   // gate r
+                gather_slice(tile0, condA_f, n, cta_s0, P.emb_sig, P.emb_pred, P.emb_exc, idx_s, 1, p, lane);   // gate r
                 __threadfence_block();
                 bar_arrive(BAR_FULL0, CNT_FULL);
-                gather_slice<LPCNET_GB>(tile1, condA_f, n, cta_s0, P.emb_sig, P.emb_pred, P.emb_exc, idx_s, 2, p, lane);   // gate h
+                gather_slice(tile1, condA_f, n, cta_s0, P.emb_sig, P.emb_pred, P.emb_exc, idx_s, 2, p, lane);   // gate h
                 __threadfence_block();
                 bar_arrive(BAR_FULL1, CNT_FULL);
                 bar_sync(BAR_EMPTY0, CNT_FULL);                          // gate r consumed
-                gather_slice<LPCNET_GB>(tile0, condA_f, n, cta_s0, P.emb_sig, P.emb_pred, P.emb_exc, idx_s, 0, p, lane);   // gate z
+                gather_slice(tile0, condA_f, n, cta_s0, P.emb_sig, P.emb_pred, P.emb_exc, idx_s, 0, p, lane);   // gate z
                 __threadfence_block();
                 bar_arrive(BAR_FULL0, CNT_FULL);
             }
