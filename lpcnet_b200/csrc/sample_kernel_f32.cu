@@ -19,10 +19,11 @@
 
 namespace lpcnet_b200 {
 
+#if LPCNET_NWC == 16
 namespace {
 
 constexpr int F_NWC = 16, F_GPW = NGRP / F_NWC, F_THREADS = (F_NWC + 1) * 32;
-static_assert(F_NWC == NWC && F_GPW == GPW, "the float kernel shares the image geometry (NWC x GPW) with the int8 build");
+
 enum { FB_IDX = 1, FB_READ = 2, FB_X = 3, FB_ACCB = 4, FB_HB = 5 };
 
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -299,6 +300,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) lpcnet_sample_kernel_f32(const _
     }
 }
 
+#else   // LPCNET_F32_DISABLED: tuning builds with another compute-warp count do not carry the float flavour
+cudaError_t launch_sample_kernel_f32(const SampleParams &, cudaStream_t) { return cudaErrorNotSupported; }
+#endif
+
+#if LPCNET_NWC == 16
 cudaError_t launch_sample_kernel_f32(const SampleParams &p, cudaStream_t st)
 {
     cudaError_t e = cudaFuncSetAttribute(lpcnet_sample_kernel_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -307,5 +313,7 @@ cudaError_t launch_sample_kernel_f32(const SampleParams &p, cudaStream_t st)
     lpcnet_sample_kernel_f32<<<ctas, F_THREADS, p.L.total_bytes, st>>>(p);
     return cudaGetLastError();
 }
+
+#endif
 
 }  // namespace lpcnet_b200

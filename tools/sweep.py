@@ -13,6 +13,7 @@ VARIANTS = {
     "c24p7b2": ["LPCNET_NWC=24", "LPCNET_NWP=7", "LPCNET_GB=2"],
     "c24p3b3": ["LPCNET_NWC=24", "LPCNET_NWP=3", "LPCNET_GB=3"],
 }
+VARIANTS = {"c16p7": ["LPCNET_NWC=16","LPCNET_NWP=7"], "c24p7": ["LPCNET_NWC=24","LPCNET_NWP=7"], "c24p5": ["LPCNET_NWC=24","LPCNET_NWP=5"], "c12p7": ["LPCNET_NWC=12","LPCNET_NWP=7"], "c12p3": ["LPCNET_NWC=12","LPCNET_NWP=3"]}
 if sys.argv[1] == "build":
     from lpcnet_b200 import build
     for k, v in VARIANTS.items():
