@@ -38,14 +38,31 @@ constexpr int NGRP = NA / 8;                 // 48 groups of 8 neurons (one 8-ro
 constexpr int GPW = NGRP / NWC;              // neuron groups per compute warp
 static_assert(NGRP % NWC == 0, "compute warps must divide the 48 neuron groups");
 constexpr int SAMPLE_THREADS = (NWC + NWP + 1) * 32;   // + 1 sampler warp (tree sampler, LPC filter, u-law, de-emphasis)
-constexpr int XS_BYTES = (NA / 4) * 32 * 4;  // quantised GRU_A state of 32 streams: [96 words][32 lanes]
-constexpr int FCW_ROW = 36;                  // dual_fc rows kept in shared memory are padded 32->36 floats: 144 B stride = 16 mod 128, so the per-lane
-                                             // LDS.128 row reads of lanes on different nodes mostly land in different 4-bank groups
+constexpr int XS_BYTES = (NA / 4) * 32 * 4;  // quantised GRU_A state of 32 streams: [96 column blocks][32 words], see xs_offset()
+constexpr int FCW_ROW = 36;                  // dual_fc row: 32 weights (16 per channel) + {bias0, bias1, factor0, factor1}; 144 B stride = 16 mod 128, so the
+                                             // per-lane LDS.128 row reads of lanes on different nodes mostly land in different 4-bank groups
 constexpr int FCW_SMEM_NODES = 64;           // tree levels 0..5 (nodes 1..63) live in shared memory, levels 6,7 are read from global (L2)
-constexpr int KPARTS = (NWC >= 24) ? 4 : 2;  // K split of the GRU_B input GEMV
+constexpr int KPARTS = 2;                    // K split of the GRU_B input GEMV
 constexpr int NWB = 6 * KPARTS;              // warps used by the GRU_B input GEMV: (row group 0..5) x (K part)
 static_assert(NWB <= NWC, "one (row group, K part) of GRU_B per compute warp");
 constexpr int NBW = (NB + NWC - 1) / NWC;    // GRU_B neurons finished per compute warp
+constexpr int ACCB_ROW = 36;                 // int32 per output row of the GRU_B partial sums (32 streams + 4 pad: the MMA accumulator stores of a warp
+                                             // (rows 2t, columns gid) then fall into 32 different banks)
+
+// ---- int8 flavour: the integer GEMVs run on the tensor cores (mma.sync m16n8k16, u8 x s8 -> s32, exact) ----
+// A "quad" is four 8x4 weight blocks of one 8-row group = one MMA: 16 streams x (4 blocks x 4 inputs) x 8 outputs.
+//   weights: 128 B per quad, word [gid][t] = the 4 int8 weights of output row gid for the block in slot t   (B fragment of lane gid*4+t)
+//   meta   : 4 x u16 per quad, one per slot: xs_offset(column block of the slot, stream 0)
+// Quantised state xs: column block c (inputs 4c..4c+3) is a 128-byte row; the word of stream s sits at
+//   c*128 + (((s & 7) * 16) ^ ((c & 3) * 32)) + (s >> 3) * 4
+// i.e. the four streams {gid, gid+8, gid+16, gid+24} that lane (gid, t) feeds to its two MMAs are one 16-byte vector,
+// and the XOR keeps the four slots of a quad (whose column blocks are ordered to have distinct c & 3 where possible)
+// in different bank groups.
+constexpr uint32_t QUAD_BYTES = 128, QUAD_META_BYTES = 8;
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+constexpr uint32_t xs_offset(uint32_t c, uint32_t s) { return c * 128u + ((((s & 7u) * 16u) ^ ((c & 3u) * 32u))) + (s >> 3) * 4u; }
 
 // ---- shared-memory map of the per-sample kernel ----
 // Everything whose size does not depend on the model's sparsity pattern sits at a COMPILE-TIME offset (keeps the
@@ -53,15 +70,15 @@ constexpr int NBW = (NB + NWC - 1) / NWC;    // GRU_B neurons finished per compu
 // [SM_IMAGE, SM_IMAGE + image_bytes) is copied verbatim from the global "SMEM image" built at model-load time
 // (TMA bulk copies); [0, SM_IMAGE) is the mutable working set.
 constexpr uint32_t al128(uint32_t x) { return (x + 127u) & ~127u; }
-constexpr int GIN_ROW = 388;                                       // floats per stream in a gather tile: 384 + 4 pad => row stride 1552 B
-                                                                   // (= 16 mod 128): per-lane LDS.128 of a quarter-warp hit 8 disjoint 4-bank groups
+constexpr int GIN_ROW = 392;                                       // floats per stream in a gather tile: 384 + 8 pad => row stride = 8 words mod 32:
+                                                                   // the LDS.64 of lanes (gid, t) = row gid, column 2t hit 32 different banks per half-warp
 constexpr uint32_t TILE_BYTES = 32 * GIN_ROW * 4;
-constexpr uint32_t SM_XS    = 0;                                   // 2 x quantised GRU_A state [96 words][32 lanes] (double-buffered)
-constexpr uint32_t SM_XB    = SM_XS + 2 * XS_BYTES;                    // 2 x [4 words][32]: quantised GRU_B state
+constexpr uint32_t SM_XS    = 0;                                   // 2 x quantised GRU_A state (double-buffered)
+constexpr uint32_t SM_XB    = SM_XS + 2 * XS_BYTES;                // 2 x [4 words][32]: quantised GRU_B state
 constexpr uint32_t SM_T0    = SM_XB + 2 * 4 * 32 * 4;              // gather tile 0: gate r, later gate z   (float [32 streams][GIN_ROW])
 constexpr uint32_t SM_T1    = SM_T0 + TILE_BYTES;                  // gather tile 1: gate h
-constexpr uint32_t SM_ACCB  = SM_T1;                               // int32 [KPARTS][48][32] partial sums of the GRU_B input GEMV     } alias tile 1:
-constexpr uint32_t SM_HBS   = SM_ACCB + KPARTS * 3 * NB * 32 * 4;       // float [16][32] GRU_B state for the sampler warp                  } live only between the
+constexpr uint32_t SM_ACCB  = SM_T1;                               // int32 [KPARTS][48][ACCB_ROW] partial sums of the GRU_B input GEMV } alias tile 1:
+constexpr uint32_t SM_HBS   = SM_ACCB + KPARTS * 3 * NB * ACCB_ROW * 4;  // float [16][32] GRU_B state for the sampler warp            } live only between the
                                                                    //                                                                 } h-gate and the next indices
 constexpr uint32_t SM_IDX   = SM_T1 + TILE_BYTES;                  // int32 [3][32]: last_sig_ulaw, pred_ulaw, last_exc
 constexpr uint32_t SM_MBAR  = al128(SM_IDX + 3 * 32 * 4);          // 8-byte mbarrier of the image copy
@@ -71,11 +88,9 @@ static_assert(SM_HBS + NB * 32 * 4 <= SM_IDX, "GRU_B scratch must fit inside the
 constexpr uint32_t IM_RCP   = 0;                                   // u32 [2048] RCPPS table, pre-biased: T[k] + 0x3f800000 (one IADD rebuilds the result)
 constexpr uint32_t IM_LOGIT = IM_RCP + 2048 * 4;                   // float [256] sampling_logit_table
 constexpr uint32_t IM_U2L   = IM_LOGIT + 256 * 4;                  // float [256] ulaw2lin
-constexpr uint32_t IM_FCW   = IM_U2L + 256 * 4;                    // float [FCW_SMEM_NODES][FCW_ROW] dual_fc weights of the upper tree levels
-constexpr uint32_t IM_FCB   = IM_FCW + FCW_SMEM_NODES * FCW_ROW * 4;   // float [2][256]
-constexpr uint32_t IM_FCF   = IM_FCB + 512 * 4;                    // float [2][256]
-constexpr uint32_t IM_PARA  = IM_FCF + 512 * 4;                    // float [NWC][GPW][3 gates][16] = recurrent su-bias[8], diag[8]
-constexpr uint32_t IM_DIRA  = IM_PARA + NWC * GPW * 3 * 16 * 4;    // uint32 [NWC][GPW][3][2] = {first block, padded (even) block count}
+constexpr uint32_t IM_FCW   = IM_U2L + 256 * 4;                    // float [FCW_SMEM_NODES][FCW_ROW] dual_fc rows of the upper tree levels
+constexpr uint32_t IM_PARA  = IM_FCW + FCW_SMEM_NODES * FCW_ROW * 4;   // float [NWC][GPW][3 gates][16] = recurrent su-bias[8], diag[8]
+constexpr uint32_t IM_DIRA  = IM_PARA + NWC * GPW * 3 * 16 * 4;    // uint32 [NWC][GPW][3][2] = {first quad, quad count}
 constexpr uint32_t IM_GRPA  = IM_DIRA + NWC * GPW * 3 * 2 * 4;     // uint32 [NWC][GPW] neuron-group id
 constexpr uint32_t IM_DIRB  = IM_GRPA + NWC * GPW * 4;             // uint32 [NWB][2]
 constexpr uint32_t IM_WBREC = IM_DIRB + NWB * 2 * 4;               // int8 [6][4][8][4] GRU_B recurrent blocks
@@ -105,19 +120,19 @@ constexpr uint32_t FI_VAR   = al128(FI_PARB + 6 * NB * 4);
 
 // offsets used by the (flavour-agnostic) image builder
 struct ImageMap { uint32_t sm_image, rcp, logit, u2l, fcw, fcb, fcf, parA, dirA, grpA, dirB, wBrec, parB, var; };
-constexpr ImageMap MAP_INT8 = {SM_IMAGE, IM_RCP, IM_LOGIT, IM_U2L, IM_FCW, IM_FCB, IM_FCF, IM_PARA, IM_DIRA, IM_GRPA, IM_DIRB, IM_WBREC, IM_PARB, IM_VAR};
+constexpr ImageMap MAP_INT8 = {SM_IMAGE, IM_RCP, IM_LOGIT, IM_U2L, IM_FCW, 0xFFFFFFFFu, 0xFFFFFFFFu, IM_PARA, IM_DIRA, IM_GRPA, IM_DIRB, IM_WBREC, IM_PARB, IM_VAR};
 constexpr ImageMap MAP_F32  = {F_IMAGE, FI_RCP, FI_LOGIT, FI_U2L, 0xFFFFFFFFu, FI_FCB, FI_FCF, FI_PARA, FI_DIRA, FI_GRPA, FI_DIRB, 0xFFFFFFFFu, FI_PARB, FI_VAR};
 
 struct SmemLayout {          // run-time part; offsets are absolute (from the start of dynamic shared memory)
-    uint32_t wA;        // int8 GRU_A blocks, 32 B each = [8 out][4 in], ordered (warp, slot, gate, block)
-    uint32_t metaA;     // u16 per block: byte offset of the x word-row ((pos/4)*128)
-    uint32_t wB;        // int8 GRU_B input blocks, ordered (row group, K half, block)
-    uint32_t metaB;     // u16 per block
+    uint32_t wA;        // GRU_A weights, ordered (warp, slot, gate): int8 flavour 128-byte quads, float flavour 64-byte fp16 blocks
+    uint32_t metaA;     // int8: 4 x u16 per quad (xs_offset of each slot's column block); float: u16 per block
+    uint32_t wB;        // GRU_B input weights, ordered (row group, K part)
+    uint32_t metaB;
     uint32_t wBrecF;    // float flavour only: fp32 [16 in][48 out] GRU_B recurrent weights
     uint32_t sm_image;  // where the image starts (SM_IMAGE for int8, F_IMAGE for the float flavour)
     uint32_t image_bytes;
     uint32_t total_bytes;
-    uint32_t nblkA_padded, nblkB_padded;
+    uint32_t nblkA_padded, nblkB_padded;   // units in wA / wB: quads (int8 flavour) or blocks (float flavour)
 };
 
 // Device-resident model (one per batch; weights replicated per GPU, ~4 MB).
@@ -128,7 +143,7 @@ struct DeviceModel {
     uint8_t *image;                  // [L.image_bytes] global copy of the SMEM image
     // per-sample gathers (L2-resident): [256][3*NA] each
     float *emb_sig, *emb_pred, *emb_exc;
-    float *fcw;                      // dual_fc weights [256][32] (the lower tree levels are read from here)
+    float *fcw;                      // dual_fc rows [256][FCW_ROW] = 32 weights, 2 biases, 2 factors (the lower tree levels are read from here)
     // frame network (fp32, reference layouts kept: column-major W[j*N+i], conv W[(k*in+i)*out+o])
     float *embed_pitch;              // [256][64]
     float *conv1_w, *conv1_b, *conv2_w, *conv2_b;
@@ -151,7 +166,7 @@ struct SampleParams {
     SmemLayout L;
     const uint8_t *image;
     const float *emb_sig, *emb_pred, *emb_exc;
-    const float *fcw;        // [256][32] dual_fc weights (levels 6,7 of the sampling tree)
+    const float *fcw;        // [256][FCW_ROW] dual_fc rows (levels 6,7 of the sampling tree)
     const float *condA;      // [nframes][n][3*NA]
     const float *condB;      // [nframes][n][3*NB]
     const float *lpc_raw;    // [nframes + 2][n][16]  (frame f uses entry f: the LPC of frame f-2)

@@ -7,6 +7,7 @@
 //     owning warp, su-bias/diag per row group, dual_fc, sampler tables) and
 //   * plain device copies of the frame-rate fp32 layers and the three 1.18 MB gather tables.
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -97,8 +98,9 @@ uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
 struct HostModel {               // everything model_load needs after parsing, before any CUDA call
     std::vector<uint8_t> img;
+    std::vector<float> fc_rows;  // [256][FCW_ROW]
     const float *embed_pitch, *conv1_w, *conv1_b, *conv2_w, *conv2_b, *dense1_w, *dense1_b, *dense2_w, *dense2_b;
-    const float *gad_w, *gad_b, *gbd_w, *gbd_b, *emb_sig, *emb_pred, *emb_exc, *fc_w;
+    const float *gad_w, *gad_b, *gbd_w, *gbd_b, *emb_sig, *emb_pred, *emb_exc;
 };
 
 static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *blob, int len, float lpc_gamma)
@@ -174,13 +176,14 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
     }
 
     // ---------------- SMEM layout ----------------
+    // unit of the weight arrays: int8 flavour = quad (4 blocks, one MMA), float flavour = block (lists padded to even length)
     SmemLayout &L = m->L;
-    auto padded = [](size_t n) { return (uint32_t)((n + 1) & ~size_t(1)); };
+    const bool is_float = m->is_float != 0;
+    auto padded = [is_float](size_t n) { return is_float ? (uint32_t)((n + 1) & ~size_t(1)) : (uint32_t)((n + 3) / 4); };
     uint32_t nA_pad = 0, nB_pad = 0;
     for (int w = 0; w < NWC; w++) for (int s = 0; s < GPW; s++) for (int q = 0; q < 3; q++) nA_pad += padded(rowsA[q * NGRP + grp[w][s]].size());
     // GRU_B input GEMV: warp (rg, part) takes a contiguous KPARTS-th of the row group's block list
     uint32_t dirB_h[NWB][2];
-    const bool is_float = m->is_float != 0;
     auto part_lo = [is_float](size_t n, int k) { return is_float ? (k == 0 ? (size_t)0 : n) : (n * k + KPARTS - 1) / KPARTS; };
     for (int rg = 0; rg < 6; rg++) {
         size_t n = rowsB[rg].size();
@@ -192,11 +195,12 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
     const ImageMap M = is_float ? MAP_F32 : MAP_INT8;
     uint32_t off = M.sm_image + M.var;
     auto take = [&](uint32_t bytes, uint32_t align = 16) { off = align_up(off, align); uint32_t o = off; off += bytes; return o; };
-    // +2 blocks / +4 meta entries of readable slack behind every array: the pipelined GEMV prefetches past the list end
-    L.wA = take((nA_pad + 2) * img_blk, 128);
-    L.metaA = take((nA_pad + 4) * 2);
-    L.wB = take((nB_pad + 2) * img_blk, 128);
-    L.metaB = take((nB_pad + 4) * 2);
+    // readable slack behind every array: the pipelined GEMVs prefetch past the list end (values never used)
+    const uint32_t unit_w = is_float ? img_blk : QUAD_BYTES, unit_m = is_float ? 2 : QUAD_META_BYTES, slack_w = 2, slack_m = is_float ? 4 : 2;
+    L.wA = take((nA_pad + slack_w) * unit_w, 128);
+    L.metaA = take((nA_pad + slack_m) * unit_m);
+    L.wB = take((nB_pad + slack_w) * unit_w, 128);
+    L.metaB = take((nB_pad + slack_m) * unit_m);
     L.wBrecF = is_float ? take(3 * NB * NB * 4, 16) : 0;
     L.total_bytes = align_up(off, 128);
     L.sm_image = M.sm_image;
@@ -213,6 +217,42 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
         for (int i = 0; i < 32; i++) h[i] = __float2half_rn(f[i]);
     };
     const uint32_t oWA = L.wA - M.sm_image, oMA = L.metaA - M.sm_image, oWB = L.wB - M.sm_image, oMB = L.metaB - M.sm_image;
+    // int8 flavour: write one block list as quads.  Any order of the blocks gives the same integer sum, so the blocks are
+    // dealt into quads such that the four slots of a quad have column blocks of different (c & 3) classes whenever the
+    // list allows it (the four LDS.128 of a quarter-warp then hit disjoint bank groups, see xs_offset()).  Empty slots
+    // keep zero weights and point at a column block of an unused class.
+    auto put_quads = [&](const Blk *lst, size_t n, uint32_t q0, uint32_t owq, uint32_t omq) {
+        std::vector<int> bucket[4];
+        for (size_t j = 0; j < n; j++) bucket[(lst[j].pos / 4) & 3].push_back((int)j);
+        const uint32_t nq = (uint32_t)((n + 3) / 4);
+        size_t left = n;
+        for (uint32_t q = 0; q < nq; q++) {
+            std::array<int, 4> pick = {-1, -1, -1, -1};
+            bool used[4] = {false, false, false, false};
+            int filled = 0;
+            const size_t later = (size_t)(nq - 1 - q) * 4;                // capacity of the quads after this one
+            const int need = left > later ? (int)(left - later) : 0;      // blocks this quad must take
+            int ord[4] = {0, 1, 2, 3};
+            std::stable_sort(ord, ord + 4, [&](int a, int b) { return bucket[a].size() > bucket[b].size(); });
+            for (int k : ord)                                             // one block per class, largest classes first
+                if (!bucket[k].empty()) { pick[filled++] = bucket[k].back(); bucket[k].pop_back(); used[k] = true; left--; }
+            for (int k : ord)                                             // repeats only when the list forces them
+                while (filled < need && !bucket[k].empty()) { pick[filled++] = bucket[k].back(); bucket[k].pop_back(); left--; }
+            uint8_t *wq = &img[owq + (size_t)(q0 + q) * QUAD_BYTES];
+            uint16_t *mq = reinterpret_cast<uint16_t *>(&img[omq + (size_t)(q0 + q) * QUAD_META_BYTES]);
+            for (int t = 0; t < 4; t++) {
+                if (pick[t] >= 0) {
+                    const unsigned char *src = lst[pick[t]].w;                       // [8 out][4 in] int8
+                    for (int o = 0; o < 8; o++) memcpy(wq + o * 16 + t * 4, src + o * 4, 4);
+                    mq[t] = (uint16_t)xs_offset((uint32_t)lst[pick[t]].pos / 4, 0);
+                } else {
+                    int k = 0; while (k < 3 && used[k]) k++;
+                    used[k] = true;
+                    mq[t] = (uint16_t)xs_offset((uint32_t)k, 0);
+                }
+            }
+        }
+    };
     uint16_t *metaA = reinterpret_cast<uint16_t *>(&img[oMA]);
     float *parA = reinterpret_cast<float *>(&img[M.parA]);
     uint32_t *dirA = reinterpret_cast<uint32_t *>(&img[M.dirA]);
@@ -226,11 +266,13 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
             uint32_t np = padded(lst.size());
             dirA[((w * GPW + s) * 3 + q) * 2 + 0] = blk;
             dirA[((w * GPW + s) * 3 + q) * 2 + 1] = np;
-            for (size_t j = 0; j < lst.size(); j++) {
-                put_block(&img[oWA + (size_t)(blk + j) * img_blk], lst[j].w);
-                metaA[blk + j] = (uint16_t)(is_float ? lst[j].pos * 128 : (lst[j].pos / 4) * 128);
-            }
-            blk += np;    // padding blocks stay all-zero (weights 0, x row 0): contribute exactly 0
+            if (is_float) {
+                for (size_t j = 0; j < lst.size(); j++) {
+                    put_block(&img[oWA + (size_t)(blk + j) * img_blk], lst[j].w);
+                    metaA[blk + j] = (uint16_t)(lst[j].pos * 128);
+                }
+            } else put_quads(lst.data(), lst.size(), blk, oWA, oMA);
+            blk += np;    // padding stays all-zero (weights 0, x row 0): contributes exactly 0
             float *pp = &parA[((w * GPW + s) * 3 + q) * 16];
             for (int i = 0; i < 8; i++) {
                 pp[i] = (is_float ? ga_bias : ga_subias)[3 * NA + q * NA + 8 * g + i];   // recurrent (su-)bias (nnet.c:425-430)
@@ -247,10 +289,12 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
             size_t b0 = part_lo(lst.size(), k), b1 = part_lo(lst.size(), k + 1);
             dirB[(rg * KPARTS + k) * 2 + 0] = blk;
             dirB[(rg * KPARTS + k) * 2 + 1] = dirB_h[rg * KPARTS + k][1];
-            for (size_t j = b0; j < b1; j++) {
-                put_block(&img[oWB + (size_t)(blk + (j - b0)) * img_blk], lst[j].w);
-                metaB[blk + (j - b0)] = (uint16_t)(is_float ? lst[j].pos * 128 : (lst[j].pos / 4) * 128);
-            }
+            if (is_float) {
+                for (size_t j = b0; j < b1; j++) {
+                    put_block(&img[oWB + (size_t)(blk + (j - b0)) * img_blk], lst[j].w);
+                    metaB[blk + (j - b0)] = (uint16_t)(lst[j].pos * 128);
+                }
+            } else put_quads(lst.data() + b0, b1 - b0, blk, oWB, oMB);
             blk += dirB_h[rg * KPARTS + k][1];
         }
     }
@@ -277,18 +321,20 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
             u = u - 128.f; s = u >= 0.f ? 1.f : -1.f; u = fabs(u);
             u2l[i] = s * scale_1 * (exp(u / 128. * 5.5451774445f) - 1);
         }
-        if (!is_float) {
-            float *fw = reinterpret_cast<float *>(&img[M.fcw]);
-            for (int i = 0; i < FCW_SMEM_NODES; i++) for (int j = 0; j < 32; j++) fw[i * FCW_ROW + j] = fc_w[i * 32 + j];
+        hm.fc_rows.resize(256 * FCW_ROW);                                 // node i: 32 weights, bias[2], factor[2] (nnet.c:186-211)
+        for (int i = 0; i < 256; i++) {
+            float *r = &hm.fc_rows[(size_t)i * FCW_ROW];
+            for (int j = 0; j < 32; j++) r[j] = fc_w[i * 32 + j];
+            r[32] = fc_b[i]; r[33] = fc_b[256 + i]; r[34] = fc_f[i]; r[35] = fc_f[256 + i];
         }
-        memcpy(&img[M.fcb], fc_b, 512 * 4);
-        memcpy(&img[M.fcf], fc_f, 512 * 4);
+        if (!is_float) memcpy(&img[M.fcw], hm.fc_rows.data(), (size_t)FCW_SMEM_NODES * FCW_ROW * 4);
+        else { memcpy(&img[M.fcb], fc_b, 512 * 4); memcpy(&img[M.fcf], fc_f, 512 * 4); }
     }
 
     hm.embed_pitch = embed_pitch; hm.conv1_w = conv1_w; hm.conv1_b = conv1_b; hm.conv2_w = conv2_w; hm.conv2_b = conv2_b;
     hm.dense1_w = dense1_w; hm.dense1_b = dense1_b; hm.dense2_w = dense2_w; hm.dense2_b = dense2_b;
     hm.gad_w = gad_w; hm.gad_b = gad_b; hm.gbd_w = gbd_w; hm.gbd_b = gbd_b;
-    hm.emb_sig = emb_sig; hm.emb_pred = emb_pred; hm.emb_exc = emb_exc; hm.fc_w = fc_w;
+    hm.emb_sig = emb_sig; hm.emb_pred = emb_pred; hm.emb_exc = emb_exc;
     hm.img.swap(img);
     // algorithmic bytes per synthesized sample
     {   // float flavour: weights are read as fp16 (64 B per block); recurrent GRU_B weights as stored
@@ -320,13 +366,13 @@ int model_load(DeviceModel *m, const unsigned char *blob, int len, float lpc_gam
     const float *embed_pitch = hm.embed_pitch, *conv1_w = hm.conv1_w, *conv1_b = hm.conv1_b, *conv2_w = hm.conv2_w, *conv2_b = hm.conv2_b;
     const float *dense1_w = hm.dense1_w, *dense1_b = hm.dense1_b, *dense2_w = hm.dense2_w, *dense2_b = hm.dense2_b;
     const float *gad_w = hm.gad_w, *gad_b = hm.gad_b, *gbd_w = hm.gbd_w, *gbd_b = hm.gbd_b;
-    const float *emb_sig = hm.emb_sig, *emb_pred = hm.emb_pred, *emb_exc = hm.emb_exc, *fc_w = hm.fc_w;
+    const float *emb_sig = hm.emb_sig, *emb_pred = hm.emb_pred, *emb_exc = hm.emb_exc;
     // ---------------- device copies ----------------
     bool ok = true;
 #define UP(field, src, count) ok = ok && ((m->field = to_device(src, (size_t)(count))) != nullptr);
     UP(image, img.data(), img.size())
     UP(emb_sig, emb_sig, 256 * 3 * NA) UP(emb_pred, emb_pred, 256 * 3 * NA) UP(emb_exc, emb_exc, 256 * 3 * NA)
-    UP(fcw, fc_w, 256 * 2 * NB)
+    UP(fcw, hm.fc_rows.data(), hm.fc_rows.size())
     UP(embed_pitch, embed_pitch, 256 * PITCH_EMBED)
     UP(conv1_w, conv1_w, 3 * FRAME_IN * COND) UP(conv1_b, conv1_b, COND)
     UP(conv2_w, conv2_w, 3 * COND * COND) UP(conv2_b, conv2_b, COND)

@@ -9,21 +9,25 @@
 //   sample_mdense                src/nnet.c:163-214  +  kiss99_rand src/kiss99.c:59-81
 //   lin2ulaw / ulaw2lin          src/common.h:37-58
 //
-// One CTA = 32 independent streams, LANE == STREAM, one CTA per SM, NWC + 3 + 1 warps:
+// One CTA = 32 independent streams, one CTA per SM, NWC + NWP + 1 warps:
 //
-//   NWC compute warps own 48/NWC neuron groups (8 neurons x {z,r,h}) of GRU_A each (default 24 warps x 2 groups).  All 32 lanes walk the same
-//                     block-sparse weight list, so every 32-byte weight block is fetched from shared memory ONCE per
-//                     32 streams (broadcast LDS.128) and each lane finishes the 8 outputs of a row group in its own
-//                     registers with dp4a.u32.s32 — no cross-lane reduction.  fp32 state lives in registers for the
-//                     whole launch; only the quantised u8 state goes through shared memory.  The integer GEMV sums
-//                     S = W.q(h) do not depend on the sampled excitation, so they are computed FIRST (overlapping the
-//                     previous sample's sampler and this sample's gather) and the gathered input term is added when it
-//                     arrives:  acc = rne((bias + diag*h + gin)*16256) + S  is the same integer the reference gets.
-//    3 producer warps gather the GRU_A input term cond + E_sig[a] + E_pred[b] + E_exc[c] (compute_gru_a_input) for the 32
+//   NWC compute warps own 48/NWC neuron groups (8 neurons x {z,r,h}) of GRU_A each.  The integer GEMVs S = W.q(h) of the
+//                     32 streams are small GEMMs and run on the tensor cores: mma.sync m16n8k16 (u8 x s8 -> s32, exact, so
+//                     the summation order is free): M = 16 streams, N = the 8 neurons of a row group, K = four 8x4 weight
+//                     blocks ("quad") whose column blocks may be anywhere (block-sparse): the A fragment of lane (gid, t)
+//                     is gathered from the quantised state with ONE LDS.128 (the words of streams gid, gid+8, gid+16,
+//                     gid+24 for the column block of slot t), the B fragment is one LDS.32 of the quad's weights.  Two MMAs
+//                     per quad cover the 32 streams.  The accumulator layout makes lane (gid, t) own neurons 2t, 2t+1 of
+//                     the group for streams gid + 8j: the fp32 state of those 8 (stream, neuron) pairs lives in its
+//                     registers for the whole launch and the activations are evaluated there.  The sums do not depend
+//                     on the sampled excitation, so they are computed FIRST (overlapping the previous sample's sampler
+//                     and this sample's gather) and the gathered input term is added when it arrives:
+//                     acc = rne((bias + diag*h + gin)*16256) + S  is the same integer the reference gets.
+//   NWP producer warps gather the GRU_A input term cond + E_sig[a] + E_pred[b] + E_exc[c] (compute_gru_a_input) for the 32
 //                     streams, one gate at a time, with 512-byte contiguous LDG.128 (4 L1 lines per request instead of
-//                     32 for a per-lane gather) into two [32][388] fp32 tiles that the compute lanes read conflict-free.
-//    1 sampler warp   runs the strictly serial tail (two KISS99 draws, 8-level sigmoid tree with sequential fp32 dot
-//                     products, ulaw2lin, order-16 LPC filter, de-emphasis, lin2ulaw) for its 32 streams.
+//                     32 for a per-lane gather) into two [32][392] fp32 tiles that the compute lanes read conflict-free.
+//    1 sampler warp   (lane == stream) runs the strictly serial tail (two KISS99 draws, 8-level sigmoid tree with sequential
+//                     fp32 dot products, ulaw2lin, order-16 LPC filter, de-emphasis, lin2ulaw) for its 32 streams.
 //
 // Weights, su-biases, the upper dual_fc levels and the sampler tables are staged into shared memory once per launch
 // by TMA bulk copies (cp.async.bulk + mbarrier).  Roles hand data over with named barriers (bar.arrive / bar.sync).
@@ -82,13 +86,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 
-// acc[r] += sum over `nb` 8x4 blocks; weights broadcast from smem (LDS.128), activations one word per lane.
-// Software-pipelined by hand: while block b is multiplied, the weights + activation word of block b+1 and the
-// meta entry of block b+2 are already in flight (LDS latency ~30 cycles would otherwise stall every 4 dp4a).
-// The prefetch runs up to two entries past the end of the list: the image keeps that slack readable
-// (next list / zero padding) and the values are never used.
-// shared-memory loads as volatile asm: keeps the compiler from sinking the prefetches of the pipelined GEMV down to
-// their first use (which would expose the ~30-cycle LDS latency once per 4 dp4a)
 __device__ __forceinline__ int4 lds128(uint32_t addr)
 {
     int4 v;
@@ -107,40 +104,32 @@ __device__ __forceinline__ uint32_t lds16(uint32_t addr)
     asm volatile("{ .reg .u16 t; ld.shared.u16 t, [%1]; cvt.u32.u16 %0, t; }" : "=r"(v) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ void mac_block(int acc[8], uint32_t x, const int4 &w0, const int4 &w1)
+// D[16 streams][8 neurons] += A[16 streams][16 inputs] (u8) . B[16 inputs][8 neurons] (s8): exact int32
+__device__ __forceinline__ void imma16816(int &c0, int &c1, int &c2, int &c3, uint32_t a0, uint32_t a1, uint32_t b0)
 {
-    acc[0] = dp4a_us(x, w0.x, acc[0]); acc[1] = dp4a_us(x, w0.y, acc[1]);
-    acc[2] = dp4a_us(x, w0.z, acc[2]); acc[3] = dp4a_us(x, w0.w, acc[3]);
-    acc[4] = dp4a_us(x, w1.x, acc[4]); acc[5] = dp4a_us(x, w1.y, acc[5]);
-    acc[6] = dp4a_us(x, w1.z, acc[6]); acc[7] = dp4a_us(x, w1.w, acc[7]);
+    asm("mma.sync.aligned.m16n8k16.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+        : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3) : "r"(a0), "r"(a1), "r"(b0));
 }
-// acc[r] += sum over `nb` (even) 8x4 blocks; weights broadcast from smem (LDS.128), activations one word per lane.
-// Software-pipelined by hand with two register sets: set B (block b+1) is loaded before set A (block b) is multiplied
-// and vice versa, meta entries two blocks ahead.  The prefetch runs up to four entries past the end of the list: the
-// image keeps that slack readable (next list / zero padding) and the values are never used.
-__device__ __forceinline__ void gemv_blocks(int acc[8], uint32_t w /* smem addr */, uint32_t meta /* smem addr */,
-                                            int nb /* even */, uint32_t xs_lane /* smem addr */)
+// acc[2j+i] += sum over `nq` quads, for stream gid+8j and neuron 2t+i of the row group.
+//   w    : shared address of the first quad's weights + lane*4      (B fragment word of this lane)
+//   meta : shared address of the first quad's meta + t*2            (xs_offset of slot t's column block)
+//   xs   : shared address of the state buffer; the lane's 16-byte vector of slot t is at xs + (meta entry ^ gid*16)
+// Software-pipelined: the meta entry of quad q+2 and the operands of quad q+1 are in flight while quad q is multiplied
+// (the image keeps two quads of readable slack behind every list).
+__device__ __forceinline__ void mma_quads(int (&acc)[8], uint32_t w, uint32_t meta, int nq, uint32_t xs, uint32_t gid16)
 {
-    uint32_t mAB = lds32(meta);                          // two u16 row offsets per word (lists start on even block indices)
-    uint32_t xA = lds32(xs_lane + (mAB & 0xFFFFu));
-    int4 a0 = lds128(w), a1 = lds128(w + 16);
-    for (int b = 0; b < nb; b += 2) {
-        const uint32_t xB = lds32(xs_lane + (mAB >> 16));
-        const int4 b0 = lds128(w + 32), b1 = lds128(w + 48);
-        mAB = lds32(meta + 4);
-        mac_block(acc, xA, a0, a1);
-        xA = lds32(xs_lane + (mAB & 0xFFFFu));
-        a0 = lds128(w + 64); a1 = lds128(w + 80);
-        mac_block(acc, xB, b0, b1);
-        w += 64; meta += 4;
+    uint32_t e1 = lds16(meta + QUAD_META_BYTES);
+    int4 x = lds128(xs + (lds16(meta) ^ gid16));
+    uint32_t wv = lds32(w);
+    for (int q = 0; q < nq; q++) {
+        const int4 xn = lds128(xs + (e1 ^ gid16));
+        const uint32_t wn = lds32(w + QUAD_BYTES);
+        e1 = lds16(meta + 2 * QUAD_META_BYTES);
+        imma16816(acc[0], acc[1], acc[2], acc[3], (uint32_t)x.x, (uint32_t)x.y, wv);
+        imma16816(acc[4], acc[5], acc[6], acc[7], (uint32_t)x.z, (uint32_t)x.w, wv);
+        x = xn; wv = wn;
+        w += QUAD_BYTES; meta += QUAD_META_BYTES;
     }
-}
-
-__device__ __forceinline__ void load_gin(float gin[8], const float *__restrict__ G, int lane, int g)
-{
-    const float4 a = *reinterpret_cast<const float4 *>(G + lane * GIN_ROW + 8 * g);
-    const float4 b = *reinterpret_cast<const float4 *>(G + lane * GIN_ROW + 8 * g + 4);
-    gin[0] = a.x; gin[1] = a.y; gin[2] = a.z; gin[3] = a.w; gin[4] = b.x; gin[5] = b.y; gin[6] = b.z; gin[7] = b.w;
 }
 
 // Producer warps: ONE gate's input term for all 32 streams of the CTA,
@@ -207,7 +196,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
 
     const uint32_t *rcp = reinterpret_cast<const uint32_t *>(smem + SM_IMAGE + IM_RCP);
     uint8_t *xs = smem + SM_XS;
-    uint32_t *xbw = reinterpret_cast<uint32_t *>(smem + SM_XB);
+    uint32_t *xbw = reinterpret_cast<uint32_t *>(smem + SM_XB);   // quantised GRU_B state, [4 words][32 lanes], lane == stream
     int *accB = reinterpret_cast<int *>(smem + SM_ACCB);
     float *hBs = reinterpret_cast<float *>(smem + SM_HBS);
     int *idx_s = reinterpret_cast<int *>(smem + SM_IDX);
@@ -218,37 +207,47 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
     if (warp < NWC) {
         // =====================================================  compute warps  =====================================================
         mbar_wait(bar, 0);
+        const int gid = lane >> 2, t = lane & 3;                         // MMA fragment coordinates of this lane
+        const uint32_t gid16 = gid * 16;
         const uint32_t *grpA = reinterpret_cast<const uint32_t *>(smem + SM_IMAGE + IM_GRPA);
         const uint32_t *dirA = reinterpret_cast<const uint32_t *>(smem + SM_IMAGE + IM_DIRA) + warp * GPW * 3 * 2;
-        const float *parA = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_PARA) + warp * GPW * 3 * 16;
-        const uint32_t metaA = smem_u32(smem + L.metaA);
-        const uint32_t wA = smem_u32(smem + L.wA);
+        const float *parA = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_PARA) + warp * GPW * 3 * 16 + 2 * t;
+        const uint32_t metaA = smem_u32(smem + L.metaA) + t * 2;
+        const uint32_t wA = smem_u32(smem + L.wA) + lane * 4;
         const uint32_t *dirB = reinterpret_cast<const uint32_t *>(smem + SM_IMAGE + IM_DIRB);
-        const uint32_t metaB = smem_u32(smem + L.metaB);
-        const uint32_t wB = smem_u32(smem + L.wB);
+        const uint32_t metaB = smem_u32(smem + L.metaB) + t * 2;
+        const uint32_t wB = smem_u32(smem + L.wB) + lane * 4;
         const float *parB = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_PARB);
         const uint8_t *wBrec = smem + SM_IMAGE + IM_WBREC;
-        const uint32_t xs_lane0 = smem_u32(xs + lane * 4);
-        uint32_t *xs_w0 = reinterpret_cast<uint32_t *>(xs);
+        const uint32_t xs0 = smem_u32(xs);
+        // the 4 streams of this lane (rows gid, gid+8 of the two MMAs); dead streams shadow the last one, stores masked
+        int sj[4]; bool livej[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) { const int r = cta_s0 + gid + 8 * j; livej[j] = r < n; sj[j] = livej[j] ? r : n - 1; }
 
-        int grp[GPW];
-        float h[GPW][8];
+        int gcol[GPW];                                                   // tile column / neuron index of this lane's first neuron: 8*g + 2t
+        uint32_t xoff[GPW];                                              // byte offset (in a state buffer) of this lane's two quantised neurons, stream gid
+        float h[GPW][8];                                                 // fp32 state: [stream j][neuron i] at 2j+i
 #pragma unroll
         for (int sl = 0; sl < GPW; sl++) {
-            grp[sl] = (int)grpA[warp * GPW + sl];
+            const int g = (int)grpA[warp * GPW + sl];
+            gcol[sl] = 8 * g + 2 * t;
+            xoff[sl] = xs_offset(2 * g + (t >> 1), gid) + (t & 1) * 2;
 #pragma unroll
-            for (int i = 0; i < 8; i++) h[sl][i] = P.hA[(size_t)(8 * grp[sl] + i) * n + s];
+            for (int j = 0; j < 4; j++)
+#pragma unroll
+                for (int i = 0; i < 2; i++) h[sl][2 * j + i] = P.hA[(size_t)(gcol[sl] + i) * n + sj[j]];
         }
-        // GRU_B neurons finished by this warp: jb = warp + k*NWC < NB
+        // GRU_B neurons finished by this warp (lane == stream there): jb = warp + k*NWC < NB
         float hb[NBW];
 #pragma unroll
         for (int k = 0; k < NBW; k++) hb[k] = P.hB[(size_t)min(warp + k * NWC, NB - 1) * n + s];
         // quantised copies of the restored state: xs <- q(hA), xb[0] <- q(hB)
 #pragma unroll
-        for (int sl = 0; sl < GPW; sl++) {
-            xs_w0[(2 * grp[sl]) * 32 + lane] = quant_u8(h[sl][0]) | (quant_u8(h[sl][1]) << 8) | (quant_u8(h[sl][2]) << 16) | (quant_u8(h[sl][3]) << 24);
-            xs_w0[(2 * grp[sl] + 1) * 32 + lane] = quant_u8(h[sl][4]) | (quant_u8(h[sl][5]) << 8) | (quant_u8(h[sl][6]) << 16) | (quant_u8(h[sl][7]) << 24);
-        }
+        for (int sl = 0; sl < GPW; sl++)
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                *reinterpret_cast<uint16_t *>(xs + xoff[sl] + 4 * j) = (uint16_t)(quant_u8(h[sl][2 * j]) | (quant_u8(h[sl][2 * j + 1]) << 8));
 #pragma unroll
         for (int k = 0; k < NBW; k++) {
             const int jb = warp + k * NWC;
@@ -265,10 +264,10 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
                 const int jb = min(warp + k * NWC, NB - 1);
                 cbz[k] = __ldg(condBp + jb); cbr[k] = __ldg(condBp + NB + jb); cbh[k] = __ldg(condBp + 2 * NB + jb);
             }
-            for (int t = 0; t < spf; t++, step++) {
+            for (int t_ = 0; t_ < spf; t_++, step++) {
                 const int cur = step & 1, nxt = cur ^ 1;                 // double buffers of the quantised states
-                const uint32_t xs_lane = xs_lane0 + cur * XS_BYTES;
-                uint32_t *xs_w = xs_w0 + nxt * (XS_BYTES / 4);
+                const uint32_t xs_cur = xs0 + cur * XS_BYTES;
+                uint8_t *xs_nxt = xs + nxt * XS_BYTES;
                 int Sh[GPW][8];                                          // candidate-gate GEMV sums; later (bit pattern) rec_h * r, then h~
                 // ---- A: candidate-gate GEMV  S_h = W_h . q(h)   (needs only the previous state: overlaps sampler + gather) ----
 #pragma unroll
@@ -276,7 +275,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
                     const uint32_t *dir = dirA + sl * 3 * 2;
 #pragma unroll
                     for (int i = 0; i < 8; i++) Sh[sl][i] = 0;
-                    gemv_blocks(Sh[sl], wA + dir[4] * 32, metaA + dir[4] * 2, (int)dir[5], xs_lane);
+                    mma_quads(Sh[sl], wA + dir[4] * QUAD_BYTES, metaA + dir[4] * QUAD_META_BYTES, (int)dir[5], xs_cur, gid16);
                 }
                 // ---- B: reset gate r (nnet.c:431-435): GEMV first, then the gathered input term from tile 0 ----
 #pragma unroll
@@ -286,67 +285,80 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
                     int Sr[8];
 #pragma unroll
                     for (int i = 0; i < 8; i++) Sr[i] = 0;
-                    gemv_blocks(Sr, wA + dir[2] * 32, metaA + dir[2] * 2, (int)dir[3], xs_lane);
+                    mma_quads(Sr, wA + dir[2] * QUAD_BYTES, metaA + dir[2] * QUAD_META_BYTES, (int)dir[3], xs_cur, gid16);
                     if (sl == 0) bar_sync(BAR_FULL0, CNT_FULL);          // gate r of all 32 streams is in tile 0
-                    float gin[8];
-                    load_gin(gin, tile0, lane, grp[sl]);
+                    const float2 br = *reinterpret_cast<const float2 *>(par + 16), dr = *reinterpret_cast<const float2 *>(par + 24);
+                    const float2 bh = *reinterpret_cast<const float2 *>(par + 32), dh = *reinterpret_cast<const float2 *>(par + 40);
+                    const float bri[2] = {br.x, br.y}, dri[2] = {dr.x, dr.y}, bhi[2] = {bh.x, bh.y}, dhi[2] = {dh.x, dh.y};
 #pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const int acc = acc_init(__fadd_rn(__fadd_rn(par[16 + i], __fmul_rn(par[24 + i], h[sl][i])), gin[i])) + Sr[i];
-                        const float r = sigmoid_approx(acc_finish(acc), rcp);
-                        // candidate pre-activation: rec_h = bias + diag*h (+ GEMV), no input term (nnet.c:436-440); keep rec_h * r
-                        const int acch = acc_init(__fadd_rn(par[32 + i], __fmul_rn(par[40 + i], h[sl][i]))) + Sh[sl][i];
-                        Sh[sl][i] = __float_as_int(__fmul_rn(acc_finish(acch), r));
+                    for (int j = 0; j < 4; j++) {
+                        const float2 gv = *reinterpret_cast<const float2 *>(tile0 + (gid + 8 * j) * GIN_ROW + gcol[sl]);
+                        const float gin[2] = {gv.x, gv.y};
+#pragma unroll
+                        for (int i = 0; i < 2; i++) {
+                            const float hv = h[sl][2 * j + i];
+                            const int acc = acc_init(__fadd_rn(__fadd_rn(bri[i], __fmul_rn(dri[i], hv)), gin[i])) + Sr[2 * j + i];
+                            const float r = sigmoid_approx(acc_finish(acc), rcp);
+                            // candidate pre-activation: rec_h = bias + diag*h (+ GEMV), no input term (nnet.c:436-440); keep rec_h * r
+                            const int acch = acc_init(__fadd_rn(bhi[i], __fmul_rn(dhi[i], hv))) + Sh[sl][2 * j + i];
+                            Sh[sl][2 * j + i] = __float_as_int(__fmul_rn(acc_finish(acch), r));
+                        }
                     }
                 }
                 bar_arrive(BAR_EMPTY0, CNT_FULL);                        // tile 0 may now receive gate z
                 // ---- C: h~ = tanh(rec_h*r + gin_h) from tile 1 (nnet.c:443-445) ----
                 bar_sync(BAR_FULL1, CNT_FULL);                           // gate h is in tile 1
 #pragma unroll
-                for (int sl = 0; sl < GPW; sl++) {
-                    float gin[8];
-                    load_gin(gin, tile1, lane, grp[sl]);
+                for (int sl = 0; sl < GPW; sl++)
 #pragma unroll
-                    for (int i = 0; i < 8; i++)
-                        Sh[sl][i] = __float_as_int(tanh_approx(__fadd_rn(__int_as_float(Sh[sl][i]), gin[i]), rcp));
-                }
+                    for (int j = 0; j < 4; j++) {
+                        const float2 gv = *reinterpret_cast<const float2 *>(tile1 + (gid + 8 * j) * GIN_ROW + gcol[sl]);
+                        Sh[sl][2 * j] = __float_as_int(tanh_approx(__fadd_rn(__int_as_float(Sh[sl][2 * j]), gv.x), rcp));
+                        Sh[sl][2 * j + 1] = __float_as_int(tanh_approx(__fadd_rn(__int_as_float(Sh[sl][2 * j + 1]), gv.y), rcp));
+                    }
                 // ---- D: update gate z (GEMV + input term from tile 0, 2nd phase), h <- z*h + (1-z)*h~ (nnet.c:446-447), new state ----
 #pragma unroll
                 for (int sl = 0; sl < GPW; sl++) {
-                    const int g = grp[sl];
                     const float *par = parA + sl * 3 * 16;
                     const uint32_t *dir = dirA + sl * 3 * 2;
                     int Sz[8];
 #pragma unroll
                     for (int i = 0; i < 8; i++) Sz[i] = 0;
-                    gemv_blocks(Sz, wA + dir[0] * 32, metaA + dir[0] * 2, (int)dir[1], xs_lane);
+                    mma_quads(Sz, wA + dir[0] * QUAD_BYTES, metaA + dir[0] * QUAD_META_BYTES, (int)dir[1], xs_cur, gid16);
                     if (sl == 0) bar_sync(BAR_FULL0, CNT_FULL);          // gate z of all 32 streams is in tile 0
-                    float gin[8];
-                    load_gin(gin, tile0, lane, g);
-                    uint32_t q[8];
+                    const float2 bz = *reinterpret_cast<const float2 *>(par), dz = *reinterpret_cast<const float2 *>(par + 8);
+                    const float bzi[2] = {bz.x, bz.y}, dzi[2] = {dz.x, dz.y};
 #pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const int acc = acc_init(__fadd_rn(__fadd_rn(par[i], __fmul_rn(par[8 + i], h[sl][i])), gin[i])) + Sz[i];
-                        const float z = sigmoid_approx(acc_finish(acc), rcp);
-                        const float hn = __fadd_rn(__fmul_rn(z, h[sl][i]), __fmul_rn(__fsub_rn(1.f, z), __int_as_float(Sh[sl][i])));
-                        h[sl][i] = hn;
-                        q[i] = quant_u8(hn);
+                    for (int j = 0; j < 4; j++) {
+                        const float2 gv = *reinterpret_cast<const float2 *>(tile0 + (gid + 8 * j) * GIN_ROW + gcol[sl]);
+                        const float gin[2] = {gv.x, gv.y};
+                        uint32_t q[2];
+#pragma unroll
+                        for (int i = 0; i < 2; i++) {
+                            const float hv = h[sl][2 * j + i];
+                            const int acc = acc_init(__fadd_rn(__fadd_rn(bzi[i], __fmul_rn(dzi[i], hv)), gin[i])) + Sz[2 * j + i];
+                            const float z = sigmoid_approx(acc_finish(acc), rcp);
+                            const float hn = __fadd_rn(__fmul_rn(z, hv), __fmul_rn(__fsub_rn(1.f, z), __int_as_float(Sh[sl][2 * j + i])));
+                            h[sl][2 * j + i] = hn;
+                            q[i] = quant_u8(hn);
+                        }
+                        // other buffer: readers of the old state are unaffected
+                        *reinterpret_cast<uint16_t *>(xs_nxt + xoff[sl] + 4 * j) = (uint16_t)(q[0] | (q[1] << 8));
                     }
-                    xs_w[(2 * g) * 32 + lane] = q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24);     // other buffer: readers of the old state are unaffected
-                    xs_w[(2 * g + 1) * 32 + lane] = q[4] | (q[5] << 8) | (q[6] << 16) | (q[7] << 24);
                 }
                 bar_sync(BAR_X, CNT_C);                                  // new quantised GRU_A state complete (tile 1 is dead: accB/hBs may use it)
 
-                // ---------------- E: GRU_B input GEMV (48 x 384 int8): warp = (row group, K part) ----------------
+                // ---------------- E: GRU_B input GEMV (48 x 384 int8, dense): warp = (row group, K part) ----------------
                 if (warp < NWB) {
                     int acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                    const uint32_t b0 = dirB[warp * 2], nb = dirB[warp * 2 + 1];
-                    gemv_blocks(acc, wB + b0 * 32, metaB + b0 * 2, (int)nb, xs_lane0 + nxt * XS_BYTES);
+                    const uint32_t q0 = dirB[warp * 2], nq = dirB[warp * 2 + 1];
+                    mma_quads(acc, wB + q0 * QUAD_BYTES, metaB + q0 * QUAD_META_BYTES, (int)nq, xs0 + nxt * XS_BYTES, gid16);
                     const int rgp = warp / KPARTS, part = warp % KPARTS;
+                    int *dst = accB + (part * 3 * NB + rgp * 8 + 2 * t) * ACCB_ROW + gid;
 #pragma unroll
-                    for (int i = 0; i < 8; i++) accB[(part * 3 * NB + rgp * 8 + i) * 32 + lane] = acc[i];
+                    for (int j = 0; j < 4; j++) { dst[8 * j] = acc[2 * j]; dst[ACCB_ROW + 8 * j] = acc[2 * j + 1]; }
                 }
-                // ---------------- GRU_B finish (nnet.c:346-371): neurons warp, warp + NWC, ... ----------------
+                // ---------------- GRU_B finish (nnet.c:346-371), lane == stream: neurons warp, warp + NWC, ... ----------------
                 {
                     const uint32_t *xbc = xbw + cur * 4 * 32;
                     const uint32_t xw[4] = {xbc[lane], xbc[32 + lane], xbc[64 + lane], xbc[96 + lane]};
@@ -372,9 +384,9 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
                         int az = acc_init(__fadd_rn(parB[jb], cbz[k2])), ar = acc_init(__fadd_rn(parB[NB + jb], cbr[k2])), ah = acc_init(__fadd_rn(parB[2 * NB + jb], cbh[k2]));
 #pragma unroll
                         for (int kp = 0; kp < KPARTS; kp++) {
-                            az += accB[(kp * 3 * NB + jb) * 32 + lane];
-                            ar += accB[(kp * 3 * NB + NB + jb) * 32 + lane];
-                            ah += accB[(kp * 3 * NB + 2 * NB + jb) * 32 + lane];
+                            az += accB[(kp * 3 * NB + jb) * ACCB_ROW + lane];
+                            ar += accB[(kp * 3 * NB + NB + jb) * ACCB_ROW + lane];
+                            ah += accB[(kp * 3 * NB + 2 * NB + jb) * ACCB_ROW + lane];
                         }
                         const float zz = sigmoid_approx(__fadd_rn(acc_finish(az), acc_finish(rz[k2])), rcp);
                         const float rrr = sigmoid_approx(__fadd_rn(acc_finish(ar), acc_finish(rr[k2])), rcp);
@@ -389,11 +401,15 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
             }
         }
         // ---- save the recurrent state ----
+#pragma unroll
+        for (int sl = 0; sl < GPW; sl++)
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (livej[j]) {
+                    P.hA[(size_t)gcol[sl] * n + sj[j]] = h[sl][2 * j];
+                    P.hA[(size_t)(gcol[sl] + 1) * n + sj[j]] = h[sl][2 * j + 1];
+                }
         if (live) {
-#pragma unroll
-            for (int sl = 0; sl < GPW; sl++)
-#pragma unroll
-                for (int i = 0; i < 8; i++) P.hA[(size_t)(8 * grp[sl] + i) * n + s] = h[sl][i];
 #pragma unroll
             for (int k = 0; k < NBW; k++) if (warp + k * NWC < NB) P.hB[(size_t)(warp + k * NWC) * n + s] = hb[k];
         }
@@ -422,8 +438,6 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
         const float *logit = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_LOGIT);
         const float *u2l = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_U2L);
         const float *fcw = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_FCW);
-        const float *fcb = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_FCB);
-        const float *fcf = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_FCF);
 
         float ls[LPC_ORDER], lpc[LPC_ORDER];
 #pragma unroll
@@ -467,10 +481,12 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
 #pragma unroll
                 for (int b = 0; b < 8; b++) {                            // sample_mdense, nnet.c:186-211
                     const int i = (1 << b) | val;
-                    float sum1 = fcb[i], sum2 = fcb[256 + i];
+                    float sum1, sum2, fac1, fac2;
                     // two sequential 16-term chains (one per channel), fed 8 weights at a time to keep the live set small
-                    if (b < 6) {                                         // nodes < 64: weights in shared memory (rows padded to 36 floats)
+                    if (b < 6) {                                         // nodes < 64: rows in shared memory
                         const float *wr = fcw + i * FCW_ROW;
+                        const float4 bf = *reinterpret_cast<const float4 *>(wr + 32);
+                        sum1 = bf.x; sum2 = bf.y; fac1 = bf.z; fac2 = bf.w;
 #pragma unroll
                         for (int j0 = 0; j0 < NB; j0 += 8) {
                             const float4 a0 = *reinterpret_cast<const float4 *>(wr + j0), a1 = *reinterpret_cast<const float4 *>(wr + j0 + 4);
@@ -482,8 +498,10 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
                                 sum2 = __fadd_rn(sum2, __fmul_rn(wc[j], hbv[j0 + j]));
                             }
                         }
-                    } else {                                             // lower levels: one 128-byte row per lane from global (L2-resident)
-                        const float *wr = P.fcw + i * 32;
+                    } else {                                             // lower levels: one 144-byte row per lane from global (L2-resident)
+                        const float *wr = P.fcw + i * FCW_ROW;
+                        const float4 bf = ldg4(wr + 32);
+                        sum1 = bf.x; sum2 = bf.y; fac1 = bf.z; fac2 = bf.w;
 #pragma unroll
                         for (int j0 = 0; j0 < NB; j0 += 8) {
                             const float4 a0 = ldg4(wr + j0), a1 = ldg4(wr + j0 + 4), c0 = ldg4(wr + NB + j0), c1 = ldg4(wr + NB + j0 + 4);
@@ -495,8 +513,8 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
                             }
                         }
                     }
-                    sum1 = __fmul_rn(fcf[i], tanh_approx(sum1, rcp));
-                    sum2 = __fmul_rn(fcf[256 + i], tanh_approx(sum2, rcp));
+                    sum1 = __fmul_rn(fac1, tanh_approx(sum1, rcp));
+                    sum2 = __fmul_rn(fac2, tanh_approx(sum2, rcp));
                     sum1 = __fadd_rn(sum1, sum2);
                     val = (val << 1) | (thr[b] < sum1 ? 1 : 0);
                 }

@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) lpcnet_sample_kernel_f32(const _
                 for (int b = 0; b < 8; b++) {
                     const int i = (1 << b) | val;
                     float sum1 = fcb[i], sum2 = fcb[256 + i];
-                    const float *wr = P.fcw + i * 32;
+                    const float *wr = P.fcw + i * FCW_ROW;
 #pragma unroll
                     for (int j0 = 0; j0 < NB; j0 += 8) {
                         const float4 a0 = ldg4(wr + j0), a1 = ldg4(wr + j0 + 4), c0 = ldg4(wr + NB + j0), c1 = ldg4(wr + NB + j0 + 4);

@@ -67,8 +67,8 @@ def test_blob_validation(L):
 
 
 def test_smem_image_replays_to_the_dense_model(L):
-    """Walk the image exactly like the kernel (warp -> slot -> gate -> padded block list; (row group, K half) for
-    GRU_B) and check the integer GEMV it encodes equals the dense int8 matrices of the model for random u8 inputs."""
+    """Walk the image exactly like the kernel (warp -> slot -> gate -> list of quads = MMA operands; (row group, K half)
+    for GRU_B) and check the integer GEMV it encodes equals the dense int8 matrices of the model for random u8 inputs."""
     import gen_model
     common, only8, _ = gen_model.make_model()
     arrs = {n: a for n, _, a in common + only8}
@@ -92,48 +92,63 @@ def test_smem_image_replays_to_the_dense_model(L):
     x = rng.integers(0, 255, 384).astype(np.int32)
     want_A, want_B = MA @ x, MB @ x
 
+    def xs_offset(c, s):
+        return c * 128 + (((s & 7) * 16) ^ ((c & 3) * 32)) + (s >> 3) * 4
+
+    def replay_quads(wq, mq, q0, nq):
+        """sum over quads q0..q0+nq of W[8 out][slot][4 in] . x[column block of the slot]; also counts bank-group clashes"""
+        acc = np.zeros(8, np.int64); clash = 0
+        for q in range(q0, q0 + nq):
+            classes = set()
+            for t in range(4):
+                e = int(mq[q, t]); c = e >> 7
+                assert e == xs_offset(c, 0) and c < 96
+                classes.add(c & 3)
+                acc += wq[q, :, t, :] @ x[4 * c:4 * c + 4]
+            clash += 4 - len(classes)
+        return acc, clash
+
     dirA = img[DIRA:DIRA + NWC * GPW * 3 * 2 * 4].view(np.uint32).reshape(NWC, GPW, 3, 2)
     grpA = img[GRPA:GRPA + NWC * GPW * 4].view(np.uint32).reshape(NWC, GPW)
     parA = img[PARA:PARA + NWC * GPW * 3 * 16 * 4].view(np.float32).reshape(NWC, GPW, 3, 2, 8)
-    wAi = img[rel(wA):rel(wA) + nA * 32].view(np.int8).astype(np.int32).reshape(nA, 8, 4)
-    mA = img[rel(metaA):rel(metaA) + nA * 2].view(np.uint16)
+    wAi = img[rel(wA):rel(wA) + nA * 128].view(np.int8).astype(np.int32).reshape(nA, 8, 4, 4)     # [quad][out][slot][in]
+    mA = img[rel(metaA):rel(metaA) + nA * 8].view(np.uint16).reshape(nA, 4)
     assert sorted(grpA.reshape(-1).tolist()) == list(range(48))           # every neuron group owned exactly once
     got = np.zeros(1152, np.int64)
-    loads = []
+    loads = []; clashes = 0
     for w in range(NWC):
         tot = 0
         for sl in range(GPW):
             g = int(grpA[w, sl])
             for q in range(3):
-                b0, nb = int(dirA[w, sl, q, 0]), int(dirA[w, sl, q, 1])
-                assert nb % 2 == 0
-                tot += nb
-                for b in range(b0, b0 + nb):
-                    assert mA[b] % 128 == 0
-                    pos = int(mA[b]) // 128 * 4
-                    got[q * 384 + 8 * g:q * 384 + 8 * g + 8] += wAi[b] @ x[pos:pos + 4]
+                q0, nq = int(dirA[w, sl, q, 0]), int(dirA[w, sl, q, 1])
+                tot += nq
+                acc, cl = replay_quads(wAi, mA, q0, nq)
+                got[q * 384 + 8 * g:q * 384 + 8 * g + 8] += acc; clashes += cl
                 np.testing.assert_array_equal(parA[w, sl, q, 0], arrs["sparse_gru_a_subias"][1, q * 384 + 8 * g:q * 384 + 8 * g + 8])
                 np.testing.assert_array_equal(parA[w, sl, q, 1], arrs["sparse_gru_a_recurrent_weights_diag"][q * 384 + 8 * g:q * 384 + 8 * g + 8])
         loads.append(tot)
     np.testing.assert_array_equal(got, want_A)
-    assert max(loads) <= 1.15 * (sum(loads) / NWC)                         # LPT balancing of the compute warps
+    assert sum(loads) == nA and max(loads) <= 1.2 * (sum(loads) / NWC)    # LPT balancing of the compute warps
+    assert clashes <= 0.15 * 4 * nA                                       # slots of a quad mostly in different bank groups
 
     dirB = img[DIRB:DIRB + 6 * KP * 2 * 4].view(np.uint32).reshape(6, KP, 2)
-    wBi = img[rel(wB):rel(wB) + nB * 32].view(np.int8).astype(np.int32).reshape(nB, 8, 4)
-    mB = img[rel(metaB):rel(metaB) + nB * 2].view(np.uint16)
+    wBi = img[rel(wB):rel(wB) + nB * 128].view(np.int8).astype(np.int32).reshape(nB, 8, 4, 4)
+    mB = img[rel(metaB):rel(metaB) + nB * 8].view(np.uint16).reshape(nB, 4)
     gotB = np.zeros(48, np.int64)
     for rg in range(6):
         for half in range(KP):
-            b0, nb = int(dirB[rg, half, 0]), int(dirB[rg, half, 1])
-            for b in range(b0, b0 + nb):
-                pos = int(mB[b]) // 128 * 4
-                gotB[rg * 8:rg * 8 + 8] += wBi[b] @ x[pos:pos + 4]
+            acc, cl = replay_quads(wBi, mB, int(dirB[rg, half, 0]), int(dirB[rg, half, 1]))
+            gotB[rg * 8:rg * 8 + 8] += acc
+            assert cl == 0                                                # dense rows: always conflict-free
     np.testing.assert_array_equal(gotB, want_B)
     # GRU_B recurrent block layout [out/8][in/4][8][4] and su-biases
     np.testing.assert_array_equal(img[WBREC:WBREC + 768].view(np.int8), arrs["gru_b_recurrent_weights"])
     np.testing.assert_array_equal(img[PARB:PARB + 96 * 4].view(np.float32), arrs["gru_b_subias"].reshape(-1))
     fcw = img[FCW:FCW + FCN * 36 * 4].view(np.float32).reshape(FCN, 36)
     np.testing.assert_array_equal(fcw[:, :32], arrs["dual_fc_weights"].reshape(256, 32)[:FCN])
+    np.testing.assert_array_equal(fcw[:, 32:34], arrs["dual_fc_bias"].reshape(2, 256).T[:FCN])
+    np.testing.assert_array_equal(fcw[:, 34:36], arrs["dual_fc_factor"].reshape(2, 256).T[:FCN])
 
 
 def test_python_mirror_matches_reference_operator_names():
