@@ -42,11 +42,14 @@ constexpr int XS_BYTES = (NA / 4) * 32 * 4;  // quantised GRU_A state of 32 stre
 constexpr int FCW_ROW = 36;                  // dual_fc row: 32 weights (16 per channel) + {bias0, bias1, factor0, factor1}; 144 B stride = 16 mod 128, so the
                                              // per-lane LDS.128 row reads of lanes on different nodes mostly land in different 4-bank groups
 constexpr int FCW_SMEM_NODES = 64;           // tree levels 0..5 (nodes 1..63) live in shared memory, levels 6,7 are read from global (L2)
-constexpr int KPARTS = 2;                    // K split of the GRU_B input GEMV
+constexpr int KPARTS = (NWC >= 24) ? 4 : 2;  // K split of the GRU_B input GEMV
 constexpr int NWB = 6 * KPARTS;              // warps used by the GRU_B input GEMV: (row group 0..5) x (K part)
 static_assert(NWB <= NWC, "one (row group, K part) of GRU_B per compute warp");
-constexpr int NBW = (NB + NWC - 1) / NWC;    // GRU_B neurons finished per compute warp
-constexpr int ACCB_ROW = 36;                 // int32 per output row of the GRU_B partial sums (32 streams + 4 pad: the MMA accumulator stores of a warp
+constexpr int HALF = 16;                     // the 32 streams of a CTA are stepped as two halves of 16 (= the M of one MMA), half a sample apart:
+                                             // while the sampler / gather of one half run, the compute warps work on the other half
+constexpr int NFIN = NB * HALF / 32;         // compute warps that finish GRU_B for a half: lane = (neuron parity, stream in half)
+static_assert(NFIN <= NWC, "GRU_B finishing warps");
+constexpr int ACCB_ROW = 20;                 // int32 per output row of the GRU_B partial sums (16 streams + 4 pad: the MMA accumulator stores of a warp
                                              // (rows 2t, columns gid) then fall into 32 different banks)
 
 // ---- int8 flavour: the integer GEMVs run on the tensor cores (mma.sync m16n8k16, u8 x s8 -> s32, exact) ----
@@ -72,18 +75,20 @@ constexpr uint32_t xs_offset(uint32_t c, uint32_t s) { return c * 128u + ((((s &
 constexpr uint32_t al128(uint32_t x) { return (x + 127u) & ~127u; }
 constexpr int GIN_ROW = 392;                                       // floats per stream in a gather tile: 384 + 8 pad => row stride = 8 words mod 32:
                                                                    // the LDS.64 of lanes (gid, t) = row gid, column 2t hit 32 different banks per half-warp
-constexpr uint32_t TILE_BYTES = 32 * GIN_ROW * 4;
-constexpr uint32_t SM_XS    = 0;                                   // 2 x quantised GRU_A state (double-buffered)
-constexpr uint32_t SM_XB    = SM_XS + 2 * XS_BYTES;                // 2 x [4 words][32]: quantised GRU_B state
-constexpr uint32_t SM_T0    = SM_XB + 2 * 4 * 32 * 4;              // gather tile 0: gate r, later gate z   (float [32 streams][GIN_ROW])
-constexpr uint32_t SM_T1    = SM_T0 + TILE_BYTES;                  // gather tile 1: gate h
-constexpr uint32_t SM_ACCB  = SM_T1;                               // int32 [KPARTS][48][ACCB_ROW] partial sums of the GRU_B input GEMV } alias tile 1:
-constexpr uint32_t SM_HBS   = SM_ACCB + KPARTS * 3 * NB * ACCB_ROW * 4;  // float [16][32] GRU_B state for the sampler warp            } live only between the
-                                                                   //                                                                 } h-gate and the next indices
-constexpr uint32_t SM_IDX   = SM_T1 + TILE_BYTES;                  // int32 [3][32]: last_sig_ulaw, pred_ulaw, last_exc
-constexpr uint32_t SM_MBAR  = al128(SM_IDX + 3 * 32 * 4);          // 8-byte mbarrier of the image copy
+constexpr int NTILE = 4;                                           // ring of gather tiles, filled in the order (half A: r, z, h), (half B: r, z, h), ...
+constexpr uint32_t TILE_BYTES = HALF * GIN_ROW * 4;                // one gate of one half: float [16 streams][GIN_ROW]
+constexpr uint32_t SM_XS    = 0;                                   // 2 x quantised GRU_A state (double-buffered), both halves interleaved (xs_offset)
+constexpr uint32_t SM_XB    = SM_XS + 2 * XS_BYTES;                // u32 [2 halves][2 buffers][4 words][16 streams]: quantised GRU_B state
+constexpr uint32_t SM_TILES = SM_XB + 2 * 2 * 4 * HALF * 4;
+// the tile that held a half's candidate gate is dead once h~ is computed; until the half's next indices are out it carries
+constexpr uint32_t T_ACCB   = 0;                                   //   int32 [KPARTS][48][ACCB_ROW] partial sums of the GRU_B input GEMV
+constexpr uint32_t T_HBS    = T_ACCB + KPARTS * 3 * NB * ACCB_ROW * 4;   //   float [16 neurons][16 streams] GRU_B state for the sampler
+static_assert(T_HBS + NB * HALF * 4 <= TILE_BYTES, "GRU_B scratch must fit inside the gather tile it aliases");
+constexpr uint32_t SM_IDX   = SM_TILES + NTILE * TILE_BYTES;       // int32 [2 halves][3][16]: last_sig_ulaw, pred_ulaw, last_exc
+constexpr uint32_t SM_MBAR  = al128(SM_IDX + 2 * 3 * HALF * 4);    // mbarriers: image | full[NTILE] | empty[NTILE] | idx[2] | hb[2]
+constexpr uint32_t MB_IMAGE = SM_MBAR, MB_FULL = SM_MBAR + 8, MB_EMPTY = MB_FULL + 8 * NTILE, MB_IDX = MB_EMPTY + 8 * NTILE, MB_HB = MB_IDX + 16;
 constexpr uint32_t SM_IMAGE = SM_MBAR + 128;
-static_assert(SM_HBS + NB * 32 * 4 <= SM_IDX, "GRU_B scratch must fit inside the gather tile it aliases");
+static_assert(MB_HB + 16 <= SM_IMAGE, "mbarrier block");
 // image, fixed part (offsets relative to SM_IMAGE)
 constexpr uint32_t IM_RCP   = 0;                                   // u32 [2048] RCPPS table, pre-biased: T[k] + 0x3f800000 (one IADD rebuilds the result)
 constexpr uint32_t IM_LOGIT = IM_RCP + 2048 * 4;                   // float [256] sampling_logit_table

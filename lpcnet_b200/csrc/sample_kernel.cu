@@ -9,28 +9,32 @@
 //   sample_mdense                src/nnet.c:163-214  +  kiss99_rand src/kiss99.c:59-81
 //   lin2ulaw / ulaw2lin          src/common.h:37-58
 //
-// One CTA = 32 independent streams, one CTA per SM, NWC + NWP + 1 warps:
+// One CTA = 32 independent streams on one SM, stepped as two HALVES of 16 streams that run half a sample apart:
+// a GRU step cannot start before the previous sample of the same stream has been drawn and its embedding rows gathered,
+// so while that serial tail (sampler -> indices -> gather) runs for one half, the compute warps work on the other half.
+// NWC + NWP + 1 warps:
 //
-//   NWC compute warps own 48/NWC neuron groups (8 neurons x {z,r,h}) of GRU_A each.  The integer GEMVs S = W.q(h) of the
-//                     32 streams are small GEMMs and run on the tensor cores: mma.sync m16n8k16 (u8 x s8 -> s32, exact, so
-//                     the summation order is free): M = 16 streams, N = the 8 neurons of a row group, K = four 8x4 weight
-//                     blocks ("quad") whose column blocks may be anywhere (block-sparse): the A fragment of lane (gid, t)
-//                     is gathered from the quantised state with ONE LDS.128 (the words of streams gid, gid+8, gid+16,
-//                     gid+24 for the column block of slot t), the B fragment is one LDS.32 of the quad's weights.  Two MMAs
-//                     per quad cover the 32 streams.  The accumulator layout makes lane (gid, t) own neurons 2t, 2t+1 of
-//                     the group for streams gid + 8j: the fp32 state of those 8 (stream, neuron) pairs lives in its
-//                     registers for the whole launch and the activations are evaluated there.  The sums do not depend
-//                     on the sampled excitation, so they are computed FIRST (overlapping the previous sample's sampler
-//                     and this sample's gather) and the gathered input term is added when it arrives:
+//   NWC compute warps own 48/NWC neuron groups (8 neurons x {z,r,h}) of GRU_A each.  The integer GEMVs S = W.q(h) of a
+//                     half are small GEMMs and run on the tensor cores: mma.sync m16n8k16 (u8 x s8 -> s32, exact, so the
+//                     summation order is free): M = the 16 streams of the half, N = the 8 neurons of a row group, K = four
+//                     8x4 weight blocks ("quad") whose column blocks may be anywhere (block-sparse): the A fragment of lane
+//                     (gid, t) is gathered from the quantised state with ONE LDS.64 (the words of streams gid, gid+8 for
+//                     the column block of slot t), the B fragment is one LDS.32 of the quad's weights.  The accumulator
+//                     layout makes lane (gid, t) own neurons 2t, 2t+1 of the group for streams gid, gid+8 of each half:
+//                     the fp32 state of those (stream, neuron) pairs lives in its registers for the whole launch and the
+//                     activations are evaluated there.  The sums do not depend on the sampled excitation, so they are
+//                     computed before the gathered input term is waited for:
 //                     acc = rne((bias + diag*h + gin)*16256) + S  is the same integer the reference gets.
-//   NWP producer warps gather the GRU_A input term cond + E_sig[a] + E_pred[b] + E_exc[c] (compute_gru_a_input) for the 32
-//                     streams, one gate at a time, with 512-byte contiguous LDG.128 (4 L1 lines per request instead of
-//                     32 for a per-lane gather) into two [32][392] fp32 tiles that the compute lanes read conflict-free.
-//    1 sampler warp   (lane == stream) runs the strictly serial tail (two KISS99 draws, 8-level sigmoid tree with sequential
-//                     fp32 dot products, ulaw2lin, order-16 LPC filter, de-emphasis, lin2ulaw) for its 32 streams.
+//   NWP producer warps gather the GRU_A input term cond + E_sig[a] + E_pred[b] + E_exc[c] (compute_gru_a_input), one gate of
+//                     one half at a time, with 512-byte contiguous LDG.128 into a ring of four [16][392] fp32 tiles
+//                     (full/empty mbarriers) that the compute lanes read conflict-free.
+//    1 sampler warp   (lane == stream; lanes 0-15 half A, 16-31 half B) runs the strictly serial tail (two KISS99 draws,
+//                     8-level sigmoid tree with sequential fp32 dot products, ulaw2lin, order-16 LPC filter, de-emphasis,
+//                     lin2ulaw), one half at a time.
 //
 // Weights, su-biases, the upper dual_fc levels and the sampler tables are staged into shared memory once per launch
-// by TMA bulk copies (cp.async.bulk + mbarrier).  Roles hand data over with named barriers (bar.arrive / bar.sync).
+// by TMA bulk copies (cp.async.bulk + mbarrier).  Roles hand data over with mbarriers; the compute warps synchronise
+// among themselves with two named barriers.
 #include <cstdint>
 #include "engine.h"
 #include "devmath.cuh"
@@ -43,20 +47,14 @@ namespace lpcnet_b200 {
 
 namespace {
 
-// named barriers: who arrives (A) / who waits (S) and the thread count each one is armed with
+// named barriers of the compute warps
 enum {
-    BAR_IDX = 1,     // A sampler, S producers : indices of the next sample are in idx_s                 (32 + 96)
-    BAR_FULL0 = 2,   // A producers, S compute : tile 0 holds gate r (1st phase) / gate z (2nd phase)     (96 + 32 NWC)
-    BAR_FULL1 = 3,   // A producers, S compute : tile 1 holds gate h                                     (96 + 384)
-    BAR_EMPTY0 = 4,  // A compute, S producers : tile 0 (gate r) consumed, may be overwritten with gate z (384 + 96)
-    BAR_X = 5,       // S compute              : new quantised GRU_A state complete                       (384)
-    BAR_ACCB = 6,    // S compute              : GRU_B partial sums complete                              (384)
-    BAR_HB = 7       // A compute, S sampler   : GRU_B state of this sample is in hBs                     (384 + 32)
+    BAR_X = 1,       // new quantised GRU_A state of the half complete (and its candidate-gate tile consumed)
+    BAR_ACCB = 2     // GRU_B partial sums complete
 };
-constexpr int CNT_IDX = 32 + NWP * 32, CNT_FULL = (NWP + NWC) * 32, CNT_C = NWC * 32, CNT_HB = NWC * 32 + 32;
+constexpr int CNT_C = NWC * 32;
 
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // ---- TMA bulk copy global -> shared, completion on an mbarrier ----
@@ -72,6 +70,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// one arrival per warp: the lanes' shared-memory accesses are ordered before it by the fence + warp barrier
+__device__ __forceinline__ void warp_arrive(uint32_t bar, int lane)
+{
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
@@ -110,49 +119,54 @@ __device__ __forceinline__ void imma16816(int &c0, int &c1, int &c2, int &c3, ui
     asm("mma.sync.aligned.m16n8k16.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
         : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3) : "r"(a0), "r"(a1), "r"(b0));
 }
-// acc[2j+i] += sum over `nq` quads, for stream gid+8j and neuron 2t+i of the row group.
+__device__ __forceinline__ int2 lds64(uint32_t addr)
+{
+    int2 v;
+    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+// acc[2jj+i] += sum over `nq` quads, for stream gid+8jj (of one half) and neuron 2t+i of the row group.
 //   w    : shared address of the first quad's weights + lane*4      (B fragment word of this lane)
 //   meta : shared address of the first quad's meta + t*2            (xs_offset of slot t's column block)
-//   xs   : shared address of the state buffer; the lane's 16-byte vector of slot t is at xs + (meta entry ^ gid*16)
+//   xs   : shared address of the state buffer + 8*half; the lane's 8-byte vector of slot t is at xs + (meta entry ^ gid*16)
 // Software-pipelined: the meta entry of quad q+2 and the operands of quad q+1 are in flight while quad q is multiplied
 // (the image keeps two quads of readable slack behind every list).
-__device__ __forceinline__ void mma_quads(int (&acc)[8], uint32_t w, uint32_t meta, int nq, uint32_t xs, uint32_t gid16)
+__device__ __forceinline__ void mma_quads(int (&acc)[4], uint32_t w, uint32_t meta, int nq, uint32_t xs, uint32_t gid16)
 {
     uint32_t e1 = lds16(meta + QUAD_META_BYTES);
-    int4 x = lds128(xs + (lds16(meta) ^ gid16));
+    int2 x = lds64(xs + (lds16(meta) ^ gid16));
     uint32_t wv = lds32(w);
     for (int q = 0; q < nq; q++) {
-        const int4 xn = lds128(xs + (e1 ^ gid16));
+        const int2 xn = lds64(xs + (e1 ^ gid16));
         const uint32_t wn = lds32(w + QUAD_BYTES);
         e1 = lds16(meta + 2 * QUAD_META_BYTES);
         imma16816(acc[0], acc[1], acc[2], acc[3], (uint32_t)x.x, (uint32_t)x.y, wv);
-        imma16816(acc[4], acc[5], acc[6], acc[7], (uint32_t)x.z, (uint32_t)x.w, wv);
         x = xn; wv = wn;
         w += QUAD_BYTES; meta += QUAD_META_BYTES;
     }
 }
 
-// Producer warps: ONE gate's input term for all 32 streams of the CTA,
-//   G[s][k] = ((cond[s][k] + E_sig[a_s][k]) + E_pred[b_s][k]) + E_exc[c_s][k]        (nnet.c:484-491, left to right)
-// Producer p serves streams p, p+NWP, ...: per stream the four row pointers are formed once and the 384 columns of the
-// gate are covered by three 512-byte LDG.128 per row (4 L1 lines per request), i.e. 12 independent loads in flight per
-// lane, then 12 fp32 adds and three 512-byte conflict-free STS.128 into the [32][388] tile.
-__device__ __forceinline__ void gather_slice(float *__restrict__ G, const float *__restrict__ cond_f, int n, int cta_s0,
-                                             const float *__restrict__ emb_sig, const float *__restrict__ emb_pred,
-                                             const float *__restrict__ emb_exc, const int *__restrict__ idx_s,
-                                             int gate, int p, int lane)
+// Producer warps: ONE gate's input term for the 16 streams of a half,
+//   G[si][k] = ((cond[s][k] + E_sig[a_s][k]) + E_pred[b_s][k]) + E_exc[c_s][k]        (nnet.c:484-491, left to right)
+// Producer p serves tile rows si = p, p+NWP, ...: per stream the four row pointers are formed once and the 384 columns
+// of the gate are covered by three 512-byte LDG.128 per row (4 L1 lines per request), i.e. 12 independent loads in
+// flight per lane, then 12 fp32 adds and three 512-byte conflict-free STS.128 into the [16][392] tile.
+__device__ __forceinline__ void gather_half(float *__restrict__ G, const float *__restrict__ cond_f, int n, int s_half0,
+                                            const float *__restrict__ emb_sig, const float *__restrict__ emb_pred,
+                                            const float *__restrict__ emb_exc, const int *__restrict__ idx_h,
+                                            int gate, int p, int lane)
 {
     const int col = gate * NA + lane * 4;
-    for (int ss = p; ss < STREAMS_PER_CTA; ss += NWP) {
-        const int sg = min(cta_s0 + ss, n - 1);
+    for (int si = p; si < HALF; si += NWP) {
+        const int sg = min(s_half0 + si, n - 1);
         const float *c = cond_f + (size_t)sg * (3 * NA) + col;
-        const float *e0 = emb_sig + idx_s[ss] * (3 * NA) + col;
-        const float *e1 = emb_pred + idx_s[32 + ss] * (3 * NA) + col;
-        const float *e2 = emb_exc + idx_s[64 + ss] * (3 * NA) + col;
+        const float *e0 = emb_sig + idx_h[si] * (3 * NA) + col;
+        const float *e1 = emb_pred + idx_h[HALF + si] * (3 * NA) + col;
+        const float *e2 = emb_exc + idx_h[2 * HALF + si] * (3 * NA) + col;
         float4 a[3], b[3], d[3], e[3];
 #pragma unroll
         for (int j = 0; j < 3; j++) { a[j] = ldg4(c + 128 * j); b[j] = ldg4(e0 + 128 * j); d[j] = ldg4(e1 + 128 * j); e[j] = ldg4(e2 + 128 * j); }
-        float *g = G + ss * GIN_ROW + lane * 4;
+        float *g = G + si * GIN_ROW + lane * 4;
 #pragma unroll
         for (int j = 0; j < 3; j++) {
             float4 r;
@@ -165,6 +179,171 @@ __device__ __forceinline__ void gather_slice(float *__restrict__ G, const float 
     }
 }
 
+// ---- per-lane constants of a compute warp ----
+struct ComputeCtx {
+    uint32_t gid16;             // (lane >> 2) * 16
+    int gid, t;
+    int warp, lane;
+    uint32_t wA, metaA, wB, metaB;      // shared addresses (lane / slot offsets folded in)
+    uint32_t xs0;                       // shared address of state buffer 0
+    const uint32_t *dirA, *dirB;
+    const float *parA;                  // + 2t folded in
+    const float *parB;
+    const uint8_t *wBrec;
+    const uint32_t *rcp;
+    uint8_t *smem;
+    int gcol[GPW];                      // neuron index of this lane's first neuron of each group: 8*g + 2t
+    uint32_t xoff[GPW];                 // byte offset (in a state buffer) of this lane's two quantised neurons, stream gid of half 0
+};
+
+// One GRU_A + GRU_B step of half H (16 streams).  k0 = index of the half-step's first tile fill (gate r; z and h follow).
+template <int H>
+__device__ __forceinline__ void compute_half_step(const ComputeCtx &C, const SampleParams &P, float (&h)[GPW][4], float &hb,
+                                                  uint32_t k0, int cur, int f, int s_fin)
+{
+    uint8_t *smem = C.smem;
+    const int gid = C.gid, t = C.t, lane = C.lane, warp = C.warp;
+    const uint32_t *rcp = C.rcp;
+    const int nxt = cur ^ 1;
+    const uint32_t xs_cur = C.xs0 + cur * XS_BYTES + 8 * H;
+    uint8_t *xs_nxt = smem + SM_XS + nxt * XS_BYTES + 8 * H;
+    const uint32_t kr = k0, kz = k0 + 1, kh = k0 + 2;
+    const float *tile_r = reinterpret_cast<const float *>(smem + SM_TILES + (kr & 3) * TILE_BYTES) + gid * GIN_ROW;
+    const float *tile_z = reinterpret_cast<const float *>(smem + SM_TILES + (kz & 3) * TILE_BYTES) + gid * GIN_ROW;
+    uint8_t *tile_hb = smem + SM_TILES + (kh & 3) * TILE_BYTES;
+    const float *tile_h = reinterpret_cast<const float *>(tile_hb) + gid * GIN_ROW;
+    const uint32_t mb_full = smem_u32(smem + MB_FULL), mb_empty = smem_u32(smem + MB_EMPTY);
+
+    int Sh[GPW][4];                                              // candidate-gate GEMV sums; later (bit pattern) rec_h * r
+    int Sg[GPW][4];                                              // r-gate sums, later z-gate sums, later (bit pattern) z
+    // ---- GEMVs of the candidate and reset gates (need only the previous state) ----
+#pragma unroll
+    for (int sl = 0; sl < GPW; sl++) {
+        const uint32_t *dir = C.dirA + sl * 3 * 2;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { Sh[sl][i] = 0; Sg[sl][i] = 0; }
+        mma_quads(Sh[sl], C.wA + dir[4] * QUAD_BYTES, C.metaA + dir[4] * QUAD_META_BYTES, (int)dir[5], xs_cur, C.gid16);
+        mma_quads(Sg[sl], C.wA + dir[2] * QUAD_BYTES, C.metaA + dir[2] * QUAD_META_BYTES, (int)dir[3], xs_cur, C.gid16);
+    }
+    // ---- reset gate r (nnet.c:431-435) with the gathered input term; keep rec_h * r (nnet.c:436-440) ----
+    mbar_wait(mb_full + 8 * (kr & 3), (kr >> 2) & 1);
+#pragma unroll
+    for (int sl = 0; sl < GPW; sl++) {
+        const float *par = C.parA + sl * 3 * 16;
+        const float2 br = *reinterpret_cast<const float2 *>(par + 16), dr = *reinterpret_cast<const float2 *>(par + 24);
+        const float2 bh = *reinterpret_cast<const float2 *>(par + 32), dh = *reinterpret_cast<const float2 *>(par + 40);
+        const float bri[2] = {br.x, br.y}, dri[2] = {dr.x, dr.y}, bhi[2] = {bh.x, bh.y}, dhi[2] = {dh.x, dh.y};
+#pragma unroll
+        for (int jj = 0; jj < 2; jj++) {
+            const float2 gv = *reinterpret_cast<const float2 *>(tile_r + 8 * jj * GIN_ROW + C.gcol[sl]);
+            const float gin[2] = {gv.x, gv.y};
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                const float hv = h[sl][2 * jj + i];
+                const int acc = acc_init(__fadd_rn(__fadd_rn(bri[i], __fmul_rn(dri[i], hv)), gin[i])) + Sg[sl][2 * jj + i];
+                const float r = sigmoid_approx(acc_finish(acc), rcp);
+                const int acch = acc_init(__fadd_rn(bhi[i], __fmul_rn(dhi[i], hv))) + Sh[sl][2 * jj + i];
+                Sh[sl][2 * jj + i] = __float_as_int(__fmul_rn(acc_finish(acch), r));
+            }
+        }
+    }
+    warp_arrive(mb_empty + 8 * (kr & 3), lane);                  // gate-r tile consumed
+    // ---- update gate z (nnet.c:426-430) ----
+#pragma unroll
+    for (int sl = 0; sl < GPW; sl++) {
+        const uint32_t *dir = C.dirA + sl * 3 * 2;
+#pragma unroll
+        for (int i = 0; i < 4; i++) Sg[sl][i] = 0;
+        mma_quads(Sg[sl], C.wA + dir[0] * QUAD_BYTES, C.metaA + dir[0] * QUAD_META_BYTES, (int)dir[1], xs_cur, C.gid16);
+    }
+    mbar_wait(mb_full + 8 * (kz & 3), (kz >> 2) & 1);
+#pragma unroll
+    for (int sl = 0; sl < GPW; sl++) {
+        const float *par = C.parA + sl * 3 * 16;
+        const float2 bz = *reinterpret_cast<const float2 *>(par), dz = *reinterpret_cast<const float2 *>(par + 8);
+        const float bzi[2] = {bz.x, bz.y}, dzi[2] = {dz.x, dz.y};
+#pragma unroll
+        for (int jj = 0; jj < 2; jj++) {
+            const float2 gv = *reinterpret_cast<const float2 *>(tile_z + 8 * jj * GIN_ROW + C.gcol[sl]);
+            const float gin[2] = {gv.x, gv.y};
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                const int acc = acc_init(__fadd_rn(__fadd_rn(bzi[i], __fmul_rn(dzi[i], h[sl][2 * jj + i])), gin[i])) + Sg[sl][2 * jj + i];
+                Sg[sl][2 * jj + i] = __float_as_int(sigmoid_approx(acc_finish(acc), rcp));
+            }
+        }
+    }
+    warp_arrive(mb_empty + 8 * (kz & 3), lane);                  // gate-z tile consumed
+    // ---- h~ = tanh(rec_h*r + gin_h) (nnet.c:443-445), h <- z*h + (1-z)*h~ (nnet.c:446-447), new quantised state ----
+    mbar_wait(mb_full + 8 * (kh & 3), (kh >> 2) & 1);
+#pragma unroll
+    for (int sl = 0; sl < GPW; sl++)
+#pragma unroll
+        for (int jj = 0; jj < 2; jj++) {
+            const float2 gv = *reinterpret_cast<const float2 *>(tile_h + 8 * jj * GIN_ROW + C.gcol[sl]);
+            const float gin[2] = {gv.x, gv.y};
+            uint32_t q[2];
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                const float hh = tanh_approx(__fadd_rn(__int_as_float(Sh[sl][2 * jj + i]), gin[i]), rcp);
+                const float z = __int_as_float(Sg[sl][2 * jj + i]);
+                const float hn = __fadd_rn(__fmul_rn(z, h[sl][2 * jj + i]), __fmul_rn(__fsub_rn(1.f, z), hh));
+                h[sl][2 * jj + i] = hn;
+                q[i] = quant_u8(hn);
+            }
+            // other buffer: readers of the old state are unaffected
+            *reinterpret_cast<uint16_t *>(xs_nxt + C.xoff[sl] + 4 * jj) = (uint16_t)(q[0] | (q[1] << 8));
+        }
+    bar_sync(BAR_X, CNT_C);                                      // new quantised GRU_A state complete; candidate-gate tile dead: GRU_B scratch may use it
+
+    // ---------------- GRU_B input GEMV (48 x 384 int8, dense): warp = (row group, K part) ----------------
+    int *accB = reinterpret_cast<int *>(tile_hb + T_ACCB);
+    float *hBs = reinterpret_cast<float *>(tile_hb + T_HBS);
+    if (warp < NWB) {
+        int acc[4] = {0, 0, 0, 0};
+        const uint32_t q0 = C.dirB[warp * 2], nq = C.dirB[warp * 2 + 1];
+        mma_quads(acc, C.wB + q0 * QUAD_BYTES, C.metaB + q0 * QUAD_META_BYTES, (int)nq, C.xs0 + nxt * XS_BYTES + 8 * H, C.gid16);
+        const int rgp = warp / KPARTS, part = warp % KPARTS;
+        int *dst = accB + (part * 3 * NB + rgp * 8 + 2 * t) * ACCB_ROW + gid;
+        dst[0] = acc[0]; dst[ACCB_ROW] = acc[1]; dst[8] = acc[2]; dst[ACCB_ROW + 8] = acc[3];
+    }
+    // ---------------- GRU_B finish (nnet.c:346-371): warp < NFIN, lane = (neuron parity, stream of the half) ----------------
+    uint32_t *xb = reinterpret_cast<uint32_t *>(smem + SM_XB) + H * (2 * 4 * HALF);
+    if (warp < NFIN) {
+        const int jb = 2 * warp + (lane >> 4), si = lane & 15;
+        const float *condBp = P.condB + ((size_t)f * P.n_streams + s_fin) * (3 * NB);
+        const float cbz = __ldg(condBp + jb), cbr = __ldg(condBp + NB + jb), cbh = __ldg(condBp + 2 * NB + jb);
+        const uint32_t *xbc = xb + cur * 4 * HALF;
+        // recurrent side first: it only needs the previous GRU_B state, so it runs while other warps finish their partial sums
+        int rz = acc_init(C.parB[3 * NB + jb]), rr = acc_init(C.parB[4 * NB + jb]), rh = acc_init(C.parB[5 * NB + jb]);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {    // W_rec layout [out/8][in/4][8][4] (dump_lpcnet.py:58-59)
+            const uint32_t xw = xbc[k * HALF + si];
+            rz = dp4a_us(xw, *reinterpret_cast<const int *>(C.wBrec + (((jb >> 3) * 4 + k) * 8 + (jb & 7)) * 4), rz);
+            rr = dp4a_us(xw, *reinterpret_cast<const int *>(C.wBrec + ((((NB + jb) >> 3) * 4 + k) * 8 + ((NB + jb) & 7)) * 4), rr);
+            rh = dp4a_us(xw, *reinterpret_cast<const int *>(C.wBrec + ((((2 * NB + jb) >> 3) * 4 + k) * 8 + ((2 * NB + jb) & 7)) * 4), rh);
+        }
+        bar_sync(BAR_ACCB, CNT_C);                               // all K-part partial sums are in accB
+        int az = acc_init(__fadd_rn(C.parB[jb], cbz)), ar = acc_init(__fadd_rn(C.parB[NB + jb], cbr)), ah = acc_init(__fadd_rn(C.parB[2 * NB + jb], cbh));
+#pragma unroll
+        for (int kp = 0; kp < KPARTS; kp++) {
+            az += accB[(kp * 3 * NB + jb) * ACCB_ROW + si];
+            ar += accB[(kp * 3 * NB + NB + jb) * ACCB_ROW + si];
+            ah += accB[(kp * 3 * NB + 2 * NB + jb) * ACCB_ROW + si];
+        }
+        const float zz = sigmoid_approx(__fadd_rn(acc_finish(az), acc_finish(rz)), rcp);
+        const float rrr = sigmoid_approx(__fadd_rn(acc_finish(ar), acc_finish(rr)), rcp);
+        const float hh = tanh_approx(__fadd_rn(acc_finish(ah), __fmul_rn(acc_finish(rh), rrr)), rcp);
+        hb = __fadd_rn(__fmul_rn(zz, hb), __fmul_rn(__fsub_rn(1.f, zz), hh));
+        hBs[jb * HALF + si] = hb;
+        reinterpret_cast<uint8_t *>(xb + nxt * 4 * HALF)[((jb >> 2) * HALF + si) * 4 + (jb & 3)] = (uint8_t)quant_u8(hb);
+        warp_arrive(smem_u32(smem + MB_HB) + 8 * H, lane);       // GRU_B state of this sample is in hBs
+    } else {
+        bar_sync(BAR_ACCB, CNT_C);
+    }
+    warp_arrive(mb_empty + 8 * (kh & 3), lane);                  // (its refill is additionally gated by the half's next indices)
+}
+
 }  // namespace
 
 __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const __grid_constant__ SampleParams P)
@@ -174,14 +353,14 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = P.n_streams;
     const int cta_s0 = blockIdx.x * STREAMS_PER_CTA;
-    const int s_raw = cta_s0 + lane;
-    const bool live = s_raw < n;
-    const int s = live ? s_raw : n - 1;          // dead lanes shadow the last stream (all loads valid), stores masked
+    const int spf = P.spf;
 
-    // ---- stage the constant image with TMA bulk copies ----
-    const uint32_t bar = smem_u32(smem + SM_MBAR);
+    // ---- mbarriers; stage the constant image with TMA bulk copies ----
+    const uint32_t bar = smem_u32(smem + MB_IMAGE);
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
+        for (int b = 0; b < NTILE; b++) { mbar_init(smem_u32(smem + MB_FULL) + 8 * b, NWP); mbar_init(smem_u32(smem + MB_EMPTY) + 8 * b, NWC); }
+        for (int hh = 0; hh < 2; hh++) { mbar_init(smem_u32(smem + MB_IDX) + 8 * hh, 1); mbar_init(smem_u32(smem + MB_HB) + 8 * hh, NFIN); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -193,251 +372,117 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
             bulk_g2s(smem_u32(smem + SM_IMAGE + o), P.image + o, nbytes, bar);
         }
     }
-
     const uint32_t *rcp = reinterpret_cast<const uint32_t *>(smem + SM_IMAGE + IM_RCP);
-    uint8_t *xs = smem + SM_XS;
-    uint32_t *xbw = reinterpret_cast<uint32_t *>(smem + SM_XB);   // quantised GRU_B state, [4 words][32 lanes], lane == stream
-    int *accB = reinterpret_cast<int *>(smem + SM_ACCB);
-    float *hBs = reinterpret_cast<float *>(smem + SM_HBS);
     int *idx_s = reinterpret_cast<int *>(smem + SM_IDX);
-    float *tile0 = reinterpret_cast<float *>(smem + SM_T0);
-    float *tile1 = reinterpret_cast<float *>(smem + SM_T1);
-    const int spf = P.spf;
 
     if (warp < NWC) {
         // =====================================================  compute warps  =====================================================
         mbar_wait(bar, 0);
-        const int gid = lane >> 2, t = lane & 3;                         // MMA fragment coordinates of this lane
-        const uint32_t gid16 = gid * 16;
+        ComputeCtx C;
+        C.gid = lane >> 2; C.t = lane & 3; C.gid16 = C.gid * 16; C.warp = warp; C.lane = lane; C.smem = smem; C.rcp = rcp;
         const uint32_t *grpA = reinterpret_cast<const uint32_t *>(smem + SM_IMAGE + IM_GRPA);
-        const uint32_t *dirA = reinterpret_cast<const uint32_t *>(smem + SM_IMAGE + IM_DIRA) + warp * GPW * 3 * 2;
-        const float *parA = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_PARA) + warp * GPW * 3 * 16 + 2 * t;
-        const uint32_t metaA = smem_u32(smem + L.metaA) + t * 2;
-        const uint32_t wA = smem_u32(smem + L.wA) + lane * 4;
-        const uint32_t *dirB = reinterpret_cast<const uint32_t *>(smem + SM_IMAGE + IM_DIRB);
-        const uint32_t metaB = smem_u32(smem + L.metaB) + t * 2;
-        const uint32_t wB = smem_u32(smem + L.wB) + lane * 4;
-        const float *parB = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_PARB);
-        const uint8_t *wBrec = smem + SM_IMAGE + IM_WBREC;
-        const uint32_t xs0 = smem_u32(xs);
-        // the 4 streams of this lane (rows gid, gid+8 of the two MMAs); dead streams shadow the last one, stores masked
+        C.dirA = reinterpret_cast<const uint32_t *>(smem + SM_IMAGE + IM_DIRA) + warp * GPW * 3 * 2;
+        C.parA = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_PARA) + warp * GPW * 3 * 16 + 2 * C.t;
+        C.metaA = smem_u32(smem + L.metaA) + C.t * 2;
+        C.wA = smem_u32(smem + L.wA) + lane * 4;
+        C.dirB = reinterpret_cast<const uint32_t *>(smem + SM_IMAGE + IM_DIRB);
+        C.metaB = smem_u32(smem + L.metaB) + C.t * 2;
+        C.wB = smem_u32(smem + L.wB) + lane * 4;
+        C.parB = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_PARB);
+        C.wBrec = smem + SM_IMAGE + IM_WBREC;
+        C.xs0 = smem_u32(smem + SM_XS);
+        // the streams of this lane: cta_s0 + 16*half + gid + 8*jj; dead streams shadow the last one, stores masked
         int sj[4]; bool livej[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) { const int r = cta_s0 + gid + 8 * j; livej[j] = r < n; sj[j] = livej[j] ? r : n - 1; }
+        for (int j = 0; j < 4; j++) { const int r = cta_s0 + C.gid + 8 * j; livej[j] = r < n; sj[j] = livej[j] ? r : n - 1; }
 
-        int gcol[GPW];                                                   // tile column / neuron index of this lane's first neuron: 8*g + 2t
-        uint32_t xoff[GPW];                                              // byte offset (in a state buffer) of this lane's two quantised neurons, stream gid
-        float h[GPW][8];                                                 // fp32 state: [stream j][neuron i] at 2j+i
+        float h[2][GPW][4];                                              // fp32 state: [half][group][stream jj][neuron i] at 2jj+i
 #pragma unroll
         for (int sl = 0; sl < GPW; sl++) {
             const int g = (int)grpA[warp * GPW + sl];
-            gcol[sl] = 8 * g + 2 * t;
-            xoff[sl] = xs_offset(2 * g + (t >> 1), gid) + (t & 1) * 2;
+            C.gcol[sl] = 8 * g + 2 * C.t;
+            C.xoff[sl] = xs_offset(2 * g + (C.t >> 1), C.gid) + (C.t & 1) * 2;
 #pragma unroll
             for (int j = 0; j < 4; j++)
 #pragma unroll
-                for (int i = 0; i < 2; i++) h[sl][2 * j + i] = P.hA[(size_t)(gcol[sl] + i) * n + sj[j]];
+                for (int i = 0; i < 2; i++) h[j >> 1][sl][2 * (j & 1) + i] = P.hA[(size_t)(C.gcol[sl] + i) * n + sj[j]];
         }
-        // GRU_B neurons finished by this warp (lane == stream there): jb = warp + k*NWC < NB
-        float hb[NBW];
+        // GRU_B neuron finished by this lane (warps < NFIN): neuron 2*warp + (lane >> 4), stream lane & 15 of each half
+        const int jb_fin = min(2 * warp + (lane >> 4), NB - 1);
+        int s_fin[2]; bool live_fin[2];
+        float hb[2];
 #pragma unroll
-        for (int k = 0; k < NBW; k++) hb[k] = P.hB[(size_t)min(warp + k * NWC, NB - 1) * n + s];
-        // quantised copies of the restored state: xs <- q(hA), xb[0] <- q(hB)
+        for (int hh = 0; hh < 2; hh++) {
+            const int r = cta_s0 + HALF * hh + (lane & 15);
+            live_fin[hh] = r < n; s_fin[hh] = live_fin[hh] ? r : n - 1;
+            hb[hh] = P.hB[(size_t)jb_fin * n + s_fin[hh]];
+        }
+        // quantised copies of the restored state: xs buffer 0 <- q(hA), xb[half][0] <- q(hB)
 #pragma unroll
         for (int sl = 0; sl < GPW; sl++)
 #pragma unroll
             for (int j = 0; j < 4; j++)
-                *reinterpret_cast<uint16_t *>(xs + xoff[sl] + 4 * j) = (uint16_t)(quant_u8(h[sl][2 * j]) | (quant_u8(h[sl][2 * j + 1]) << 8));
+                *reinterpret_cast<uint16_t *>(smem + SM_XS + C.xoff[sl] + 4 * j) =
+                    (uint16_t)(quant_u8(h[j >> 1][sl][2 * (j & 1)]) | (quant_u8(h[j >> 1][sl][2 * (j & 1) + 1]) << 8));
+        if (warp < NFIN) {
 #pragma unroll
-        for (int k = 0; k < NBW; k++) {
-            const int jb = warp + k * NWC;
-            if (jb < NB) reinterpret_cast<uint8_t *>(xbw)[((jb >> 2) * 32 + lane) * 4 + (jb & 3)] = (uint8_t)quant_u8(hb[k]);
+            for (int hh = 0; hh < 2; hh++)
+                reinterpret_cast<uint8_t *>(smem + SM_XB)[(((hh * 2 + 0) * 4 + (jb_fin >> 2)) * HALF + (lane & 15)) * 4 + (jb_fin & 3)] = (uint8_t)quant_u8(hb[hh]);
         }
         bar_sync(BAR_X, CNT_C);                                          // restored quantised state visible to all compute warps
 
-        int step = 0;
-        for (int f = 0; f < P.nframes; f++) {
-            const float *condBp = P.condB + ((size_t)f * n + s) * (3 * NB);
-            float cbz[NBW], cbr[NBW], cbh[NBW];
-#pragma unroll
-            for (int k = 0; k < NBW; k++) {
-                const int jb = min(warp + k * NWC, NB - 1);
-                cbz[k] = __ldg(condBp + jb); cbr[k] = __ldg(condBp + NB + jb); cbh[k] = __ldg(condBp + 2 * NB + jb);
+        uint32_t k = 0; int step = 0;
+        for (int f = 0; f < P.nframes; f++)
+            for (int t_ = 0; t_ < spf; t_++, step++, k += 6) {
+                compute_half_step<0>(C, P, h[0], hb[0], k, step & 1, f, s_fin[0]);
+                compute_half_step<1>(C, P, h[1], hb[1], k + 3, step & 1, f, s_fin[1]);
             }
-            for (int t_ = 0; t_ < spf; t_++, step++) {
-                const int cur = step & 1, nxt = cur ^ 1;                 // double buffers of the quantised states
-                const uint32_t xs_cur = xs0 + cur * XS_BYTES;
-                uint8_t *xs_nxt = xs + nxt * XS_BYTES;
-                int Sh[GPW][8];                                          // candidate-gate GEMV sums; later (bit pattern) rec_h * r, then h~
-                // ---- A: candidate-gate GEMV  S_h = W_h . q(h)   (needs only the previous state: overlaps sampler + gather) ----
-#pragma unroll
-                for (int sl = 0; sl < GPW; sl++) {
-                    const uint32_t *dir = dirA + sl * 3 * 2;
-#pragma unroll
-                    for (int i = 0; i < 8; i++) Sh[sl][i] = 0;
-                    mma_quads(Sh[sl], wA + dir[4] * QUAD_BYTES, metaA + dir[4] * QUAD_META_BYTES, (int)dir[5], xs_cur, gid16);
-                }
-                // ---- B: reset gate r (nnet.c:431-435): GEMV first, then the gathered input term from tile 0 ----
-#pragma unroll
-                for (int sl = 0; sl < GPW; sl++) {
-                    const float *par = parA + sl * 3 * 16;
-                    const uint32_t *dir = dirA + sl * 3 * 2;
-                    int Sr[8];
-#pragma unroll
-                    for (int i = 0; i < 8; i++) Sr[i] = 0;
-                    mma_quads(Sr, wA + dir[2] * QUAD_BYTES, metaA + dir[2] * QUAD_META_BYTES, (int)dir[3], xs_cur, gid16);
-                    if (sl == 0) bar_sync(BAR_FULL0, CNT_FULL);          // gate r of all 32 streams is in tile 0
-                    const float2 br = *reinterpret_cast<const float2 *>(par + 16), dr = *reinterpret_cast<const float2 *>(par + 24);
-                    const float2 bh = *reinterpret_cast<const float2 *>(par + 32), dh = *reinterpret_cast<const float2 *>(par + 40);
-                    const float bri[2] = {br.x, br.y}, dri[2] = {dr.x, dr.y}, bhi[2] = {bh.x, bh.y}, dhi[2] = {dh.x, dh.y};
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const float2 gv = *reinterpret_cast<const float2 *>(tile0 + (gid + 8 * j) * GIN_ROW + gcol[sl]);
-                        const float gin[2] = {gv.x, gv.y};
-#pragma unroll
-                        for (int i = 0; i < 2; i++) {
-                            const float hv = h[sl][2 * j + i];
-                            const int acc = acc_init(__fadd_rn(__fadd_rn(bri[i], __fmul_rn(dri[i], hv)), gin[i])) + Sr[2 * j + i];
-                            const float r = sigmoid_approx(acc_finish(acc), rcp);
-                            // candidate pre-activation: rec_h = bias + diag*h (+ GEMV), no input term (nnet.c:436-440); keep rec_h * r
-                            const int acch = acc_init(__fadd_rn(bhi[i], __fmul_rn(dhi[i], hv))) + Sh[sl][2 * j + i];
-                            Sh[sl][2 * j + i] = __float_as_int(__fmul_rn(acc_finish(acch), r));
-                        }
-                    }
-                }
-                bar_arrive(BAR_EMPTY0, CNT_FULL);                        // tile 0 may now receive gate z
-                // ---- C: h~ = tanh(rec_h*r + gin_h) from tile 1 (nnet.c:443-445) ----
-                bar_sync(BAR_FULL1, CNT_FULL);                           // gate h is in tile 1
-#pragma unroll
-                for (int sl = 0; sl < GPW; sl++)
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const float2 gv = *reinterpret_cast<const float2 *>(tile1 + (gid + 8 * j) * GIN_ROW + gcol[sl]);
-                        Sh[sl][2 * j] = __float_as_int(tanh_approx(__fadd_rn(__int_as_float(Sh[sl][2 * j]), gv.x), rcp));
-                        Sh[sl][2 * j + 1] = __float_as_int(tanh_approx(__fadd_rn(__int_as_float(Sh[sl][2 * j + 1]), gv.y), rcp));
-                    }
-                // ---- D: update gate z (GEMV + input term from tile 0, 2nd phase), h <- z*h + (1-z)*h~ (nnet.c:446-447), new state ----
-#pragma unroll
-                for (int sl = 0; sl < GPW; sl++) {
-                    const float *par = parA + sl * 3 * 16;
-                    const uint32_t *dir = dirA + sl * 3 * 2;
-                    int Sz[8];
-#pragma unroll
-                    for (int i = 0; i < 8; i++) Sz[i] = 0;
-                    mma_quads(Sz, wA + dir[0] * QUAD_BYTES, metaA + dir[0] * QUAD_META_BYTES, (int)dir[1], xs_cur, gid16);
-                    if (sl == 0) bar_sync(BAR_FULL0, CNT_FULL);          // gate z of all 32 streams is in tile 0
-                    const float2 bz = *reinterpret_cast<const float2 *>(par), dz = *reinterpret_cast<const float2 *>(par + 8);
-                    const float bzi[2] = {bz.x, bz.y}, dzi[2] = {dz.x, dz.y};
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const float2 gv = *reinterpret_cast<const float2 *>(tile0 + (gid + 8 * j) * GIN_ROW + gcol[sl]);
-                        const float gin[2] = {gv.x, gv.y};
-                        uint32_t q[2];
-#pragma unroll
-                        for (int i = 0; i < 2; i++) {
-                            const float hv = h[sl][2 * j + i];
-                            const int acc = acc_init(__fadd_rn(__fadd_rn(bzi[i], __fmul_rn(dzi[i], hv)), gin[i])) + Sz[2 * j + i];
-                            const float z = sigmoid_approx(acc_finish(acc), rcp);
-                            const float hn = __fadd_rn(__fmul_rn(z, hv), __fmul_rn(__fsub_rn(1.f, z), __int_as_float(Sh[sl][2 * j + i])));
-                            h[sl][2 * j + i] = hn;
-                            q[i] = quant_u8(hn);
-                        }
-                        // other buffer: readers of the old state are unaffected
-                        *reinterpret_cast<uint16_t *>(xs_nxt + xoff[sl] + 4 * j) = (uint16_t)(q[0] | (q[1] << 8));
-                    }
-                }
-                bar_sync(BAR_X, CNT_C);                                  // new quantised GRU_A state complete (tile 1 is dead: accB/hBs may use it)
-
-                // ---------------- E: GRU_B input GEMV (48 x 384 int8, dense): warp = (row group, K part) ----------------
-                if (warp < NWB) {
-                    int acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                    const uint32_t q0 = dirB[warp * 2], nq = dirB[warp * 2 + 1];
-                    mma_quads(acc, wB + q0 * QUAD_BYTES, metaB + q0 * QUAD_META_BYTES, (int)nq, xs0 + nxt * XS_BYTES, gid16);
-                    const int rgp = warp / KPARTS, part = warp % KPARTS;
-                    int *dst = accB + (part * 3 * NB + rgp * 8 + 2 * t) * ACCB_ROW + gid;
-#pragma unroll
-                    for (int j = 0; j < 4; j++) { dst[8 * j] = acc[2 * j]; dst[ACCB_ROW + 8 * j] = acc[2 * j + 1]; }
-                }
-                // ---------------- GRU_B finish (nnet.c:346-371), lane == stream: neurons warp, warp + NWC, ... ----------------
-                {
-                    const uint32_t *xbc = xbw + cur * 4 * 32;
-                    const uint32_t xw[4] = {xbc[lane], xbc[32 + lane], xbc[64 + lane], xbc[96 + lane]};
-                    uint8_t *xbn = reinterpret_cast<uint8_t *>(xbw + nxt * 4 * 32);
-                    // recurrent side first: it only needs the previous GRU_B state, so it runs while other warps finish their partial sums
-                    int rz[NBW], rr[NBW], rh[NBW];
-#pragma unroll
-                    for (int k2 = 0; k2 < NBW; k2++) {
-                        const int jb = min(warp + k2 * NWC, NB - 1);
-                        rz[k2] = acc_init(parB[3 * NB + jb]); rr[k2] = acc_init(parB[4 * NB + jb]); rh[k2] = acc_init(parB[5 * NB + jb]);
-#pragma unroll
-                        for (int k = 0; k < 4; k++) {    // W_rec layout [out/8][in/4][8][4] (dump_lpcnet.py:58-59)
-                            rz[k2] = dp4a_us(xw[k], *reinterpret_cast<const int *>(wBrec + (((jb >> 3) * 4 + k) * 8 + (jb & 7)) * 4), rz[k2]);
-                            rr[k2] = dp4a_us(xw[k], *reinterpret_cast<const int *>(wBrec + ((((NB + jb) >> 3) * 4 + k) * 8 + ((NB + jb) & 7)) * 4), rr[k2]);
-                            rh[k2] = dp4a_us(xw[k], *reinterpret_cast<const int *>(wBrec + ((((2 * NB + jb) >> 3) * 4 + k) * 8 + ((2 * NB + jb) & 7)) * 4), rh[k2]);
-                        }
-                    }
-                    bar_sync(BAR_ACCB, CNT_C);                           // all K-part partial sums are in accB
-#pragma unroll
-                    for (int k2 = 0; k2 < NBW; k2++) {
-                        const int jb = warp + k2 * NWC;
-                        if (jb >= NB) break;
-                        int az = acc_init(__fadd_rn(parB[jb], cbz[k2])), ar = acc_init(__fadd_rn(parB[NB + jb], cbr[k2])), ah = acc_init(__fadd_rn(parB[2 * NB + jb], cbh[k2]));
-#pragma unroll
-                        for (int kp = 0; kp < KPARTS; kp++) {
-                            az += accB[(kp * 3 * NB + jb) * ACCB_ROW + lane];
-                            ar += accB[(kp * 3 * NB + NB + jb) * ACCB_ROW + lane];
-                            ah += accB[(kp * 3 * NB + 2 * NB + jb) * ACCB_ROW + lane];
-                        }
-                        const float zz = sigmoid_approx(__fadd_rn(acc_finish(az), acc_finish(rz[k2])), rcp);
-                        const float rrr = sigmoid_approx(__fadd_rn(acc_finish(ar), acc_finish(rr[k2])), rcp);
-                        const float hh = tanh_approx(__fadd_rn(acc_finish(ah), __fmul_rn(acc_finish(rh[k2]), rrr)), rcp);
-                        hb[k2] = __fadd_rn(__fmul_rn(zz, hb[k2]), __fmul_rn(__fsub_rn(1.f, zz), hh));
-                        hBs[jb * 32 + lane] = hb[k2];
-                        xbn[((jb >> 2) * 32 + lane) * 4 + (jb & 3)] = (uint8_t)quant_u8(hb[k2]);
-                    }
-                }
-                __threadfence_block();
-                bar_arrive(BAR_HB, CNT_HB);                              // GRU_B state of this sample is in hBs
-            }
-        }
         // ---- save the recurrent state ----
 #pragma unroll
         for (int sl = 0; sl < GPW; sl++)
 #pragma unroll
             for (int j = 0; j < 4; j++)
                 if (livej[j]) {
-                    P.hA[(size_t)gcol[sl] * n + sj[j]] = h[sl][2 * j];
-                    P.hA[(size_t)(gcol[sl] + 1) * n + sj[j]] = h[sl][2 * j + 1];
+                    P.hA[(size_t)C.gcol[sl] * n + sj[j]] = h[j >> 1][sl][2 * (j & 1)];
+                    P.hA[(size_t)(C.gcol[sl] + 1) * n + sj[j]] = h[j >> 1][sl][2 * (j & 1) + 1];
                 }
-        if (live) {
+        if (warp < NFIN) {
 #pragma unroll
-            for (int k = 0; k < NBW; k++) if (warp + k * NWC < NB) P.hB[(size_t)(warp + k * NWC) * n + s] = hb[k];
+            for (int hh = 0; hh < 2; hh++) if (live_fin[hh]) P.hB[(size_t)jb_fin * n + s_fin[hh]] = hb[hh];
         }
     } else if (warp < NWC + NWP) {
         // =====================================================  producer warps  =====================================================
         const int p = warp - NWC;
+        const uint32_t mb_full = smem_u32(smem + MB_FULL), mb_empty = smem_u32(smem + MB_EMPTY), mb_idx = smem_u32(smem + MB_IDX);
+        uint32_t k = 0, it = 0;
         for (int f = 0; f < P.nframes; f++) {
             const float *condA_f = P.condA + (size_t)f * n * (3 * NA);
-            for (int t = 0; t < spf; t++) {
-                bar_sync(BAR_IDX, CNT_IDX);                              // indices of this sample are in idx_s
-                gather_slice(tile0, condA_f, n, cta_s0, P.emb_sig, P.emb_pred, P.emb_exc, idx_s, 1, p, lane);   // gate r
-                __threadfence_block();
-                bar_arrive(BAR_FULL0, CNT_FULL);
-                gather_slice(tile1, condA_f, n, cta_s0, P.emb_sig, P.emb_pred, P.emb_exc, idx_s, 2, p, lane);   // gate h
-                __threadfence_block();
-                bar_arrive(BAR_FULL1, CNT_FULL);
-                bar_sync(BAR_EMPTY0, CNT_FULL);                          // gate r consumed
-                gather_slice(tile0, condA_f, n, cta_s0, P.emb_sig, P.emb_pred, P.emb_exc, idx_s, 0, p, lane);   // gate z
-                __threadfence_block();
-                bar_arrive(BAR_FULL0, CNT_FULL);
-            }
+            for (int t_ = 0; t_ < spf; t_++, it++)
+#pragma unroll 1
+                for (int hh = 0; hh < 2; hh++) {
+                    mbar_wait(mb_idx + 8 * hh, it & 1);                  // indices of this sample of the half are in idx_s
+#pragma unroll 1
+                    for (int gi = 0; gi < 3; gi++, k++) {
+                        const int gate = gi == 0 ? 1 : (gi == 1 ? 0 : 2);    // fill order r, z, h
+                        mbar_wait(mb_empty + 8 * (k & 3), ((k >> 2) & 1) ^ 1);  // previous contents of the tile consumed
+                        gather_half(reinterpret_cast<float *>(smem + SM_TILES + (k & 3) * TILE_BYTES), condA_f, n, cta_s0 + HALF * hh,
+                                    P.emb_sig, P.emb_pred, P.emb_exc, idx_s + hh * 3 * HALF, gate, p, lane);
+                        warp_arrive(mb_full + 8 * (k & 3), lane);
+                    }
+                }
         }
     } else {
         // =====================================================  sampler warp  =====================================================
         mbar_wait(bar, 0);
+        const int s_raw = cta_s0 + lane;
+        const bool live = s_raw < n;
+        const int s = live ? s_raw : n - 1;          // dead lanes shadow the last stream (all loads valid), stores masked
+        const int myh = lane >> 4, si = lane & 15;
         const float *logit = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_LOGIT);
         const float *u2l = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_U2L);
         const float *fcw = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_FCW);
+        const uint32_t mb_idx = smem_u32(smem + MB_IDX), mb_hb = smem_u32(smem + MB_HB);
+        int *idx_h = idx_s + myh * 3 * HALF;
 
         float ls[LPC_ORDER], lpc[LPC_ORDER];
 #pragma unroll
@@ -447,88 +492,104 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
         Kiss99 rng;
         rng.z = P.rng[s]; rng.w = P.rng[(size_t)n + s]; rng.jsr = P.rng[2 * (size_t)n + s]; rng.jcong = P.rng[3 * (size_t)n + s];
         short *pcm_out = P.pcm + (size_t)s * P.pcm_stream_stride;
+        float pred = 0.f;
 
-        for (int f = 0; f < P.nframes; f++) {
-            {   // frame f uses the LPC computed from the features of frame f-2 (lpcnet.c:110-112), weighted by gamma^i (freq.c:299-308)
-                const float *lp = P.lpc_raw + ((size_t)f * n + s) * LPC_ORDER;
-                const float4 a = ldg4(lp), b = ldg4(lp + 4), c = ldg4(lp + 8), d = ldg4(lp + 12);
-                const float raw[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
-#pragma unroll
-                for (int j = 0; j < LPC_ORDER; j++) lpc[j] = __fmul_rn(raw[j], __ldg(&P.gamma_pow[j]));
-            }
-            for (int t = 0; t < spf; t++) {
-                // prediction and conditioning indices of this sample (lpcnet.c:251-254)
-                float pred = 0.f;
+        // publish the conditioning indices of the half's next sample (lpcnet.c:251-254); the lanes of the other half idle
+        auto publish = [&](int hh) {
+            if (myh == hh) {
+                pred = 0.f;
 #pragma unroll
                 for (int j = 0; j < LPC_ORDER; j++) pred = __fsub_rn(pred, __fmul_rn(ls[j], lpc[j]));
-                idx_s[lane] = lin2ulaw(ls[0]);
-                idx_s[32 + lane] = lin2ulaw(pred);
-                idx_s[64 + lane] = last_exc;
-                __threadfence_block();
-                bar_arrive(BAR_IDX, CNT_IDX);
-                // thresholds (nnet.c:178-184): two RNG words -> 8 logits; does not depend on the network
-                float thr[8];
-                {
-                    uint32_t r0 = kiss99_rand(rng), r1 = kiss99_rand(rng);
-                    thr[0] = logit[r0 & 0xFF]; thr[1] = logit[(r0 >> 8) & 0xFF]; thr[2] = logit[(r0 >> 16) & 0xFF]; thr[3] = logit[r0 >> 24];
-                    thr[4] = logit[r1 & 0xFF]; thr[5] = logit[(r1 >> 8) & 0xFF]; thr[6] = logit[(r1 >> 16) & 0xFF]; thr[7] = logit[r1 >> 24];
-                }
-                bar_sync(BAR_HB, CNT_HB);                                // wait for GRU_B
-                float hbv[NB];
+                idx_h[si] = lin2ulaw(ls[0]);
+                idx_h[HALF + si] = lin2ulaw(pred);
+                idx_h[2 * HALF + si] = last_exc;
+            }
+            warp_arrive(mb_idx + 8 * hh, lane);
+        };
+        auto load_lpc = [&](int f) {   // frame f uses the LPC computed from the features of frame f-2 (lpcnet.c:110-112), weighted by gamma^i (freq.c:299-308)
+            const float *lp = P.lpc_raw + ((size_t)f * n + s) * LPC_ORDER;
+            const float4 a = ldg4(lp), b = ldg4(lp + 4), c = ldg4(lp + 8), d = ldg4(lp + 12);
+            const float raw[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
 #pragma unroll
-                for (int j = 0; j < NB; j++) hbv[j] = hBs[j * 32 + lane];
-                int val = 0;
-#pragma unroll
-                for (int b = 0; b < 8; b++) {                            // sample_mdense, nnet.c:186-211
-                    const int i = (1 << b) | val;
-                    float sum1, sum2, fac1, fac2;
-                    // two sequential 16-term chains (one per channel), fed 8 weights at a time to keep the live set small
-                    if (b < 6) {                                         // nodes < 64: rows in shared memory
-                        const float *wr = fcw + i * FCW_ROW;
-                        const float4 bf = *reinterpret_cast<const float4 *>(wr + 32);
-                        sum1 = bf.x; sum2 = bf.y; fac1 = bf.z; fac2 = bf.w;
-#pragma unroll
-                        for (int j0 = 0; j0 < NB; j0 += 8) {
-                            const float4 a0 = *reinterpret_cast<const float4 *>(wr + j0), a1 = *reinterpret_cast<const float4 *>(wr + j0 + 4);
-                            const float4 c0 = *reinterpret_cast<const float4 *>(wr + NB + j0), c1 = *reinterpret_cast<const float4 *>(wr + NB + j0 + 4);
-                            const float wa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, wc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-#pragma unroll
-                            for (int j = 0; j < 8; j++) {
-                                sum1 = __fadd_rn(sum1, __fmul_rn(wa[j], hbv[j0 + j]));
-                                sum2 = __fadd_rn(sum2, __fmul_rn(wc[j], hbv[j0 + j]));
-                            }
+            for (int j = 0; j < LPC_ORDER; j++) lpc[j] = __fmul_rn(raw[j], __ldg(&P.gamma_pow[j]));
+        };
+        load_lpc(0);
+        publish(0); publish(1);
+        uint32_t it = 0, k = 0;
+        for (int f = 0; f < P.nframes; f++) {
+            for (int t_ = 0; t_ < spf; t_++, it++, k += 6) {
+                const bool last_t = t_ == spf - 1, last = last_t && f == P.nframes - 1;
+#pragma unroll 1
+                for (int hh = 0; hh < 2; hh++) {
+                    mbar_wait(mb_hb + 8 * hh, it & 1);                   // GRU_B state of the half is in hBs (inside the half's candidate-gate tile)
+                    if (myh == hh) {
+                        const float *hBs = reinterpret_cast<const float *>(smem + SM_TILES + ((k + 3 * hh + 2) & 3) * TILE_BYTES + T_HBS);
+                        // thresholds (nnet.c:178-184): two RNG words -> 8 logits
+                        float thr[8];
+                        {
+                            uint32_t r0 = kiss99_rand(rng), r1 = kiss99_rand(rng);
+                            thr[0] = logit[r0 & 0xFF]; thr[1] = logit[(r0 >> 8) & 0xFF]; thr[2] = logit[(r0 >> 16) & 0xFF]; thr[3] = logit[r0 >> 24];
+                            thr[4] = logit[r1 & 0xFF]; thr[5] = logit[(r1 >> 8) & 0xFF]; thr[6] = logit[(r1 >> 16) & 0xFF]; thr[7] = logit[r1 >> 24];
                         }
-                    } else {                                             // lower levels: one 144-byte row per lane from global (L2-resident)
-                        const float *wr = P.fcw + i * FCW_ROW;
-                        const float4 bf = ldg4(wr + 32);
-                        sum1 = bf.x; sum2 = bf.y; fac1 = bf.z; fac2 = bf.w;
+                        float hbv[NB];
 #pragma unroll
-                        for (int j0 = 0; j0 < NB; j0 += 8) {
-                            const float4 a0 = ldg4(wr + j0), a1 = ldg4(wr + j0 + 4), c0 = ldg4(wr + NB + j0), c1 = ldg4(wr + NB + j0 + 4);
-                            const float wa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, wc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                        for (int j = 0; j < NB; j++) hbv[j] = hBs[j * HALF + si];
+                        int val = 0;
 #pragma unroll
-                            for (int j = 0; j < 8; j++) {
-                                sum1 = __fadd_rn(sum1, __fmul_rn(wa[j], hbv[j0 + j]));
-                                sum2 = __fadd_rn(sum2, __fmul_rn(wc[j], hbv[j0 + j]));
+                        for (int b = 0; b < 8; b++) {                    // sample_mdense, nnet.c:186-211
+                            const int i = (1 << b) | val;
+                            float sum1, sum2, fac1, fac2;
+                            // two sequential 16-term chains (one per channel), fed 8 weights at a time to keep the live set small
+                            if (b < 6) {                                 // nodes < 64: rows in shared memory
+                                const float *wr = fcw + i * FCW_ROW;
+                                const float4 bf = *reinterpret_cast<const float4 *>(wr + 32);
+                                sum1 = bf.x; sum2 = bf.y; fac1 = bf.z; fac2 = bf.w;
+#pragma unroll
+                                for (int j0 = 0; j0 < NB; j0 += 8) {
+                                    const float4 a0 = *reinterpret_cast<const float4 *>(wr + j0), a1 = *reinterpret_cast<const float4 *>(wr + j0 + 4);
+                                    const float4 c0 = *reinterpret_cast<const float4 *>(wr + NB + j0), c1 = *reinterpret_cast<const float4 *>(wr + NB + j0 + 4);
+                                    const float wa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, wc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+                                    for (int j = 0; j < 8; j++) {
+                                        sum1 = __fadd_rn(sum1, __fmul_rn(wa[j], hbv[j0 + j]));
+                                        sum2 = __fadd_rn(sum2, __fmul_rn(wc[j], hbv[j0 + j]));
+                                    }
+                                }
+                            } else {                                     // lower levels: one 144-byte row per lane from global (L2-resident)
+                                const float *wr = P.fcw + i * FCW_ROW;
+                                const float4 bf = ldg4(wr + 32);
+                                sum1 = bf.x; sum2 = bf.y; fac1 = bf.z; fac2 = bf.w;
+#pragma unroll
+                                for (int j0 = 0; j0 < NB; j0 += 8) {
+                                    const float4 a0 = ldg4(wr + j0), a1 = ldg4(wr + j0 + 4), c0 = ldg4(wr + NB + j0), c1 = ldg4(wr + NB + j0 + 4);
+                                    const float wa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, wc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+                                    for (int j = 0; j < 8; j++) {
+                                        sum1 = __fadd_rn(sum1, __fmul_rn(wa[j], hbv[j0 + j]));
+                                        sum2 = __fadd_rn(sum2, __fmul_rn(wc[j], hbv[j0 + j]));
+                                    }
+                                }
                             }
+                            sum1 = __fmul_rn(fac1, tanh_approx(sum1, rcp));
+                            sum2 = __fmul_rn(fac2, tanh_approx(sum2, rcp));
+                            sum1 = __fadd_rn(sum1, sum2);
+                            val = (val << 1) | (thr[b] < sum1 ? 1 : 0);
                         }
+                        const int exc = val;
+                        float pcm = __fadd_rn(pred, u2l[exc]);           // lpcnet.c:260
+#pragma unroll
+                        for (int j = LPC_ORDER - 1; j > 0; j--) ls[j] = ls[j - 1];
+                        ls[0] = pcm;
+                        last_exc = exc;
+                        pcm = __fadd_rn(pcm, __fmul_rn(0.85f, deemph));  // PREEMPH, lpcnet.c:265
+                        deemph = pcm;
+                        if (pcm < -32767) pcm = -32767;
+                        if (pcm > 32767) pcm = 32767;
+                        if (live) pcm_out[(size_t)f * spf + t_] = (short)__double2int_rd(0.5 + (double)pcm);   // (int)floor(.5 + pcm)
+                        if (last_t && !last) load_lpc(f + 1);
                     }
-                    sum1 = __fmul_rn(fac1, tanh_approx(sum1, rcp));
-                    sum2 = __fmul_rn(fac2, tanh_approx(sum2, rcp));
-                    sum1 = __fadd_rn(sum1, sum2);
-                    val = (val << 1) | (thr[b] < sum1 ? 1 : 0);
+                    if (!last) publish(hh);                              // indices of the half's next sample
                 }
-                const int exc = val;
-                float pcm = __fadd_rn(pred, u2l[exc]);                   // lpcnet.c:260
-#pragma unroll
-                for (int j = LPC_ORDER - 1; j > 0; j--) ls[j] = ls[j - 1];
-                ls[0] = pcm;
-                last_exc = exc;
-                pcm = __fadd_rn(pcm, __fmul_rn(0.85f, deemph));          // PREEMPH, lpcnet.c:265
-                deemph = pcm;
-                if (pcm < -32767) pcm = -32767;
-                if (pcm > 32767) pcm = 32767;
-                if (live) pcm_out[(size_t)f * spf + t] = (short)__double2int_rd(0.5 + (double)pcm);   // (int)floor(.5 + pcm)
             }
         }
         if (live) {
