@@ -56,16 +56,20 @@ constexpr int ACCB_ROW = 20;                 // int32 per output row of the GRU_
 // A "quad" is four 8x4 weight blocks of one 8-row group = one MMA: 16 streams x (4 blocks x 4 inputs) x 8 outputs.
 //   weights: 128 B per quad, word [gid][t] = the 4 int8 weights of output row gid for the block in slot t   (B fragment of lane gid*4+t)
 //   meta   : 4 x u16 per quad, one per slot: xs_offset(column block of the slot, stream 0)
-// Quantised state xs: column block c (inputs 4c..4c+3) is a 128-byte row; the word of stream s sits at
-//   c*128 + (((s & 7) * 16) ^ ((c & 3) * 32)) + (s >> 3) * 4
-// i.e. the four streams {gid, gid+8, gid+16, gid+24} that lane (gid, t) feeds to its two MMAs are one 16-byte vector,
-// and the XOR keeps the four slots of a quad (whose column blocks are ordered to have distinct c & 3 where possible)
-// in different bank groups.
+// Quantised state xs: column block c (inputs 4c..4c+3) is a 128-byte row = 2 halves x 8 streams x 2 words; the word of
+// stream s = 16*H + 8*jj + gid sits at
+//   c*128 + (((H << 6) | (gid << 3)) ^ (((c & 1) << 6) | ((c & 2) << 4))) + jj*4
+// i.e. the two streams {gid, gid+8} of a half that lane (gid, t) feeds to its MMA are one 8-byte vector, and the XOR
+// spreads the four slots of a quad (whose column blocks are ordered to have distinct c & 3 where possible) over the
+// four 32-byte bank groups that a half-warp (gid 0..3 or 4..7) does not already separate: conflict-free LDS.64.
 constexpr uint32_t QUAD_BYTES = 128, QUAD_META_BYTES = 8;
 #ifdef __CUDACC__
 __host__ __device__
 #endif
-constexpr uint32_t xs_offset(uint32_t c, uint32_t s) { return c * 128u + ((((s & 7u) * 16u) ^ ((c & 3u) * 32u))) + (s >> 3) * 4u; }
+constexpr uint32_t xs_offset(uint32_t c, uint32_t s)
+{
+    return c * 128u + (((((s >> 4) & 1u) << 6) | ((s & 7u) << 3)) ^ (((c & 1u) << 6) | ((c & 2u) << 4))) + ((s >> 3) & 1u) * 4u;
+}
 
 // ---- shared-memory map of the per-sample kernel ----
 // Everything whose size does not depend on the model's sparsity pattern sits at a COMPILE-TIME offset (keeps the
@@ -105,6 +109,7 @@ constexpr uint32_t IM_VAR   = al128(IM_PARB + 6 * NB * 4);         // start of t
 // ---- shared-memory map of the FLOAT-flavour per-sample kernel (sample_kernel_f32.cu) ----
 // fp32 GRU_A state tile instead of the u8 one, no gather tiles (per-lane gather), fp16 weights (64 B per block),
 // the whole dual_fc table read from global memory.
+constexpr int F_NWC = 16, F_GPW = NGRP / F_NWC, F_KPARTS = 2, F_NWB = 6 * F_KPARTS;   // geometry of the float kernel (independent of NWC)
 constexpr uint32_t F_XS    = 0;                                    // float [384][32]: GRU_A state of the 32 streams (single buffer)
 constexpr uint32_t F_HB    = F_XS + NA * 32 * 4;                   // float [2][16][32]: GRU_B state (double-buffered)
 constexpr uint32_t F_ACCB  = F_HB + 2 * NB * 32 * 4;                   // float [48][32]: GRU_B input-side pre-activations
@@ -116,11 +121,11 @@ constexpr uint32_t FI_LOGIT = FI_RCP + 2048 * 2;
 constexpr uint32_t FI_U2L   = FI_LOGIT + 256 * 4;
 constexpr uint32_t FI_FCB   = FI_U2L + 256 * 4;
 constexpr uint32_t FI_FCF   = FI_FCB + 512 * 4;
-constexpr uint32_t FI_PARA  = FI_FCF + 512 * 4;                    // float [NWC][GPW][3][16] = recurrent bias[8], diag[8]
-constexpr uint32_t FI_DIRA  = FI_PARA + NWC * GPW * 3 * 16 * 4;
-constexpr uint32_t FI_GRPA  = FI_DIRA + NWC * GPW * 3 * 2 * 4;
-constexpr uint32_t FI_DIRB  = FI_GRPA + NWC * GPW * 4;             // uint32 [6*KPARTS][2] (only part 0 of each row group is non-empty)
-constexpr uint32_t FI_PARB  = FI_DIRB + NWB * 2 * 4;               // float [96]: input-side bias[48], recurrent-side bias[48]
+constexpr uint32_t FI_PARA  = FI_FCF + 512 * 4;                    // float [F_NWC][F_GPW][3][16] = recurrent bias[8], diag[8]
+constexpr uint32_t FI_DIRA  = FI_PARA + F_NWC * F_GPW * 3 * 16 * 4;
+constexpr uint32_t FI_GRPA  = FI_DIRA + F_NWC * F_GPW * 3 * 2 * 4;
+constexpr uint32_t FI_DIRB  = FI_GRPA + F_NWC * F_GPW * 4;         // uint32 [6*F_KPARTS][2] (only part 0 of each row group is non-empty)
+constexpr uint32_t FI_PARB  = FI_DIRB + F_NWB * 2 * 4;               // float [96]: input-side bias[48], recurrent-side bias[48]
 constexpr uint32_t FI_VAR   = al128(FI_PARB + 6 * NB * 4);
 
 // offsets used by the (flavour-agnostic) image builder

@@ -164,32 +164,35 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
         p = idxB; w = wB->data;
         for (int rg = 0; rg < 3 * NB / 8; rg++) { int nb = *p++; for (int j = 0; j < nb; j++) { rowsB[rg].push_back({*p++, w}); w += src_blk; } }
     }
+    // geometry of the kernel that will consume the image
+    const bool is_float = m->is_float != 0;
+    const int nwc = is_float ? F_NWC : NWC, gpw = NGRP / nwc, kparts = is_float ? F_KPARTS : KPARTS, nwb = 6 * kparts;
     std::vector<int> cost(NGRP), order(NGRP);
     for (int g = 0; g < NGRP; g++) cost[g] = (int)(rowsA[g].size() + rowsA[NGRP + g].size() + rowsA[2 * NGRP + g].size());
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
-    int grp[NWC][GPW]; int load[NWC] = {0}, fill[NWC] = {0};
+    std::vector<std::vector<int>> grp(nwc);
+    std::vector<int> load(nwc, 0);
     for (int g : order) {
         int best = -1;
-        for (int w = 0; w < NWC; w++) if (fill[w] < GPW && (best < 0 || load[w] < load[best])) best = w;
-        grp[best][fill[best]++] = g; load[best] += cost[g];
+        for (int w = 0; w < nwc; w++) if ((int)grp[w].size() < gpw && (best < 0 || load[w] < load[best])) best = w;
+        grp[best].push_back(g); load[best] += cost[g];
     }
 
     // ---------------- SMEM layout ----------------
     // unit of the weight arrays: int8 flavour = quad (4 blocks, one MMA), float flavour = block (lists padded to even length)
     SmemLayout &L = m->L;
-    const bool is_float = m->is_float != 0;
     auto padded = [is_float](size_t n) { return is_float ? (uint32_t)((n + 1) & ~size_t(1)) : (uint32_t)((n + 3) / 4); };
     uint32_t nA_pad = 0, nB_pad = 0;
-    for (int w = 0; w < NWC; w++) for (int s = 0; s < GPW; s++) for (int q = 0; q < 3; q++) nA_pad += padded(rowsA[q * NGRP + grp[w][s]].size());
+    for (int w = 0; w < nwc; w++) for (int s = 0; s < gpw; s++) for (int q = 0; q < 3; q++) nA_pad += padded(rowsA[q * NGRP + grp[w][s]].size());
     // GRU_B input GEMV: warp (rg, part) takes a contiguous KPARTS-th of the row group's block list
-    uint32_t dirB_h[NWB][2];
-    auto part_lo = [is_float](size_t n, int k) { return is_float ? (k == 0 ? (size_t)0 : n) : (n * k + KPARTS - 1) / KPARTS; };
+    std::vector<std::array<uint32_t, 2>> dirB_h(nwb);
+    auto part_lo = [is_float, kparts](size_t n, int k) { return is_float ? (k == 0 ? (size_t)0 : n) : (n * k + kparts - 1) / kparts; };
     for (int rg = 0; rg < 6; rg++) {
         size_t n = rowsB[rg].size();
-        for (int k = 0; k < KPARTS; k++) {
-            dirB_h[rg * KPARTS + k][1] = padded(part_lo(n, k + 1) - part_lo(n, k));
-            nB_pad += dirB_h[rg * KPARTS + k][1];
+        for (int k = 0; k < kparts; k++) {
+            dirB_h[rg * kparts + k][1] = padded(part_lo(n, k + 1) - part_lo(n, k));
+            nB_pad += dirB_h[rg * kparts + k][1];
         }
     }
     const ImageMap M = is_float ? MAP_F32 : MAP_INT8;
@@ -258,14 +261,14 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
     uint32_t *dirA = reinterpret_cast<uint32_t *>(&img[M.dirA]);
     uint32_t *grpA = reinterpret_cast<uint32_t *>(&img[M.grpA]);
     uint32_t blk = 0;
-    for (int w = 0; w < NWC; w++) for (int s = 0; s < GPW; s++) {
+    for (int w = 0; w < nwc; w++) for (int s = 0; s < gpw; s++) {
         int g = grp[w][s];
-        grpA[w * GPW + s] = (uint32_t)g;
+        grpA[w * gpw + s] = (uint32_t)g;
         for (int q = 0; q < 3; q++) {
             const auto &lst = rowsA[q * NGRP + g];
             uint32_t np = padded(lst.size());
-            dirA[((w * GPW + s) * 3 + q) * 2 + 0] = blk;
-            dirA[((w * GPW + s) * 3 + q) * 2 + 1] = np;
+            dirA[((w * gpw + s) * 3 + q) * 2 + 0] = blk;
+            dirA[((w * gpw + s) * 3 + q) * 2 + 1] = np;
             if (is_float) {
                 for (size_t j = 0; j < lst.size(); j++) {
                     put_block(&img[oWA + (size_t)(blk + j) * img_blk], lst[j].w);
@@ -273,7 +276,7 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
                 }
             } else put_quads(lst.data(), lst.size(), blk, oWA, oMA);
             blk += np;    // padding stays all-zero (weights 0, x row 0): contributes exactly 0
-            float *pp = &parA[((w * GPW + s) * 3 + q) * 16];
+            float *pp = &parA[((w * gpw + s) * 3 + q) * 16];
             for (int i = 0; i < 8; i++) {
                 pp[i] = (is_float ? ga_bias : ga_subias)[3 * NA + q * NA + 8 * g + i];   // recurrent (su-)bias (nnet.c:425-430)
                 pp[8 + i] = ga_diag[q * NA + 8 * g + i];
@@ -285,17 +288,17 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
     blk = 0;
     for (int rg = 0; rg < 6; rg++) {
         const auto &lst = rowsB[rg];
-        for (int k = 0; k < KPARTS; k++) {
+        for (int k = 0; k < kparts; k++) {
             size_t b0 = part_lo(lst.size(), k), b1 = part_lo(lst.size(), k + 1);
-            dirB[(rg * KPARTS + k) * 2 + 0] = blk;
-            dirB[(rg * KPARTS + k) * 2 + 1] = dirB_h[rg * KPARTS + k][1];
+            dirB[(rg * kparts + k) * 2 + 0] = blk;
+            dirB[(rg * kparts + k) * 2 + 1] = dirB_h[rg * kparts + k][1];
             if (is_float) {
                 for (size_t j = b0; j < b1; j++) {
                     put_block(&img[oWB + (size_t)(blk + (j - b0)) * img_blk], lst[j].w);
                     metaB[blk + (j - b0)] = (uint16_t)(lst[j].pos * 128);
                 }
             } else put_quads(lst.data() + b0, b1 - b0, blk, oWB, oMB);
-            blk += dirB_h[rg * KPARTS + k][1];
+            blk += dirB_h[rg * kparts + k][1];
         }
     }
     if (is_float) memcpy(&img[L.wBrecF - M.sm_image], wBrec->data, 3 * NB * NB * 4);    // float [in 16][out 48] (sgemv_accum16 layout)

@@ -39,10 +39,6 @@
 #include "engine.h"
 #include "devmath.cuh"
 
-#ifndef LPCNET_GB
-#define LPCNET_GB 3      // units (4 LDG.128 each) a producer lane keeps in flight
-#endif
-
 namespace lpcnet_b200 {
 
 namespace {
@@ -50,9 +46,11 @@ namespace {
 // named barriers of the compute warps
 enum {
     BAR_X = 1,       // new quantised GRU_A state of the half complete (and its candidate-gate tile consumed)
-    BAR_ACCB = 2     // GRU_B partial sums complete
+    BAR_ACCB = 2,    // GRU_B partial sums complete
+    BAR_HB = 3       // (+ half) finishing warps arrive, sampler waits: GRU_B state of the half's sample is in hBs
 };
-constexpr int CNT_C = NWC * 32;
+constexpr int CNT_C = NWC * 32, CNT_HB = NFIN * 32 + 32;
+__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -128,16 +126,18 @@ __device__ __forceinline__ int2 lds64(uint32_t addr)
 // acc[2jj+i] += sum over `nq` quads, for stream gid+8jj (of one half) and neuron 2t+i of the row group.
 //   w    : shared address of the first quad's weights + lane*4      (B fragment word of this lane)
 //   meta : shared address of the first quad's meta + t*2            (xs_offset of slot t's column block)
-//   xs   : shared address of the state buffer + 8*half; the lane's 8-byte vector of slot t is at xs + (meta entry ^ gid*16)
+//   xs   : shared address of the state buffer; the lane's 8-byte vector of slot t is at xs + (meta entry ^ lc), lc = (half << 6) | (gid << 3)
 // Software-pipelined: the meta entry of quad q+2 and the operands of quad q+1 are in flight while quad q is multiplied
-// (the image keeps two quads of readable slack behind every list).
-__device__ __forceinline__ void mma_quads(int (&acc)[4], uint32_t w, uint32_t meta, int nq, uint32_t xs, uint32_t gid16)
+// (the image keeps two quads of readable slack behind every list).  w and meta are left pointing behind the list: the
+// lists of a neuron group are contiguous (z, r, h), so the caller walks r and h with one address set-up.
+__device__ __forceinline__ void mma_quads(int (&acc)[4], uint32_t &w, uint32_t &meta, int nq, uint32_t xs, uint32_t lc)
 {
     uint32_t e1 = lds16(meta + QUAD_META_BYTES);
-    int2 x = lds64(xs + (lds16(meta) ^ gid16));
+    int2 x = lds64(xs + (lds16(meta) ^ lc));
     uint32_t wv = lds32(w);
+#pragma unroll 1
     for (int q = 0; q < nq; q++) {
-        const int2 xn = lds64(xs + (e1 ^ gid16));
+        const int2 xn = lds64(xs + (e1 ^ lc));
         const uint32_t wn = lds32(w + QUAD_BYTES);
         e1 = lds16(meta + 2 * QUAD_META_BYTES);
         imma16816(acc[0], acc[1], acc[2], acc[3], (uint32_t)x.x, (uint32_t)x.y, wv);
@@ -157,6 +157,7 @@ __device__ __forceinline__ void gather_half(float *__restrict__ G, const float *
                                             int gate, int p, int lane)
 {
     const int col = gate * NA + lane * 4;
+#pragma unroll 1
     for (int si = p; si < HALF; si += NWP) {
         const int sg = min(s_half0 + si, n - 1);
         const float *c = cond_f + (size_t)sg * (3 * NA) + col;
@@ -181,7 +182,7 @@ __device__ __forceinline__ void gather_half(float *__restrict__ G, const float *
 
 // ---- per-lane constants of a compute warp ----
 struct ComputeCtx {
-    uint32_t gid16;             // (lane >> 2) * 16
+    uint32_t gid8;              // (lane >> 2) * 8
     int gid, t;
     int warp, lane;
     uint32_t wA, metaA, wB, metaB;      // shared addresses (lane / slot offsets folded in)
@@ -193,7 +194,7 @@ struct ComputeCtx {
     const uint32_t *rcp;
     uint8_t *smem;
     int gcol[GPW];                      // neuron index of this lane's first neuron of each group: 8*g + 2t
-    uint32_t xoff[GPW];                 // byte offset (in a state buffer) of this lane's two quantised neurons, stream gid of half 0
+    uint32_t xoff[GPW];                 // byte offset (in a state buffer) of this lane's two quantised neurons, stream gid of half 0 (half 1: ^ 64, stream gid+8: + 4)
 };
 
 // One GRU_A + GRU_B step of half H (16 streams).  k0 = index of the half-step's first tile fill (gate r; z and h follow).
@@ -205,8 +206,8 @@ __device__ __forceinline__ void compute_half_step(const ComputeCtx &C, const Sam
     const int gid = C.gid, t = C.t, lane = C.lane, warp = C.warp;
     const uint32_t *rcp = C.rcp;
     const int nxt = cur ^ 1;
-    const uint32_t xs_cur = C.xs0 + cur * XS_BYTES + 8 * H;
-    uint8_t *xs_nxt = smem + SM_XS + nxt * XS_BYTES + 8 * H;
+    const uint32_t xs_cur = C.xs0 + cur * XS_BYTES, lc = C.gid8 | (H << 6);
+    uint8_t *xs_nxt = smem + SM_XS + nxt * XS_BYTES;
     const uint32_t kr = k0, kz = k0 + 1, kh = k0 + 2;
     const float *tile_r = reinterpret_cast<const float *>(smem + SM_TILES + (kr & 3) * TILE_BYTES) + gid * GIN_ROW;
     const float *tile_z = reinterpret_cast<const float *>(smem + SM_TILES + (kz & 3) * TILE_BYTES) + gid * GIN_ROW;
@@ -222,8 +223,9 @@ __device__ __forceinline__ void compute_half_step(const ComputeCtx &C, const Sam
         const uint32_t *dir = C.dirA + sl * 3 * 2;
 #pragma unroll
         for (int i = 0; i < 4; i++) { Sh[sl][i] = 0; Sg[sl][i] = 0; }
-        mma_quads(Sh[sl], C.wA + dir[4] * QUAD_BYTES, C.metaA + dir[4] * QUAD_META_BYTES, (int)dir[5], xs_cur, C.gid16);
-        mma_quads(Sg[sl], C.wA + dir[2] * QUAD_BYTES, C.metaA + dir[2] * QUAD_META_BYTES, (int)dir[3], xs_cur, C.gid16);
+        uint32_t w = C.wA + dir[2] * QUAD_BYTES, meta = C.metaA + dir[2] * QUAD_META_BYTES;
+        mma_quads(Sg[sl], w, meta, (int)dir[3], xs_cur, lc);      // r list, directly followed by the h list
+        mma_quads(Sh[sl], w, meta, (int)dir[5], xs_cur, lc);
     }
     // ---- reset gate r (nnet.c:431-435) with the gathered input term; keep rec_h * r (nnet.c:436-440) ----
     mbar_wait(mb_full + 8 * (kr & 3), (kr >> 2) & 1);
@@ -254,7 +256,8 @@ __device__ __forceinline__ void compute_half_step(const ComputeCtx &C, const Sam
         const uint32_t *dir = C.dirA + sl * 3 * 2;
 #pragma unroll
         for (int i = 0; i < 4; i++) Sg[sl][i] = 0;
-        mma_quads(Sg[sl], C.wA + dir[0] * QUAD_BYTES, C.metaA + dir[0] * QUAD_META_BYTES, (int)dir[1], xs_cur, C.gid16);
+        uint32_t w = C.wA + dir[0] * QUAD_BYTES, meta = C.metaA + dir[0] * QUAD_META_BYTES;
+        mma_quads(Sg[sl], w, meta, (int)dir[1], xs_cur, lc);
     }
     mbar_wait(mb_full + 8 * (kz & 3), (kz >> 2) & 1);
 #pragma unroll
@@ -292,7 +295,7 @@ __device__ __forceinline__ void compute_half_step(const ComputeCtx &C, const Sam
                 q[i] = quant_u8(hn);
             }
             // other buffer: readers of the old state are unaffected
-            *reinterpret_cast<uint16_t *>(xs_nxt + C.xoff[sl] + 4 * jj) = (uint16_t)(q[0] | (q[1] << 8));
+            *reinterpret_cast<uint16_t *>(xs_nxt + (C.xoff[sl] ^ (H << 6)) + 4 * jj) = (uint16_t)(q[0] | (q[1] << 8));
         }
     bar_sync(BAR_X, CNT_C);                                      // new quantised GRU_A state complete; candidate-gate tile dead: GRU_B scratch may use it
 
@@ -302,7 +305,8 @@ __device__ __forceinline__ void compute_half_step(const ComputeCtx &C, const Sam
     if (warp < NWB) {
         int acc[4] = {0, 0, 0, 0};
         const uint32_t q0 = C.dirB[warp * 2], nq = C.dirB[warp * 2 + 1];
-        mma_quads(acc, C.wB + q0 * QUAD_BYTES, C.metaB + q0 * QUAD_META_BYTES, (int)nq, C.xs0 + nxt * XS_BYTES + 8 * H, C.gid16);
+        uint32_t w = C.wB + q0 * QUAD_BYTES, meta = C.metaB + q0 * QUAD_META_BYTES;
+        mma_quads(acc, w, meta, (int)nq, C.xs0 + nxt * XS_BYTES, lc);
         const int rgp = warp / KPARTS, part = warp % KPARTS;
         int *dst = accB + (part * 3 * NB + rgp * 8 + 2 * t) * ACCB_ROW + gid;
         dst[0] = acc[0]; dst[ACCB_ROW] = acc[1]; dst[8] = acc[2]; dst[ACCB_ROW + 8] = acc[3];
@@ -337,7 +341,8 @@ __device__ __forceinline__ void compute_half_step(const ComputeCtx &C, const Sam
         hb = __fadd_rn(__fmul_rn(zz, hb), __fmul_rn(__fsub_rn(1.f, zz), hh));
         hBs[jb * HALF + si] = hb;
         reinterpret_cast<uint8_t *>(xb + nxt * 4 * HALF)[((jb >> 2) * HALF + si) * 4 + (jb & 3)] = (uint8_t)quant_u8(hb);
-        warp_arrive(smem_u32(smem + MB_HB) + 8 * H, lane);       // GRU_B state of this sample is in hBs
+        __threadfence_block();
+        bar_arrive(BAR_HB + H, CNT_HB);                          // GRU_B state of this sample is in hBs
     } else {
         bar_sync(BAR_ACCB, CNT_C);
     }
@@ -360,7 +365,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         for (int b = 0; b < NTILE; b++) { mbar_init(smem_u32(smem + MB_FULL) + 8 * b, NWP); mbar_init(smem_u32(smem + MB_EMPTY) + 8 * b, NWC); }
-        for (int hh = 0; hh < 2; hh++) { mbar_init(smem_u32(smem + MB_IDX) + 8 * hh, 1); mbar_init(smem_u32(smem + MB_HB) + 8 * hh, NFIN); }
+        for (int hh = 0; hh < 2; hh++) { mbar_init(smem_u32(smem + MB_IDX) + 8 * hh, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -379,7 +384,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
         // =====================================================  compute warps  =====================================================
         mbar_wait(bar, 0);
         ComputeCtx C;
-        C.gid = lane >> 2; C.t = lane & 3; C.gid16 = C.gid * 16; C.warp = warp; C.lane = lane; C.smem = smem; C.rcp = rcp;
+        C.gid = lane >> 2; C.t = lane & 3; C.gid8 = C.gid * 8; C.warp = warp; C.lane = lane; C.smem = smem; C.rcp = rcp;
         const uint32_t *grpA = reinterpret_cast<const uint32_t *>(smem + SM_IMAGE + IM_GRPA);
         C.dirA = reinterpret_cast<const uint32_t *>(smem + SM_IMAGE + IM_DIRA) + warp * GPW * 3 * 2;
         C.parA = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_PARA) + warp * GPW * 3 * 16 + 2 * C.t;
@@ -422,7 +427,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
         for (int sl = 0; sl < GPW; sl++)
 #pragma unroll
             for (int j = 0; j < 4; j++)
-                *reinterpret_cast<uint16_t *>(smem + SM_XS + C.xoff[sl] + 4 * j) =
+                *reinterpret_cast<uint16_t *>(smem + SM_XS + (C.xoff[sl] ^ ((j >> 1) << 6)) + 4 * (j & 1)) =
                     (uint16_t)(quant_u8(h[j >> 1][sl][2 * (j & 1)]) | (quant_u8(h[j >> 1][sl][2 * (j & 1) + 1]) << 8));
         if (warp < NFIN) {
 #pragma unroll
@@ -481,7 +486,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
         const float *logit = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_LOGIT);
         const float *u2l = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_U2L);
         const float *fcw = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_FCW);
-        const uint32_t mb_idx = smem_u32(smem + MB_IDX), mb_hb = smem_u32(smem + MB_HB);
+        const uint32_t mb_idx = smem_u32(smem + MB_IDX);
         int *idx_h = idx_s + myh * 3 * HALF;
 
         float ls[LPC_ORDER], lpc[LPC_ORDER];
@@ -521,7 +526,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
                 const bool last_t = t_ == spf - 1, last = last_t && f == P.nframes - 1;
 #pragma unroll 1
                 for (int hh = 0; hh < 2; hh++) {
-                    mbar_wait(mb_hb + 8 * hh, it & 1);                   // GRU_B state of the half is in hBs (inside the half's candidate-gate tile)
+                    bar_sync(BAR_HB + hh, CNT_HB);                       // GRU_B state of the half is in hBs (inside the half's candidate-gate tile)
                     if (myh == hh) {
                         const float *hBs = reinterpret_cast<const float *>(smem + SM_TILES + ((k + 3 * hh + 2) & 3) * TILE_BYTES + T_HBS);
                         // thresholds (nnet.c:178-184): two RNG words -> 8 logits

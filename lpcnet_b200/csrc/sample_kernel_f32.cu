@@ -19,10 +19,9 @@
 
 namespace lpcnet_b200 {
 
-#if LPCNET_NWC == 16
 namespace {
 
-constexpr int F_NWC = 16, F_GPW = NGRP / F_NWC, F_THREADS = (F_NWC + 1) * 32;
+constexpr int F_THREADS = (F_NWC + 1) * 32;
 
 enum { FB_IDX = 1, FB_READ = 2, FB_X = 3, FB_ACCB = 4, FB_HB = 5 };
 
@@ -183,7 +182,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) lpcnet_sample_kernel_f32(const _
                     const float cb[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
 #pragma unroll
                     for (int i = 0; i < 8; i++) y[i] = __fadd_rn(parB[warp * 8 + i], cb[i]);
-                    const uint32_t b0 = dirB[(warp * KPARTS) * 2], nb = dirB[(warp * KPARTS) * 2 + 1];
+                    const uint32_t b0 = dirB[(warp * F_KPARTS) * 2], nb = dirB[(warp * F_KPARTS) * 2 + 1];
                     gemv_f32(y, wB + (size_t)b0 * 64, metaB + b0, (int)nb, xs_lane);
 #pragma unroll
                     for (int i = 0; i < 8; i++) accB[(warp * 8 + i) * 32 + lane] = y[i];
@@ -300,11 +299,6 @@ __global__ void __launch_bounds__(F_THREADS, 1) lpcnet_sample_kernel_f32(const _
     }
 }
 
-#else   // LPCNET_F32_DISABLED: tuning builds with another compute-warp count do not carry the float flavour
-cudaError_t launch_sample_kernel_f32(const SampleParams &, cudaStream_t) { return cudaErrorNotSupported; }
-#endif
-
-#if LPCNET_NWC == 16
 cudaError_t launch_sample_kernel_f32(const SampleParams &p, cudaStream_t st)
 {
     cudaError_t e = cudaFuncSetAttribute(lpcnet_sample_kernel_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -313,7 +307,5 @@ cudaError_t launch_sample_kernel_f32(const SampleParams &p, cudaStream_t st)
     lpcnet_sample_kernel_f32<<<ctas, F_THREADS, p.L.total_bytes, st>>>(p);
     return cudaGetLastError();
 }
-
-#endif
 
 }  // namespace lpcnet_b200

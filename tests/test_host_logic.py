@@ -93,7 +93,7 @@ def test_smem_image_replays_to_the_dense_model(L):
     want_A, want_B = MA @ x, MB @ x
 
     def xs_offset(c, s):
-        return c * 128 + (((s & 7) * 16) ^ ((c & 3) * 32)) + (s >> 3) * 4
+        return c * 128 + (((((s >> 4) & 1) << 6) | ((s & 7) << 3)) ^ (((c & 1) << 6) | ((c & 2) << 4))) + ((s >> 3) & 1) * 4
 
     def replay_quads(wq, mq, q0, nq):
         """sum over quads q0..q0+nq of W[8 out][slot][4 in] . x[column block of the slot]; also counts bank-group clashes"""

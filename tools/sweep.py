@@ -4,16 +4,12 @@ import os, subprocess, sys
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, ROOT)
 VARIANTS = {
-    "c16p7b3": ["LPCNET_NWC=16", "LPCNET_NWP=7", "LPCNET_GB=3"],
-    "c16p7b4": ["LPCNET_NWC=16", "LPCNET_NWP=7", "LPCNET_GB=4"],
-    "c16p7b2": ["LPCNET_NWC=16", "LPCNET_NWP=7", "LPCNET_GB=2"],
-    "c16p3b5": ["LPCNET_NWC=16", "LPCNET_NWP=3", "LPCNET_GB=5"],
-    "c12p3b6": ["LPCNET_NWC=12", "LPCNET_NWP=3", "LPCNET_GB=6"],
-    "c12p7b4": ["LPCNET_NWC=12", "LPCNET_NWP=7", "LPCNET_GB=4"],
-    "c24p7b2": ["LPCNET_NWC=24", "LPCNET_NWP=7", "LPCNET_GB=2"],
-    "c24p3b3": ["LPCNET_NWC=24", "LPCNET_NWP=3", "LPCNET_GB=3"],
+    "c16p7u3": ["LPCNET_NWC=16", "LPCNET_NWP=7", "LPCNET_GU=3"],
+    "c16p4u4": ["LPCNET_NWC=16", "LPCNET_NWP=4", "LPCNET_GU=4"],
+    "c16p4u3": ["LPCNET_NWC=16", "LPCNET_NWP=4", "LPCNET_GU=3"],
+    "c16p3u5": ["LPCNET_NWC=16", "LPCNET_NWP=3", "LPCNET_GU=5"],
+    "c16p5u3": ["LPCNET_NWC=16", "LPCNET_NWP=5", "LPCNET_GU=3"],
 }
-VARIANTS = {"c16p7": ["LPCNET_NWC=16","LPCNET_NWP=7"], "c24p7": ["LPCNET_NWC=24","LPCNET_NWP=7"], "c24p5": ["LPCNET_NWC=24","LPCNET_NWP=5"], "c12p7": ["LPCNET_NWC=12","LPCNET_NWP=7"], "c12p3": ["LPCNET_NWC=12","LPCNET_NWP=3"]}
 if sys.argv[1] == "build":
     from lpcnet_b200 import build
     for k, v in VARIANTS.items():
