@@ -191,6 +191,7 @@ static int synth_device(LPCNetB200Batch *b, const float *d_feat, long long strea
             SampleParams p;
             p.L = b->model.L; p.image = b->model.image;
             p.emb_sig = b->model.emb_sig; p.emb_pred = b->model.emb_pred; p.emb_exc = b->model.emb_exc; p.fcw = b->model.fcw;
+            p.fast_cvt = b->model.fast_cvt && !getenv("LPCNET_B200_EXACT_CVT");   // env: force the conversion-unit path (tests)
             p.condA = b->condA + (size_t)silent * n * 3 * NA;
             p.condB = b->condB + (size_t)silent * n * 3 * NB;
             p.lpc_raw = b->lpc_raw + (size_t)silent * n * LPC_ORDER;

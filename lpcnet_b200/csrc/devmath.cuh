@@ -27,9 +27,19 @@ __device__ __forceinline__ float rcp_emul(float x, const uint32_t *__restrict__ 
     return __uint_as_float(t - (u & 0x7F800000u));
 }
 
+// same table at an 8 KB-aligned SHARED address: the entry address is formed with one shift and one (a & b) | c
+struct RcpShared { uint32_t addr; };
+__device__ __forceinline__ float rcp_emul(float x, RcpShared tab)
+{
+    const uint32_t u = __float_as_uint(x);
+    uint32_t t;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(t) : "r"(tab.addr | ((u >> 10) & 0x1FFCu)));
+    return __uint_as_float(t - (u & 0x7F800000u));
+}
+
 // tanh8_approx (vec_avx.h:393-411)
 template <typename TAB>
-__device__ __forceinline__ float tanh_approx(float x, const TAB *__restrict__ tab16)
+__device__ __forceinline__ float tanh_approx(float x, TAB tab16)
 {
     const float N0 = 952.52801514f, N1 = 96.39235687f, N2 = 0.60863042f;
     const float D0 = 952.72399902f, D1 = 413.36801147f, D2 = 11.88600922f;
@@ -44,7 +54,7 @@ __device__ __forceinline__ float tanh_approx(float x, const TAB *__restrict__ ta
 
 // sigmoid8_approx (vec_avx.h:421-440)
 template <typename TAB>
-__device__ __forceinline__ float sigmoid_approx(float x, const TAB *__restrict__ tab16)
+__device__ __forceinline__ float sigmoid_approx(float x, TAB tab16)
 {
     const float N0 = 238.13200378f, N1 = 6.02452230f, N2 = 0.00950985f;
     const float D0 = 952.72399902f, D1 = 103.34200287f, D2 = 0.74287558f;
@@ -67,6 +77,29 @@ __device__ __forceinline__ uint32_t quant_u8(float x)
 // accumulator entry/exit of the int8 GEMVs (vec_avx.h:803-806,854-856)
 __device__ __forceinline__ int acc_init(float rec) { return __float2int_rn(__fmul_rn(rec, LPCNET_SCALE)); }
 __device__ __forceinline__ float acc_finish(int acc) { return __fmul_rn(__int2float_rn(acc), LPCNET_SCALE_1); }
+
+// The same two conversions without the conversion unit, for models whose pre-activations are PROVEN (model.cu,
+// cvt_range_ok) to stay below 2^22 in accumulator units: adding 1.5*2^23 to |v| < 2^22 rounds v to the nearest-even
+// integer exactly like cvtps2dq and leaves 0x4B400000 + rne(v) in the float's bit pattern; the accumulator keeps that
+// bias while the integer GEMV sum is added, and subtracting 1.5*2^23 from the biased pattern is exactly (float)acc.
+#define LPCNET_CVT_MAGIC 12582912.f              // 1.5 * 2^23 = 0x4B400000
+template <bool FAST> __device__ __forceinline__ int acc_init_t(float rec)
+{
+    if (FAST) return __float_as_int(__fadd_rn(__fmul_rn(rec, LPCNET_SCALE), LPCNET_CVT_MAGIC));
+    return acc_init(rec);
+}
+template <bool FAST> __device__ __forceinline__ float acc_finish_t(int acc)
+{
+    if (FAST) return __fmul_rn(__fsub_rn(__int_as_float(acc), LPCNET_CVT_MAGIC), LPCNET_SCALE_1);
+    return acc_finish(acc);
+}
+// quantised byte of a state value |h| <= 1 (fma(h,127,127) in [0,254]: the saturation of vector_ps_to_epi8 cannot trigger);
+// FAST leaves it in the low byte of the biased pattern
+template <bool FAST> __device__ __forceinline__ uint32_t quant_u8_t(float x)
+{
+    if (FAST) return __float_as_uint(__fadd_rn(__fmaf_rn(x, 127.f, 127.f), LPCNET_CVT_MAGIC));
+    return quant_u8(x);
+}
 
 // u8 activations x s8 weights, 4 MACs (one block row of sparse_sgemv_accum8x4; maddubs+madd == exact integer sum
 // under the WeightClip pair constraint, training_tf2/lpcnet.py:216-232)

@@ -89,20 +89,25 @@ constexpr uint32_t T_ACCB   = 0;                                   //   int32 [K
 constexpr uint32_t T_HBS    = T_ACCB + KPARTS * 3 * NB * ACCB_ROW * 4;   //   float [16 neurons][16 streams] GRU_B state for the sampler
 static_assert(T_HBS + NB * HALF * 4 <= TILE_BYTES, "GRU_B scratch must fit inside the gather tile it aliases");
 constexpr uint32_t SM_IDX   = SM_TILES + NTILE * TILE_BYTES;       // int32 [2 halves][3][16]: last_sig_ulaw, pred_ulaw, last_exc
-constexpr uint32_t SM_MBAR  = al128(SM_IDX + 2 * 3 * HALF * 4);    // mbarriers: image | full[NTILE] | empty[NTILE] | idx[2] | hb[2]
-constexpr uint32_t MB_IMAGE = SM_MBAR, MB_FULL = SM_MBAR + 8, MB_EMPTY = MB_FULL + 8 * NTILE, MB_IDX = MB_EMPTY + 8 * NTILE, MB_HB = MB_IDX + 16;
+constexpr uint32_t SM_MBAR  = al128(SM_IDX + 2 * 3 * HALF * 4);    // mbarriers: image | full[NTILE] | empty[NTILE] | idx[2] | x[2] | accb[2]
+constexpr uint32_t MB_IMAGE = SM_MBAR, MB_FULL = SM_MBAR + 8, MB_EMPTY = MB_FULL + 8 * NTILE, MB_IDX = MB_EMPTY + 8 * NTILE, MB_X = MB_IDX + 16, MB_ACCB = MB_X + 16;
 constexpr uint32_t SM_IMAGE = SM_MBAR + 128;
-static_assert(MB_HB + 16 <= SM_IMAGE, "mbarrier block");
+static_assert(MB_ACCB + 16 <= SM_IMAGE, "mbarrier block");
 // image, fixed part (offsets relative to SM_IMAGE)
-constexpr uint32_t IM_RCP   = 0;                                   // u32 [2048] RCPPS table, pre-biased: T[k] + 0x3f800000 (one IADD rebuilds the result)
-constexpr uint32_t IM_LOGIT = IM_RCP + 2048 * 4;                   // float [256] sampling_logit_table
+constexpr uint32_t SMEM_RESERVED = 1024;                           // shared-window address of dynamic shared memory on sm_100 (checked at kernel start)
+constexpr uint32_t IM_LOGIT = 0;                                   // float [256] sampling_logit_table
 constexpr uint32_t IM_U2L   = IM_LOGIT + 256 * 4;                  // float [256] ulaw2lin
-constexpr uint32_t IM_FCW   = IM_U2L + 256 * 4;                    // float [FCW_SMEM_NODES][FCW_ROW] dual_fc rows of the upper tree levels
-constexpr uint32_t IM_PARA  = IM_FCW + FCW_SMEM_NODES * FCW_ROW * 4;   // float [NWC][GPW][3 gates][16] = recurrent su-bias[8], diag[8]
-constexpr uint32_t IM_DIRA  = IM_PARA + NWC * GPW * 3 * 16 * 4;    // uint32 [NWC][GPW][3][2] = {first quad, quad count}
+constexpr uint32_t IM_DIRA  = IM_U2L + 256 * 4;                    // uint32 [NWC][GPW][3][2] = {first quad, quad count}
 constexpr uint32_t IM_GRPA  = IM_DIRA + NWC * GPW * 3 * 2 * 4;     // uint32 [NWC][GPW] neuron-group id
 constexpr uint32_t IM_DIRB  = IM_GRPA + NWC * GPW * 4;             // uint32 [NWB][2]
-constexpr uint32_t IM_WBREC = IM_DIRB + NWB * 2 * 4;               // int8 [6][4][8][4] GRU_B recurrent blocks
+constexpr uint32_t IM_PRE_END = IM_DIRB + NWB * 2 * 4;
+// u32 [2048] RCPPS table, pre-biased: T[k] + 0x3f800000 (one IADD rebuilds the result); its absolute shared address is
+// 8 KB-aligned so that the entry address is table | index (no add)
+constexpr uint32_t IM_RCP   = IM_PRE_END + (8192u - (SMEM_RESERVED + SM_IMAGE + IM_PRE_END) % 8192u) % 8192u;
+static_assert((SMEM_RESERVED + SM_IMAGE + IM_RCP) % 8192u == 0, "rcp table alignment");
+constexpr uint32_t IM_FCW   = IM_RCP + 2048 * 4;                   // float [FCW_SMEM_NODES][FCW_ROW] dual_fc rows of the upper tree levels
+constexpr uint32_t IM_PARA  = IM_FCW + FCW_SMEM_NODES * FCW_ROW * 4;   // float [NWC][GPW][3 gates][16] = recurrent su-bias[8], diag[8]
+constexpr uint32_t IM_WBREC = IM_PARA + NWC * GPW * 3 * 16 * 4;    // int8 [6][4][8][4] GRU_B recurrent blocks
 constexpr uint32_t IM_PARB  = IM_WBREC + 3 * NB * NB;              // float [96]: input-side su-bias[48], recurrent-side su-bias[48]
 constexpr uint32_t IM_VAR   = al128(IM_PARB + 6 * NB * 4);         // start of the variable-size arrays
 
@@ -148,6 +153,7 @@ struct SmemLayout {          // run-time part; offsets are absolute (from the st
 // Device-resident model (one per batch; weights replicated per GPU, ~4 MB).
 struct DeviceModel {
     int is_float;                    // 0: int8 DOT_PROD semantics (oracle A); 1: float semantics (oracle B)
+    int fast_cvt;                    // int8: GRU_A pre-activations provably < 2^22 accumulator units (conversion-free rounding allowed)
     float lpc_gamma;
     SmemLayout L;
     uint8_t *image;                  // [L.image_bytes] global copy of the SMEM image
@@ -190,6 +196,7 @@ struct SampleParams {
     short *pcm;              // stream s, frame f, sample t at pcm[s*pcm_stream_stride + f*spf + t]
     long long pcm_stream_stride;
     int n_streams, nframes, spf;
+    int fast_cvt;
 };
 
 // ---- host-side API of the internal modules ----

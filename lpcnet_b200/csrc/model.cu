@@ -334,6 +334,28 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
         else { memcpy(&img[M.fcb], fc_b, 512 * 4); memcpy(&img[M.fcf], fc_f, 512 * 4); }
     }
 
+    // Range proof for the conversion-free rounding of the GRU_A accumulators (devmath.cuh, acc_init_t): with |h| <= 1 and
+    // the conditioning vector in [-1, 1] (tanh outputs of feature_dense2), every float that enters the accumulator and
+    // every accumulator value is bounded by   (|bias| + |diag| + |gru_a_dense_feature row| + 3 max|E|) * 16256 + 255 * sum|w|.
+    if (!is_float) {
+        double cmax = 0, emax = 0, bmax = 0, dmax = 0, smax = 0;
+        for (int i = 0; i < 3 * NA; i++) {
+            double c = fabs(gad_b[i]);
+            for (int j = 0; j < COND; j++) c += fabs(gad_w[(size_t)j * 3 * NA + i]);
+            cmax = std::max(cmax, c);
+            bmax = std::max(bmax, (double)fabs(ga_subias[3 * NA + i]));
+            dmax = std::max(dmax, (double)fabs(ga_diag[i]));
+        }
+        for (size_t i = 0; i < (size_t)256 * 3 * NA; i++)
+            emax = std::max(emax, (double)std::max(fabs(emb_sig[i]), std::max(fabs(emb_pred[i]), fabs(emb_exc[i]))));
+        for (int rg = 0; rg < 3 * NGRP; rg++) {
+            double rs[8] = {0};
+            for (auto &b : rowsA[rg]) for (int o = 0; o < 8; o++) for (int i = 0; i < 4; i++) rs[o] += abs((int)(signed char)b.w[o * 4 + i]);
+            for (int o = 0; o < 8; o++) smax = std::max(smax, rs[o]);
+        }
+        const double bound = (bmax + dmax + cmax + 3 * emax) * 1.01 * (128.0 * 127.0) + 255.0 * smax + 2;
+        m->fast_cvt = bound < 4194304.0 * 0.99;
+    }
     hm.embed_pitch = embed_pitch; hm.conv1_w = conv1_w; hm.conv1_b = conv1_b; hm.conv2_w = conv2_w; hm.conv2_b = conv2_b;
     hm.dense1_w = dense1_w; hm.dense1_b = dense1_b; hm.dense2_w = dense2_w; hm.dense2_b = dense2_b;
     hm.gad_w = gad_w; hm.gad_b = gad_b; hm.gbd_w = gbd_w; hm.gbd_b = gbd_b;

@@ -45,8 +45,7 @@ namespace {
 
 // named barriers of the compute warps
 enum {
-    BAR_X = 1,       // new quantised GRU_A state of the half complete (and its candidate-gate tile consumed)
-    BAR_ACCB = 2,    // GRU_B partial sums complete
+    BAR_X = 1,       // restored state visible (kernel start only)
     BAR_HB = 3       // (+ half) finishing warps arrive, sampler waits: GRU_B state of the half's sample is in hBs
 };
 constexpr int CNT_C = NWC * 32, CNT_HB = NFIN * 32 + 32;
@@ -191,33 +190,23 @@ struct ComputeCtx {
     const float *parA;                  // + 2t folded in
     const float *parB;
     const uint8_t *wBrec;
-    const uint32_t *rcp;
+    RcpShared rcp;
     uint8_t *smem;
     int gcol[GPW];                      // neuron index of this lane's first neuron of each group: 8*g + 2t
     uint32_t xoff[GPW];                 // byte offset (in a state buffer) of this lane's two quantised neurons, stream gid of half 0 (half 1: ^ 64, stream gid+8: + 4)
 };
 
 // One GRU_A + GRU_B step of half H (16 streams).  k0 = index of the half-step's first tile fill (gate r; z and h follow).
-template <int H>
-__device__ __forceinline__ void compute_half_step(const ComputeCtx &C, const SampleParams &P, float (&h)[GPW][4], float &hb,
-                                                  uint32_t k0, int cur, int f, int s_fin)
-{
-    uint8_t *smem = C.smem;
-    const int gid = C.gid, t = C.t, lane = C.lane, warp = C.warp;
-    const uint32_t *rcp = C.rcp;
-    const int nxt = cur ^ 1;
-    const uint32_t xs_cur = C.xs0 + cur * XS_BYTES, lc = C.gid8 | (H << 6);
-    uint8_t *xs_nxt = smem + SM_XS + nxt * XS_BYTES;
-    const uint32_t kr = k0, kz = k0 + 1, kh = k0 + 2;
-    const float *tile_r = reinterpret_cast<const float *>(smem + SM_TILES + (kr & 3) * TILE_BYTES) + gid * GIN_ROW;
-    const float *tile_z = reinterpret_cast<const float *>(smem + SM_TILES + (kz & 3) * TILE_BYTES) + gid * GIN_ROW;
-    uint8_t *tile_hb = smem + SM_TILES + (kh & 3) * TILE_BYTES;
-    const float *tile_h = reinterpret_cast<const float *>(tile_hb) + gid * GIN_ROW;
-    const uint32_t mb_full = smem_u32(smem + MB_FULL), mb_empty = smem_u32(smem + MB_EMPTY);
+// A half-step of the compute warps is issued in three pieces so that no CTA-wide barrier is waited for right after it
+// is armed:   gemv_rh<H>  |  grub<other half, previous half-step>  |  activations<H> (ends by ARRIVING on MB_X[H])
+// and grub<H> (which WAITS on MB_X[H]) only runs after the next half-step's first GEMVs.
+// k0 = index of the half-step's first tile fill (gate r; z and h follow).
 
-    int Sh[GPW][4];                                              // candidate-gate GEMV sums; later (bit pattern) rec_h * r
-    int Sg[GPW][4];                                              // r-gate sums, later z-gate sums, later (bit pattern) z
-    // ---- GEMVs of the candidate and reset gates (need only the previous state) ----
+// GEMVs of the candidate and reset gates of half H (need only the previous state)
+template <int H>
+__device__ __forceinline__ void gemv_rh(const ComputeCtx &C, int (&Sh)[GPW][4], int (&Sg)[GPW][4], int cur)
+{
+    const uint32_t xs_cur = C.xs0 + cur * XS_BYTES, lc = C.gid8 | (H << 6);
 #pragma unroll
     for (int sl = 0; sl < GPW; sl++) {
         const uint32_t *dir = C.dirA + sl * 3 * 2;
@@ -227,6 +216,25 @@ __device__ __forceinline__ void compute_half_step(const ComputeCtx &C, const Sam
         mma_quads(Sg[sl], w, meta, (int)dir[3], xs_cur, lc);      // r list, directly followed by the h list
         mma_quads(Sh[sl], w, meta, (int)dir[5], xs_cur, lc);
     }
+}
+
+// gates r, z, candidate and state update of half H; Sh / Sg = GEMV sums of the candidate / reset gate
+template <int H, bool FAST>
+__device__ __forceinline__ void activations(const ComputeCtx &C, float (&h)[GPW][4], int (&Sh)[GPW][4], int (&Sg)[GPW][4], uint32_t k0, int cur)
+{
+    uint8_t *smem = C.smem;
+    const int gid = C.gid, t = C.t, lane = C.lane, warp = C.warp;
+    const RcpShared rcp = C.rcp;
+    const int nxt = cur ^ 1;
+    const uint32_t xs_cur = C.xs0 + cur * XS_BYTES, lc = C.gid8 | (H << 6);
+    uint8_t *xs_nxt = smem + SM_XS + nxt * XS_BYTES;
+    const uint32_t kr = k0, kz = k0 + 1, kh = k0 + 2;
+    const float *tile_r = reinterpret_cast<const float *>(smem + SM_TILES + (kr & 3) * TILE_BYTES) + gid * GIN_ROW;
+    const float *tile_z = reinterpret_cast<const float *>(smem + SM_TILES + (kz & 3) * TILE_BYTES) + gid * GIN_ROW;
+    uint8_t *tile_hb = smem + SM_TILES + (kh & 3) * TILE_BYTES;
+    const float *tile_h = reinterpret_cast<const float *>(tile_hb) + gid * GIN_ROW;
+    const uint32_t mb_full = smem_u32(smem + MB_FULL), mb_empty = smem_u32(smem + MB_EMPTY);
+    (void)t; (void)warp; (void)rcp; (void)nxt; (void)xs_cur; (void)lc; (void)xs_nxt; (void)tile_r; (void)tile_z; (void)tile_h; (void)mb_full; (void)mb_empty; (void)lane;
     // ---- reset gate r (nnet.c:431-435) with the gathered input term; keep rec_h * r (nnet.c:436-440) ----
     mbar_wait(mb_full + 8 * (kr & 3), (kr >> 2) & 1);
 #pragma unroll
@@ -242,10 +250,10 @@ __device__ __forceinline__ void compute_half_step(const ComputeCtx &C, const Sam
 #pragma unroll
             for (int i = 0; i < 2; i++) {
                 const float hv = h[sl][2 * jj + i];
-                const int acc = acc_init(__fadd_rn(__fadd_rn(bri[i], __fmul_rn(dri[i], hv)), gin[i])) + Sg[sl][2 * jj + i];
-                const float r = sigmoid_approx(acc_finish(acc), rcp);
-                const int acch = acc_init(__fadd_rn(bhi[i], __fmul_rn(dhi[i], hv))) + Sh[sl][2 * jj + i];
-                Sh[sl][2 * jj + i] = __float_as_int(__fmul_rn(acc_finish(acch), r));
+                const int acc = acc_init_t<FAST>(__fadd_rn(__fadd_rn(bri[i], __fmul_rn(dri[i], hv)), gin[i])) + Sg[sl][2 * jj + i];
+                const float r = sigmoid_approx(acc_finish_t<FAST>(acc), rcp);
+                const int acch = acc_init_t<FAST>(__fadd_rn(bhi[i], __fmul_rn(dhi[i], hv))) + Sh[sl][2 * jj + i];
+                Sh[sl][2 * jj + i] = __float_as_int(__fmul_rn(acc_finish_t<FAST>(acch), r));
             }
         }
     }
@@ -271,8 +279,8 @@ __device__ __forceinline__ void compute_half_step(const ComputeCtx &C, const Sam
             const float gin[2] = {gv.x, gv.y};
 #pragma unroll
             for (int i = 0; i < 2; i++) {
-                const int acc = acc_init(__fadd_rn(__fadd_rn(bzi[i], __fmul_rn(dzi[i], h[sl][2 * jj + i])), gin[i])) + Sg[sl][2 * jj + i];
-                Sg[sl][2 * jj + i] = __float_as_int(sigmoid_approx(acc_finish(acc), rcp));
+                const int acc = acc_init_t<FAST>(__fadd_rn(__fadd_rn(bzi[i], __fmul_rn(dzi[i], h[sl][2 * jj + i])), gin[i])) + Sg[sl][2 * jj + i];
+                Sg[sl][2 * jj + i] = __float_as_int(sigmoid_approx(acc_finish_t<FAST>(acc), rcp));
             }
         }
     }
@@ -292,13 +300,32 @@ __device__ __forceinline__ void compute_half_step(const ComputeCtx &C, const Sam
                 const float z = __int_as_float(Sg[sl][2 * jj + i]);
                 const float hn = __fadd_rn(__fmul_rn(z, h[sl][2 * jj + i]), __fmul_rn(__fsub_rn(1.f, z), hh));
                 h[sl][2 * jj + i] = hn;
-                q[i] = quant_u8(hn);
+                q[i] = quant_u8_t<FAST>(hn);
             }
             // other buffer: readers of the old state are unaffected
-            *reinterpret_cast<uint16_t *>(xs_nxt + (C.xoff[sl] ^ (H << 6)) + 4 * jj) = (uint16_t)(q[0] | (q[1] << 8));
+            *reinterpret_cast<uint16_t *>(xs_nxt + (C.xoff[sl] ^ (H << 6)) + 4 * jj) = (uint16_t)__byte_perm(q[0], q[1], 0x0040);
         }
-    bar_sync(BAR_X, CNT_C);                                      // new quantised GRU_A state complete; candidate-gate tile dead: GRU_B scratch may use it
+    warp_arrive(smem_u32(smem + MB_X) + 8 * H, lane);            // this warp's part of the new quantised state is written, candidate-gate tile consumed
+}
 
+// GRU_B of half H for the half-step whose activations were issued before; par = parity of that sample
+template <int H, bool FAST>
+__device__ __forceinline__ void grub(const ComputeCtx &C, const SampleParams &P, float &hb, uint32_t k0, int cur, int f, int s_fin, uint32_t par)
+{
+    uint8_t *smem = C.smem;
+    const int gid = C.gid, t = C.t, lane = C.lane, warp = C.warp;
+    const RcpShared rcp = C.rcp;
+    const int nxt = cur ^ 1;
+    const uint32_t xs_cur = C.xs0 + cur * XS_BYTES, lc = C.gid8 | (H << 6);
+    uint8_t *xs_nxt = smem + SM_XS + nxt * XS_BYTES;
+    const uint32_t kr = k0, kz = k0 + 1, kh = k0 + 2;
+    const float *tile_r = reinterpret_cast<const float *>(smem + SM_TILES + (kr & 3) * TILE_BYTES) + gid * GIN_ROW;
+    const float *tile_z = reinterpret_cast<const float *>(smem + SM_TILES + (kz & 3) * TILE_BYTES) + gid * GIN_ROW;
+    uint8_t *tile_hb = smem + SM_TILES + (kh & 3) * TILE_BYTES;
+    const float *tile_h = reinterpret_cast<const float *>(tile_hb) + gid * GIN_ROW;
+    const uint32_t mb_full = smem_u32(smem + MB_FULL), mb_empty = smem_u32(smem + MB_EMPTY);
+    (void)t; (void)warp; (void)rcp; (void)nxt; (void)xs_cur; (void)lc; (void)xs_nxt; (void)tile_r; (void)tile_z; (void)tile_h; (void)mb_full; (void)mb_empty; (void)lane;
+    mbar_wait(smem_u32(smem + MB_X) + 8 * H, par);               // new quantised GRU_A state complete; candidate-gate tile dead: GRU_B scratch may use it
     // ---------------- GRU_B input GEMV (48 x 384 int8, dense): warp = (row group, K part) ----------------
     int *accB = reinterpret_cast<int *>(tile_hb + T_ACCB);
     float *hBs = reinterpret_cast<float *>(tile_hb + T_HBS);
@@ -310,6 +337,7 @@ __device__ __forceinline__ void compute_half_step(const ComputeCtx &C, const Sam
         const int rgp = warp / KPARTS, part = warp % KPARTS;
         int *dst = accB + (part * 3 * NB + rgp * 8 + 2 * t) * ACCB_ROW + gid;
         dst[0] = acc[0]; dst[ACCB_ROW] = acc[1]; dst[8] = acc[2]; dst[ACCB_ROW + 8] = acc[3];
+        warp_arrive(smem_u32(smem + MB_ACCB) + 8 * H, lane);
     }
     // ---------------- GRU_B finish (nnet.c:346-371): warp < NFIN, lane = (neuron parity, stream of the half) ----------------
     uint32_t *xb = reinterpret_cast<uint32_t *>(smem + SM_XB) + H * (2 * 4 * HALF);
@@ -327,7 +355,7 @@ __device__ __forceinline__ void compute_half_step(const ComputeCtx &C, const Sam
             rr = dp4a_us(xw, *reinterpret_cast<const int *>(C.wBrec + ((((NB + jb) >> 3) * 4 + k) * 8 + ((NB + jb) & 7)) * 4), rr);
             rh = dp4a_us(xw, *reinterpret_cast<const int *>(C.wBrec + ((((2 * NB + jb) >> 3) * 4 + k) * 8 + ((2 * NB + jb) & 7)) * 4), rh);
         }
-        bar_sync(BAR_ACCB, CNT_C);                               // all K-part partial sums are in accB
+        mbar_wait(smem_u32(smem + MB_ACCB) + 8 * H, par);      // all K-part partial sums are in accB
         int az = acc_init(__fadd_rn(C.parB[jb], cbz)), ar = acc_init(__fadd_rn(C.parB[NB + jb], cbr)), ah = acc_init(__fadd_rn(C.parB[2 * NB + jb], cbh));
 #pragma unroll
         for (int kp = 0; kp < KPARTS; kp++) {
@@ -343,14 +371,13 @@ __device__ __forceinline__ void compute_half_step(const ComputeCtx &C, const Sam
         reinterpret_cast<uint8_t *>(xb + nxt * 4 * HALF)[((jb >> 2) * HALF + si) * 4 + (jb & 3)] = (uint8_t)quant_u8(hb);
         __threadfence_block();
         bar_arrive(BAR_HB + H, CNT_HB);                          // GRU_B state of this sample is in hBs
-    } else {
-        bar_sync(BAR_ACCB, CNT_C);
     }
     warp_arrive(mb_empty + 8 * (kh & 3), lane);                  // (its refill is additionally gated by the half's next indices)
 }
 
 }  // namespace
 
+template <bool FAST>
 __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const __grid_constant__ SampleParams P)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -365,7 +392,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         for (int b = 0; b < NTILE; b++) { mbar_init(smem_u32(smem + MB_FULL) + 8 * b, NWP); mbar_init(smem_u32(smem + MB_EMPTY) + 8 * b, NWC); }
-        for (int hh = 0; hh < 2; hh++) { mbar_init(smem_u32(smem + MB_IDX) + 8 * hh, 1); }
+        for (int hh = 0; hh < 2; hh++) { mbar_init(smem_u32(smem + MB_IDX) + 8 * hh, 1); mbar_init(smem_u32(smem + MB_X) + 8 * hh, NWC); mbar_init(smem_u32(smem + MB_ACCB) + 8 * hh, NWB); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -377,7 +404,8 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
             bulk_g2s(smem_u32(smem + SM_IMAGE + o), P.image + o, nbytes, bar);
         }
     }
-    const uint32_t *rcp = reinterpret_cast<const uint32_t *>(smem + SM_IMAGE + IM_RCP);
+    const RcpShared rcp = {smem_u32(smem + SM_IMAGE + IM_RCP)};
+    if (threadIdx.x == 0 && (rcp.addr & 0x1FFFu) != 0) __trap();      // the table-address trick of rcp_emul needs the 8 KB alignment
     int *idx_s = reinterpret_cast<int *>(smem + SM_IDX);
 
     if (warp < NWC) {
@@ -436,12 +464,19 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
         }
         bar_sync(BAR_X, CNT_C);                                          // restored quantised state visible to all compute warps
 
-        uint32_t k = 0; int step = 0;
+        uint32_t k = 0; int step = 0, f_prev = 0;
         for (int f = 0; f < P.nframes; f++)
             for (int t_ = 0; t_ < spf; t_++, step++, k += 6) {
-                compute_half_step<0>(C, P, h[0], hb[0], k, step & 1, f, s_fin[0]);
-                compute_half_step<1>(C, P, h[1], hb[1], k + 3, step & 1, f, s_fin[1]);
+                int Sh[GPW][4], Sg[GPW][4];                              // candidate-gate sums (later rec_h * r) / r-gate, then z-gate sums (later z)
+                gemv_rh<0>(C, Sh, Sg, step & 1);
+                if (step > 0) grub<1, FAST>(C, P, hb[1], k - 3, (step - 1) & 1, f_prev, s_fin[1], (step - 1) & 1);
+                activations<0, FAST>(C, h[0], Sh, Sg, k, step & 1);
+                gemv_rh<1>(C, Sh, Sg, step & 1);
+                grub<0, FAST>(C, P, hb[0], k, step & 1, f, s_fin[0], step & 1);
+                activations<1, FAST>(C, h[1], Sh, Sg, k + 3, step & 1);
+                f_prev = f;
             }
+        if (step > 0) grub<1, FAST>(C, P, hb[1], k - 3, (step - 1) & 1, f_prev, s_fin[1], (step - 1) & 1);
         // ---- save the recurrent state ----
 #pragma unroll
         for (int sl = 0; sl < GPW; sl++)
@@ -615,10 +650,11 @@ int sample_kernel_smem_ok(uint32_t bytes)
 cudaError_t launch_sample_kernel(const SampleParams &p, cudaStream_t st)
 {
     // per-device attribute; cheap enough to set on every launch (one launch covers >= 160 x n_streams samples)
-    cudaError_t e = cudaFuncSetAttribute(lpcnet_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    auto kern = p.fast_cvt ? lpcnet_sample_kernel<true> : lpcnet_sample_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     const int ctas = (p.n_streams + STREAMS_PER_CTA - 1) / STREAMS_PER_CTA;
-    lpcnet_sample_kernel<<<ctas, SAMPLE_THREADS, p.L.total_bytes, st>>>(p);
+    kern<<<ctas, SAMPLE_THREADS, p.L.total_bytes, st>>>(p);
     return cudaGetLastError();
 }
 

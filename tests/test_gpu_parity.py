@@ -62,6 +62,17 @@ def test_synthesis_matches_reference_golden(eng):
     b.close()
 
 
+def test_conversion_unit_path_matches_golden_too(eng, monkeypatch):
+    """The kernel rounds the GRU_A accumulators without F2I/I2F when the model's pre-activations are provably small
+    (devmath.cuh acc_init_t); LPCNET_B200_EXACT_CVT forces the conversion-unit instantiation, which must agree."""
+    gold = np.load(os.path.join(H.GOLDEN, "synth_A.npz"))["pcm"]
+    monkeypatch.setenv("LPCNET_B200_EXACT_CVT", "1")
+    b = _batch(eng, 4)
+    got = b.synthesize(make_feature_batch(range(4), 40))
+    b.close()
+    assert _first_diff(got, gold) is None
+
+
 def test_synthesis_matches_oracle_ragged_batch(eng):
     """70 streams (two full CTAs + a 6-lane tail), 36-float feature stride, distinct features per stream."""
     n, T = 70, 10
