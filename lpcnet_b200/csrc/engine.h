@@ -30,14 +30,14 @@ constexpr int NWC = LPCNET_NWC;              // compute warps (12, 16 or 24): ea
                                              // GRU_B input GEMV and up to ceil(16/NWC) GRU_B neurons.  24 warps x 2 groups keeps the per-thread
                                              // working set small (h, S_h, S_z = 48 registers) so that 7 warps per scheduler hide the LDS latency
 #ifndef LPCNET_NWP
-#define LPCNET_NWP 7
+#define LPCNET_NWP 6
 #endif
 constexpr int NWP = LPCNET_NWP;              // producer warps: cooperative gather of the GRU_A input rows.  The gather is latency-bound (L2 hits, ~1k cycles
                                              // under load), so what matters is loads in flight: NWP warps x (registers/4) LDG.128 each
 constexpr int NGRP = NA / 8;                 // 48 groups of 8 neurons (one 8-row block group per gate)
 constexpr int GPW = NGRP / NWC;              // neuron groups per compute warp
 static_assert(NGRP % NWC == 0, "compute warps must divide the 48 neuron groups");
-constexpr int SAMPLE_THREADS = (NWC + NWP + 1) * 32;   // + 1 sampler warp (tree sampler, LPC filter, u-law, de-emphasis)
+constexpr int SAMPLE_THREADS = (NWC + NWP + 2) * 32;   // + 2 sampler warps, one per half (tree sampler, LPC filter, u-law, de-emphasis)
 constexpr int XS_BYTES = (NA / 4) * 32 * 4;  // quantised GRU_A state of 32 streams: [96 column blocks][32 words], see xs_offset()
 constexpr int FCW_ROW = 36;                  // dual_fc row: 32 weights (16 per channel) + {bias0, bias1, factor0, factor1}; 144 B stride = 16 mod 128, so the
                                              // per-lane LDS.128 row reads of lanes on different nodes mostly land in different 4-bank groups

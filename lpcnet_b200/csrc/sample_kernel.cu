@@ -28,9 +28,9 @@
 //   NWP producer warps gather the GRU_A input term cond + E_sig[a] + E_pred[b] + E_exc[c] (compute_gru_a_input), one gate of
 //                     one half at a time, with 512-byte contiguous LDG.128 into a ring of four [16][392] fp32 tiles
 //                     (full/empty mbarriers) that the compute lanes read conflict-free.
-//    1 sampler warp   (lane == stream; lanes 0-15 half A, 16-31 half B) runs the strictly serial tail (two KISS99 draws,
-//                     8-level sigmoid tree with sequential fp32 dot products, ulaw2lin, order-16 LPC filter, de-emphasis,
-//                     lin2ulaw), one half at a time.
+//    2 sampler warps  (one per half; lanes 0-15 = the streams, lanes 16-31 shadow them and evaluate the second dual_fc channel)
+//                     run the strictly serial tail (two KISS99 draws, 8-level sigmoid tree with sequential fp32 dot
+//                     products, ulaw2lin, order-16 LPC filter, de-emphasis, lin2ulaw).
 //
 // Weights, su-biases, the upper dual_fc levels and the sampler tables are staged into shared memory once per launch
 // by TMA bulk copies (cp.async.bulk + mbarrier).  Roles hand data over with mbarriers; the compute warps synchronise
@@ -38,6 +38,15 @@
 #include <cstdint>
 #include "engine.h"
 #include "devmath.cuh"
+
+#ifndef LPCNET_GATHER_NOALLOC
+#define LPCNET_GATHER_NOALLOC 0
+#endif
+#if LPCNET_GATHER_NOALLOC
+#define GLD ldg4_stream
+#else
+#define GLD ldg4
+#endif
 
 namespace lpcnet_b200 {
 
@@ -165,7 +174,7 @@ __device__ __forceinline__ void gather_half(float *__restrict__ G, const float *
         const float *e2 = emb_exc + idx_h[2 * HALF + si] * (3 * NA) + col;
         float4 a[3], b[3], d[3], e[3];
 #pragma unroll
-        for (int j = 0; j < 3; j++) { a[j] = ldg4(c + 128 * j); b[j] = ldg4(e0 + 128 * j); d[j] = ldg4(e1 + 128 * j); e[j] = ldg4(e2 + 128 * j); }
+        for (int j = 0; j < 3; j++) { a[j] = GLD(c + 128 * j); b[j] = GLD(e0 + 128 * j); d[j] = GLD(e1 + 128 * j); e[j] = GLD(e2 + 128 * j); }
         float *g = G + si * GIN_ROW + lane * 4;
 #pragma unroll
         for (int j = 0; j < 3; j++) {
@@ -512,17 +521,21 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
                 }
         }
     } else {
-        // =====================================================  sampler warp  =====================================================
+        // =====================================================  sampler warps  =====================================================
+        // warp NWC+NWP+hh serves half hh.  Lane = (channel, stream): both lanes of a stream run the same serial code on the
+        // same state (so they take the same decisions); they differ only in the dual_fc channel they evaluate, and the
+        // channel-1 lane issues no stores.
         mbar_wait(bar, 0);
-        const int s_raw = cta_s0 + lane;
-        const bool live = s_raw < n;
-        const int s = live ? s_raw : n - 1;          // dead lanes shadow the last stream (all loads valid), stores masked
-        const int myh = lane >> 4, si = lane & 15;
+        const int hh = warp - NWC - NWP, ch = lane >> 4, si = lane & 15;
+        const int s_raw = cta_s0 + HALF * hh + si;
+        const bool live = s_raw < n && ch == 0;
+        const int s = min(s_raw, n - 1);             // dead lanes shadow the last stream (all loads valid), stores masked
         const float *logit = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_LOGIT);
         const float *u2l = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_U2L);
-        const float *fcw = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_FCW);
-        const uint32_t mb_idx = smem_u32(smem + MB_IDX);
-        int *idx_h = idx_s + myh * 3 * HALF;
+        const float *fcw = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_FCW) + ch * NB;
+        const float *fcw_g = P.fcw + ch * NB;
+        const uint32_t mb_idx = smem_u32(smem + MB_IDX) + 8 * hh;
+        int *idx_h = idx_s + hh * 3 * HALF;
 
         float ls[LPC_ORDER], lpc[LPC_ORDER];
 #pragma unroll
@@ -534,17 +547,17 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
         short *pcm_out = P.pcm + (size_t)s * P.pcm_stream_stride;
         float pred = 0.f;
 
-        // publish the conditioning indices of the half's next sample (lpcnet.c:251-254); the lanes of the other half idle
-        auto publish = [&](int hh) {
-            if (myh == hh) {
-                pred = 0.f;
+        // publish the conditioning indices of the half's next sample (lpcnet.c:251-254)
+        auto publish = [&]() {
+            pred = 0.f;
 #pragma unroll
-                for (int j = 0; j < LPC_ORDER; j++) pred = __fsub_rn(pred, __fmul_rn(ls[j], lpc[j]));
+            for (int j = 0; j < LPC_ORDER; j++) pred = __fsub_rn(pred, __fmul_rn(ls[j], lpc[j]));
+            if (ch == 0) {
                 idx_h[si] = lin2ulaw(ls[0]);
                 idx_h[HALF + si] = lin2ulaw(pred);
                 idx_h[2 * HALF + si] = last_exc;
             }
-            warp_arrive(mb_idx + 8 * hh, lane);
+            warp_arrive(mb_idx, lane);
         };
         auto load_lpc = [&](int f) {   // frame f uses the LPC computed from the features of frame f-2 (lpcnet.c:110-112), weighted by gamma^i (freq.c:299-308)
             const float *lp = P.lpc_raw + ((size_t)f * n + s) * LPC_ORDER;
@@ -554,82 +567,63 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
             for (int j = 0; j < LPC_ORDER; j++) lpc[j] = __fmul_rn(raw[j], __ldg(&P.gamma_pow[j]));
         };
         load_lpc(0);
-        publish(0); publish(1);
-        uint32_t it = 0, k = 0;
+        publish();
+        uint32_t k = 0;
         for (int f = 0; f < P.nframes; f++) {
-            for (int t_ = 0; t_ < spf; t_++, it++, k += 6) {
+            for (int t_ = 0; t_ < spf; t_++, k += 6) {
                 const bool last_t = t_ == spf - 1, last = last_t && f == P.nframes - 1;
-#pragma unroll 1
-                for (int hh = 0; hh < 2; hh++) {
-                    bar_sync(BAR_HB + hh, CNT_HB);                       // GRU_B state of the half is in hBs (inside the half's candidate-gate tile)
-                    if (myh == hh) {
-                        const float *hBs = reinterpret_cast<const float *>(smem + SM_TILES + ((k + 3 * hh + 2) & 3) * TILE_BYTES + T_HBS);
-                        // thresholds (nnet.c:178-184): two RNG words -> 8 logits
-                        float thr[8];
-                        {
-                            uint32_t r0 = kiss99_rand(rng), r1 = kiss99_rand(rng);
-                            thr[0] = logit[r0 & 0xFF]; thr[1] = logit[(r0 >> 8) & 0xFF]; thr[2] = logit[(r0 >> 16) & 0xFF]; thr[3] = logit[r0 >> 24];
-                            thr[4] = logit[r1 & 0xFF]; thr[5] = logit[(r1 >> 8) & 0xFF]; thr[6] = logit[(r1 >> 16) & 0xFF]; thr[7] = logit[r1 >> 24];
-                        }
-                        float hbv[NB];
-#pragma unroll
-                        for (int j = 0; j < NB; j++) hbv[j] = hBs[j * HALF + si];
-                        int val = 0;
-#pragma unroll
-                        for (int b = 0; b < 8; b++) {                    // sample_mdense, nnet.c:186-211
-                            const int i = (1 << b) | val;
-                            float sum1, sum2, fac1, fac2;
-                            // two sequential 16-term chains (one per channel), fed 8 weights at a time to keep the live set small
-                            if (b < 6) {                                 // nodes < 64: rows in shared memory
-                                const float *wr = fcw + i * FCW_ROW;
-                                const float4 bf = *reinterpret_cast<const float4 *>(wr + 32);
-                                sum1 = bf.x; sum2 = bf.y; fac1 = bf.z; fac2 = bf.w;
-#pragma unroll
-                                for (int j0 = 0; j0 < NB; j0 += 8) {
-                                    const float4 a0 = *reinterpret_cast<const float4 *>(wr + j0), a1 = *reinterpret_cast<const float4 *>(wr + j0 + 4);
-                                    const float4 c0 = *reinterpret_cast<const float4 *>(wr + NB + j0), c1 = *reinterpret_cast<const float4 *>(wr + NB + j0 + 4);
-                                    const float wa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, wc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-#pragma unroll
-                                    for (int j = 0; j < 8; j++) {
-                                        sum1 = __fadd_rn(sum1, __fmul_rn(wa[j], hbv[j0 + j]));
-                                        sum2 = __fadd_rn(sum2, __fmul_rn(wc[j], hbv[j0 + j]));
-                                    }
-                                }
-                            } else {                                     // lower levels: one 144-byte row per lane from global (L2-resident)
-                                const float *wr = P.fcw + i * FCW_ROW;
-                                const float4 bf = ldg4(wr + 32);
-                                sum1 = bf.x; sum2 = bf.y; fac1 = bf.z; fac2 = bf.w;
-#pragma unroll
-                                for (int j0 = 0; j0 < NB; j0 += 8) {
-                                    const float4 a0 = ldg4(wr + j0), a1 = ldg4(wr + j0 + 4), c0 = ldg4(wr + NB + j0), c1 = ldg4(wr + NB + j0 + 4);
-                                    const float wa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, wc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-#pragma unroll
-                                    for (int j = 0; j < 8; j++) {
-                                        sum1 = __fadd_rn(sum1, __fmul_rn(wa[j], hbv[j0 + j]));
-                                        sum2 = __fadd_rn(sum2, __fmul_rn(wc[j], hbv[j0 + j]));
-                                    }
-                                }
-                            }
-                            sum1 = __fmul_rn(fac1, tanh_approx(sum1, rcp));
-                            sum2 = __fmul_rn(fac2, tanh_approx(sum2, rcp));
-                            sum1 = __fadd_rn(sum1, sum2);
-                            val = (val << 1) | (thr[b] < sum1 ? 1 : 0);
-                        }
-                        const int exc = val;
-                        float pcm = __fadd_rn(pred, u2l[exc]);           // lpcnet.c:260
-#pragma unroll
-                        for (int j = LPC_ORDER - 1; j > 0; j--) ls[j] = ls[j - 1];
-                        ls[0] = pcm;
-                        last_exc = exc;
-                        pcm = __fadd_rn(pcm, __fmul_rn(0.85f, deemph));  // PREEMPH, lpcnet.c:265
-                        deemph = pcm;
-                        if (pcm < -32767) pcm = -32767;
-                        if (pcm > 32767) pcm = 32767;
-                        if (live) pcm_out[(size_t)f * spf + t_] = (short)__double2int_rd(0.5 + (double)pcm);   // (int)floor(.5 + pcm)
-                        if (last_t && !last) load_lpc(f + 1);
-                    }
-                    if (!last) publish(hh);                              // indices of the half's next sample
+                // thresholds (nnet.c:178-184): two RNG words -> 8 logits; does not depend on the network
+                float thr[8];
+                {
+                    uint32_t r0 = kiss99_rand(rng), r1 = kiss99_rand(rng);
+                    thr[0] = logit[r0 & 0xFF]; thr[1] = logit[(r0 >> 8) & 0xFF]; thr[2] = logit[(r0 >> 16) & 0xFF]; thr[3] = logit[r0 >> 24];
+                    thr[4] = logit[r1 & 0xFF]; thr[5] = logit[(r1 >> 8) & 0xFF]; thr[6] = logit[(r1 >> 16) & 0xFF]; thr[7] = logit[r1 >> 24];
                 }
+                bar_sync(BAR_HB + hh, CNT_HB);                           // GRU_B state of the half is in hBs (inside the half's candidate-gate tile)
+                const float *hBs = reinterpret_cast<const float *>(smem + SM_TILES + ((k + 3 * hh + 2) & 3) * TILE_BYTES + T_HBS);
+                float hbv[NB];
+#pragma unroll
+                for (int j = 0; j < NB; j++) hbv[j] = hBs[j * HALF + si];
+                int val = 0;
+#pragma unroll
+                for (int b = 0; b < 8; b++) {                            // sample_mdense, nnet.c:186-211
+                    const int i = (1 << b) | val;
+                    // this lane's channel: a sequential 16-term chain
+                    float w16[16], sum, fac;
+                    if (b < 6) {                                         // nodes < 64: rows in shared memory
+                        const float *wr = fcw + i * FCW_ROW;
+                        const float4 a0 = *reinterpret_cast<const float4 *>(wr), a1 = *reinterpret_cast<const float4 *>(wr + 4);
+                        const float4 a2 = *reinterpret_cast<const float4 *>(wr + 8), a3 = *reinterpret_cast<const float4 *>(wr + 12);
+                        w16[0] = a0.x; w16[1] = a0.y; w16[2] = a0.z; w16[3] = a0.w; w16[4] = a1.x; w16[5] = a1.y; w16[6] = a1.z; w16[7] = a1.w;
+                        w16[8] = a2.x; w16[9] = a2.y; w16[10] = a2.z; w16[11] = a2.w; w16[12] = a3.x; w16[13] = a3.y; w16[14] = a3.z; w16[15] = a3.w;
+                        sum = wr[2 * NB - ch * NB + ch]; fac = wr[2 * NB - ch * NB + 2 + ch];
+                    } else {                                             // lower levels: the row comes from global memory (L2/L1-resident)
+                        const float *wr = fcw_g + i * FCW_ROW;
+                        const float4 a0 = ldg4(wr), a1 = ldg4(wr + 4), a2 = ldg4(wr + 8), a3 = ldg4(wr + 12);
+                        w16[0] = a0.x; w16[1] = a0.y; w16[2] = a0.z; w16[3] = a0.w; w16[4] = a1.x; w16[5] = a1.y; w16[6] = a1.z; w16[7] = a1.w;
+                        w16[8] = a2.x; w16[9] = a2.y; w16[10] = a2.z; w16[11] = a2.w; w16[12] = a3.x; w16[13] = a3.y; w16[14] = a3.z; w16[15] = a3.w;
+                        sum = __ldg(wr + 2 * NB - ch * NB + ch); fac = __ldg(wr + 2 * NB - ch * NB + 2 + ch);
+                    }
+#pragma unroll
+                    for (int j = 0; j < NB; j++) sum = __fadd_rn(sum, __fmul_rn(w16[j], hbv[j]));
+                    const float mine = __fmul_rn(fac, tanh_approx(sum, rcp));
+                    const float other = __shfl_xor_sync(0xffffffffu, mine, 16);
+                    const float tot = __fadd_rn(mine, other);            // channel 0 + channel 1 (commutative: both lanes get the same bits)
+                    val = (val << 1) | (thr[b] < tot ? 1 : 0);
+                }
+                const int exc = val;
+                float pcm = __fadd_rn(pred, u2l[exc]);                   // lpcnet.c:260
+#pragma unroll
+                for (int j = LPC_ORDER - 1; j > 0; j--) ls[j] = ls[j - 1];
+                ls[0] = pcm;
+                last_exc = exc;
+                pcm = __fadd_rn(pcm, __fmul_rn(0.85f, deemph));          // PREEMPH, lpcnet.c:265
+                deemph = pcm;
+                if (pcm < -32767) pcm = -32767;
+                if (pcm > 32767) pcm = 32767;
+                if (live) pcm_out[(size_t)f * spf + t_] = (short)__double2int_rd(0.5 + (double)pcm);   // (int)floor(.5 + pcm)
+                if (last_t && !last) load_lpc(f + 1);
+                if (!last) publish();                                    // indices of the half's next sample
             }
         }
         if (live) {

@@ -4,11 +4,8 @@ import os, subprocess, sys
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, ROOT)
 VARIANTS = {
-    "c16p7u3": ["LPCNET_NWC=16", "LPCNET_NWP=7", "LPCNET_GU=3"],
-    "c16p4u4": ["LPCNET_NWC=16", "LPCNET_NWP=4", "LPCNET_GU=4"],
-    "c16p4u3": ["LPCNET_NWC=16", "LPCNET_NWP=4", "LPCNET_GU=3"],
-    "c16p3u5": ["LPCNET_NWC=16", "LPCNET_NWP=3", "LPCNET_GU=5"],
-    "c16p5u3": ["LPCNET_NWC=16", "LPCNET_NWP=5", "LPCNET_GU=3"],
+    "alloc": ["LPCNET_GATHER_NOALLOC=0"],
+    "noalloc": ["LPCNET_GATHER_NOALLOC=1"],
 }
 if sys.argv[1] == "build":
     from lpcnet_b200 import build
