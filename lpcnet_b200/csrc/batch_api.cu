@@ -47,6 +47,16 @@ static int ensure(void **p, size_t *cap, size_t bytes)
     return 0;
 }
 
+#ifdef LPCNET_TRACE
+static long long *g_trace = nullptr;
+extern "C" __attribute__((visibility("default"))) int lpcnet_b200_debug_read_trace(long long *out)
+{
+    if (!g_trace) return -1;
+    cudaDeviceSynchronize();
+    return cudaMemcpy(out, g_trace, 8 * 32 * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
+}
+#endif
+
 extern "C" {
 
 int lpcnet_b200_version(void) { return 100; }
@@ -192,6 +202,9 @@ static int synth_device(LPCNetB200Batch *b, const float *d_feat, long long strea
             p.L = b->model.L; p.image = b->model.image;
             p.emb_sig = b->model.emb_sig; p.emb_pred = b->model.emb_pred; p.emb_exc = b->model.emb_exc; p.fcw = b->model.fcw;
             p.fast_cvt = b->model.fast_cvt && !getenv("LPCNET_B200_EXACT_CVT");   // env: force the conversion-unit path (tests)
+#ifdef LPCNET_TRACE
+            { static long long *d_trace = nullptr; if (!d_trace) { CK(cudaMalloc(&d_trace, 8 * 32 * 8)); CK(cudaMemset(d_trace, 0, 8 * 32 * 8)); } p.trace = d_trace; g_trace = d_trace; }
+#endif
             p.condA = b->condA + (size_t)silent * n * 3 * NA;
             p.condB = b->condB + (size_t)silent * n * 3 * NB;
             p.lpc_raw = b->lpc_raw + (size_t)silent * n * LPC_ORDER;

@@ -197,6 +197,9 @@ struct SampleParams {
     long long pcm_stream_stride;
     int n_streams, nframes, spf;
     int fast_cvt;
+#ifdef LPCNET_TRACE
+    long long *trace;        // tuning builds only: clock64 stamps of CTA 0, [8 samples][32 events]
+#endif
 };
 
 // ---- host-side API of the internal modules ----

@@ -199,7 +199,7 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
     uint32_t off = M.sm_image + M.var;
     auto take = [&](uint32_t bytes, uint32_t align = 16) { off = align_up(off, align); uint32_t o = off; off += bytes; return o; };
     // readable slack behind every array: the pipelined GEMVs prefetch past the list end (values never used)
-    const uint32_t unit_w = is_float ? img_blk : QUAD_BYTES, unit_m = is_float ? 2 : QUAD_META_BYTES, slack_w = 2, slack_m = is_float ? 4 : 2;
+    const uint32_t unit_w = is_float ? img_blk : QUAD_BYTES, unit_m = is_float ? 2 : QUAD_META_BYTES, slack_w = is_float ? 2 : 4, slack_m = is_float ? 4 : 6;
     L.wA = take((nA_pad + slack_w) * unit_w, 128);
     L.metaA = take((nA_pad + slack_m) * unit_m);
     L.wB = take((nB_pad + slack_w) * unit_w, 128);
@@ -261,10 +261,16 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
     uint32_t *dirA = reinterpret_cast<uint32_t *>(&img[M.dirA]);
     uint32_t *grpA = reinterpret_cast<uint32_t *>(&img[M.grpA]);
     uint32_t blk = 0;
-    for (int w = 0; w < nwc; w++) for (int s = 0; s < gpw; s++) {
-        int g = grp[w][s];
-        grpA[w * gpw + s] = (uint32_t)g;
-        for (int q = 0; q < 3; q++) {
+    // order of the lists in memory.  float flavour: (warp, slot, gate z r h).  int8 flavour: per warp the r and h lists of
+    // all its slots first (r0 h0 r1 h1 ...: one contiguous quad stream for the GEMVs that precede the reset gate), then
+    // the z lists (z0 z1 ...): the pipelined loader of the kernel runs across list boundaries.
+    for (int w = 0; w < nwc; w++) {
+        std::vector<std::pair<int, int>> seq;    // (slot, gate)
+        if (is_float) { for (int s = 0; s < gpw; s++) for (int q = 0; q < 3; q++) seq.push_back({s, q}); }
+        else { for (int s = 0; s < gpw; s++) { seq.push_back({s, 1}); seq.push_back({s, 2}); } for (int s = 0; s < gpw; s++) seq.push_back({s, 0}); }
+        for (auto sq : seq) {
+            const int s = sq.first, q = sq.second, g = grp[w][s];
+            grpA[w * gpw + s] = (uint32_t)g;
             const auto &lst = rowsA[q * NGRP + g];
             uint32_t np = padded(lst.size());
             dirA[((w * gpw + s) * 3 + q) * 2 + 0] = blk;

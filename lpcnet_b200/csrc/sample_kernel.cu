@@ -48,6 +48,13 @@
 #define GLD ldg4
 #endif
 
+// tuning builds (-DLPCNET_TRACE): clock64 stamps of CTA 0 for samples 200..207 of a launch
+#ifdef LPCNET_TRACE
+#define TRACE(P_, step_, ev_, lane_) do { if (blockIdx.x == 0 && (lane_) == 0 && (step_) >= 200 && (step_) < 208) (P_).trace[((step_) - 200) * 32 + (ev_)] = clock64(); } while (0)
+#else
+#define TRACE(P_, step_, ev_, lane_) do { } while (0)
+#endif
+
 namespace lpcnet_b200 {
 
 namespace {
@@ -119,40 +126,59 @@ __device__ __forceinline__ uint32_t lds16(uint32_t addr)
     asm volatile("{ .reg .u16 t; ld.shared.u16 t, [%1]; cvt.u32.u16 %0, t; }" : "=r"(v) : "r"(addr));
     return v;
 }
-// D[16 streams][8 neurons] += A[16 streams][16 inputs] (u8) . B[16 inputs][8 neurons] (s8): exact int32
-__device__ __forceinline__ void imma16816(int &c0, int &c1, int &c2, int &c3, uint32_t a0, uint32_t a1, uint32_t b0)
-{
-    asm("mma.sync.aligned.m16n8k16.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
-        : "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3) : "r"(a0), "r"(a1), "r"(b0));
-}
 __device__ __forceinline__ int2 lds64(uint32_t addr)
 {
     int2 v;
     asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
     return v;
 }
-// acc[2jj+i] += sum over `nq` quads, for stream gid+8jj (of one half) and neuron 2t+i of the row group.
-//   w    : shared address of the first quad's weights + lane*4      (B fragment word of this lane)
-//   meta : shared address of the first quad's meta + t*2            (xs_offset of slot t's column block)
-//   xs   : shared address of the state buffer; the lane's 8-byte vector of slot t is at xs + (meta entry ^ lc), lc = (half << 6) | (gid << 3)
-// Software-pipelined: the meta entry of quad q+2 and the operands of quad q+1 are in flight while quad q is multiplied
-// (the image keeps two quads of readable slack behind every list).  w and meta are left pointing behind the list: the
-// lists of a neuron group are contiguous (z, r, h), so the caller walks r and h with one address set-up.
-__device__ __forceinline__ void mma_quads(int (&acc)[4], uint32_t &w, uint32_t &meta, int nq, uint32_t xs, uint32_t lc)
+// D[16 streams][8 neurons] += A[16 streams][16 inputs] (u8) . B[16 inputs][8 neurons] (s8): exact int32.
+// Pinned in program order (volatile) for the hand-scheduled quad pipeline below
+__device__ __forceinline__ void imma16816_v(int (&c)[4], const int2 &a, uint32_t b0)
 {
-    uint32_t e1 = lds16(meta + QUAD_META_BYTES);
-    int2 x = lds64(xs + (lds16(meta) ^ lc));
-    uint32_t wv = lds32(w);
-#pragma unroll 1
-    for (int q = 0; q < nq; q++) {
-        const int2 xn = lds64(xs + (e1 ^ lc));
-        const uint32_t wn = lds32(w + QUAD_BYTES);
-        e1 = lds16(meta + 2 * QUAD_META_BYTES);
-        imma16816(acc[0], acc[1], acc[2], acc[3], (uint32_t)x.x, (uint32_t)x.y, wv);
-        x = xn; wv = wn;
-        w += QUAD_BYTES; meta += QUAD_META_BYTES;
-    }
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a.x), "r"(a.y), "r"(b0));
 }
+// A stream of quads (several lists back to back in shared memory) walked with a two-deep operand pipeline:
+// set 0 / set 1 hold the A fragment (x) and B fragment (w) of the next two quads, eA / eB the meta entries of the two
+// quads after those.  Right after a quad is multiplied its registers are reloaded with the quad two positions ahead, so
+// every LDS has two multiplications (and their bookkeeping) to complete, also across list boundaries.  The image keeps
+// six quads of readable slack behind the arrays; what is loaded past the end of a stream is never used.
+//   w    : shared address of the current quad's weights + lane*4     (B fragment word of this lane)
+//   meta : shared address of the current quad's meta + t*2           (xs_offset of slot t's column block)
+//   xs   : shared address of the state buffer; the lane's 8-byte vector of slot t is at xs + (meta entry ^ lc), lc = (half << 6) | (gid << 3)
+struct QuadPipe {
+    uint32_t w, meta, xs, lc;
+    int2 x0, x1;
+    uint32_t w0, w1, eA, eB;
+    __device__ __forceinline__ void start(uint32_t w_, uint32_t meta_, uint32_t xs_, uint32_t lc_)
+    {
+        w = w_; meta = meta_; xs = xs_; lc = lc_;
+        const uint32_t e0 = lds16(meta), e1 = lds16(meta + QUAD_META_BYTES);
+        eA = lds16(meta + 2 * QUAD_META_BYTES); eB = lds16(meta + 3 * QUAD_META_BYTES);
+        w0 = lds32(w); w1 = lds32(w + QUAD_BYTES);
+        x0 = lds64(xs + (e0 ^ lc)); x1 = lds64(xs + (e1 ^ lc));
+    }
+    // acc[2jj+i] += sum over the next `nq` quads of the stream, for stream gid+8jj (of one half) and neuron 2t+i of the row group
+    __device__ __forceinline__ void list(int (&acc)[4], int nq)
+    {
+#pragma unroll 1
+        for (; nq >= 2; nq -= 2) {
+            imma16816_v(acc, x0, w0);
+            x0 = lds64(xs + (eA ^ lc)); w0 = lds32(w + 2 * QUAD_BYTES); eA = lds16(meta + 4 * QUAD_META_BYTES);
+            imma16816_v(acc, x1, w1);
+            x1 = lds64(xs + (eB ^ lc)); w1 = lds32(w + 3 * QUAD_BYTES); eB = lds16(meta + 5 * QUAD_META_BYTES);
+            w += 2 * QUAD_BYTES; meta += 2 * QUAD_META_BYTES;
+        }
+        if (nq) {                                                // odd tail: multiply set 0, reload it, and let the sets trade places
+            imma16816_v(acc, x0, w0);
+            const int2 xn = lds64(xs + (eA ^ lc)); const uint32_t wn = lds32(w + 2 * QUAD_BYTES), en = lds16(meta + 4 * QUAD_META_BYTES);
+            x0 = x1; w0 = w1; eA = eB;
+            x1 = xn; w1 = wn; eB = en;
+            w += QUAD_BYTES; meta += QUAD_META_BYTES;
+        }
+    }
+};
 
 // Producer warps: ONE gate's input term for the 16 streams of a half,
 //   G[si][k] = ((cond[s][k] + E_sig[a_s][k]) + E_pred[b_s][k]) + E_exc[c_s][k]        (nnet.c:484-491, left to right)
@@ -215,15 +241,15 @@ struct ComputeCtx {
 template <int H>
 __device__ __forceinline__ void gemv_rh(const ComputeCtx &C, int (&Sh)[GPW][4], int (&Sg)[GPW][4], int cur)
 {
-    const uint32_t xs_cur = C.xs0 + cur * XS_BYTES, lc = C.gid8 | (H << 6);
+    QuadPipe Q;
+    Q.start(C.wA + C.dirA[2] * QUAD_BYTES, C.metaA + C.dirA[2] * QUAD_META_BYTES, C.xs0 + cur * XS_BYTES, C.gid8 | (H << 6));
 #pragma unroll
     for (int sl = 0; sl < GPW; sl++) {
         const uint32_t *dir = C.dirA + sl * 3 * 2;
 #pragma unroll
         for (int i = 0; i < 4; i++) { Sh[sl][i] = 0; Sg[sl][i] = 0; }
-        uint32_t w = C.wA + dir[2] * QUAD_BYTES, meta = C.metaA + dir[2] * QUAD_META_BYTES;
-        mma_quads(Sg[sl], w, meta, (int)dir[3], xs_cur, lc);      // r list, directly followed by the h list
-        mma_quads(Sh[sl], w, meta, (int)dir[5], xs_cur, lc);
+        Q.list(Sg[sl], (int)dir[3]);                              // the warp's lists are stored r0 h0 r1 h1 ... (model.cu)
+        Q.list(Sh[sl], (int)dir[5]);
     }
 }
 
@@ -268,13 +294,15 @@ __device__ __forceinline__ void activations(const ComputeCtx &C, float (&h)[GPW]
     }
     warp_arrive(mb_empty + 8 * (kr & 3), lane);                  // gate-r tile consumed
     // ---- update gate z (nnet.c:426-430) ----
+    {
+        QuadPipe Q;
+        Q.start(C.wA + C.dirA[0] * QUAD_BYTES, C.metaA + C.dirA[0] * QUAD_META_BYTES, xs_cur, lc);
 #pragma unroll
-    for (int sl = 0; sl < GPW; sl++) {
-        const uint32_t *dir = C.dirA + sl * 3 * 2;
+        for (int sl = 0; sl < GPW; sl++) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) Sg[sl][i] = 0;
-        uint32_t w = C.wA + dir[0] * QUAD_BYTES, meta = C.metaA + dir[0] * QUAD_META_BYTES;
-        mma_quads(Sg[sl], w, meta, (int)dir[1], xs_cur, lc);
+            for (int i = 0; i < 4; i++) Sg[sl][i] = 0;
+            Q.list(Sg[sl], (int)C.dirA[sl * 3 * 2 + 1]);          // z0 z1 z2 are contiguous too
+        }
     }
     mbar_wait(mb_full + 8 * (kz & 3), (kz >> 2) & 1);
 #pragma unroll
@@ -319,7 +347,7 @@ __device__ __forceinline__ void activations(const ComputeCtx &C, float (&h)[GPW]
 
 // GRU_B of half H for the half-step whose activations were issued before; par = parity of that sample
 template <int H, bool FAST>
-__device__ __forceinline__ void grub(const ComputeCtx &C, const SampleParams &P, float &hb, uint32_t k0, int cur, int f, int s_fin, uint32_t par)
+__device__ __forceinline__ void grub(const ComputeCtx &C, const SampleParams &P, float &hb, uint32_t k0, int cur, int f, int s_fin, uint32_t par, int trstep = -1)
 {
     uint8_t *smem = C.smem;
     const int gid = C.gid, t = C.t, lane = C.lane, warp = C.warp;
@@ -335,19 +363,22 @@ __device__ __forceinline__ void grub(const ComputeCtx &C, const SampleParams &P,
     const uint32_t mb_full = smem_u32(smem + MB_FULL), mb_empty = smem_u32(smem + MB_EMPTY);
     (void)t; (void)warp; (void)rcp; (void)nxt; (void)xs_cur; (void)lc; (void)xs_nxt; (void)tile_r; (void)tile_z; (void)tile_h; (void)mb_full; (void)mb_empty; (void)lane;
     mbar_wait(smem_u32(smem + MB_X) + 8 * H, par);               // new quantised GRU_A state complete; candidate-gate tile dead: GRU_B scratch may use it
+    TRACE(P, trstep, 27, warp == 0 ? lane : 1);
     // ---------------- GRU_B input GEMV (48 x 384 int8, dense): warp = (row group, K part) ----------------
     int *accB = reinterpret_cast<int *>(tile_hb + T_ACCB);
     float *hBs = reinterpret_cast<float *>(tile_hb + T_HBS);
     if (warp < NWB) {
         int acc[4] = {0, 0, 0, 0};
         const uint32_t q0 = C.dirB[warp * 2], nq = C.dirB[warp * 2 + 1];
-        uint32_t w = C.wB + q0 * QUAD_BYTES, meta = C.metaB + q0 * QUAD_META_BYTES;
-        mma_quads(acc, w, meta, (int)nq, C.xs0 + nxt * XS_BYTES, lc);
+        QuadPipe Q;
+        Q.start(C.wB + q0 * QUAD_BYTES, C.metaB + q0 * QUAD_META_BYTES, C.xs0 + nxt * XS_BYTES, lc);
+        Q.list(acc, (int)nq);
         const int rgp = warp / KPARTS, part = warp % KPARTS;
         int *dst = accB + (part * 3 * NB + rgp * 8 + 2 * t) * ACCB_ROW + gid;
         dst[0] = acc[0]; dst[ACCB_ROW] = acc[1]; dst[8] = acc[2]; dst[ACCB_ROW + 8] = acc[3];
         warp_arrive(smem_u32(smem + MB_ACCB) + 8 * H, lane);
     }
+    TRACE(P, trstep, 28, warp == 0 ? lane : 1);
     // ---------------- GRU_B finish (nnet.c:346-371): warp < NFIN, lane = (neuron parity, stream of the half) ----------------
     uint32_t *xb = reinterpret_cast<uint32_t *>(smem + SM_XB) + H * (2 * 4 * HALF);
     if (warp < NFIN) {
@@ -365,6 +396,7 @@ __device__ __forceinline__ void grub(const ComputeCtx &C, const SampleParams &P,
             rh = dp4a_us(xw, *reinterpret_cast<const int *>(C.wBrec + ((((2 * NB + jb) >> 3) * 4 + k) * 8 + ((2 * NB + jb) & 7)) * 4), rh);
         }
         mbar_wait(smem_u32(smem + MB_ACCB) + 8 * H, par);      // all K-part partial sums are in accB
+        TRACE(P, trstep, 29, warp == 0 ? lane : 1);
         int az = acc_init(__fadd_rn(C.parB[jb], cbz)), ar = acc_init(__fadd_rn(C.parB[NB + jb], cbr)), ah = acc_init(__fadd_rn(C.parB[2 * NB + jb], cbh));
 #pragma unroll
         for (int kp = 0; kp < KPARTS; kp++) {
@@ -477,12 +509,24 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
         for (int f = 0; f < P.nframes; f++)
             for (int t_ = 0; t_ < spf; t_++, step++, k += 6) {
                 int Sh[GPW][4], Sg[GPW][4];                              // candidate-gate sums (later rec_h * r) / r-gate, then z-gate sums (later z)
+                const int tl = warp == 0 ? lane : 1;
+                TRACE(P, step, 0, tl);
                 gemv_rh<0>(C, Sh, Sg, step & 1);
+                TRACE(P, step, 1, tl);
                 if (step > 0) grub<1, FAST>(C, P, hb[1], k - 3, (step - 1) & 1, f_prev, s_fin[1], (step - 1) & 1);
+                TRACE(P, step, 2, tl);       // = HB of half B (previous sample) signalled
+                mbar_wait(smem_u32(smem + MB_FULL) + 8 * (k & 3), (k >> 2) & 1);
+                TRACE(P, step, 3, tl);       // r tile of half A present
                 activations<0, FAST>(C, h[0], Sh, Sg, k, step & 1);
+                TRACE(P, step, 4, tl);
                 gemv_rh<1>(C, Sh, Sg, step & 1);
-                grub<0, FAST>(C, P, hb[0], k, step & 1, f, s_fin[0], step & 1);
+                TRACE(P, step, 5, tl);
+                grub<0, FAST>(C, P, hb[0], k, step & 1, f, s_fin[0], step & 1, step);
+                TRACE(P, step, 6, tl);       // = HB of half A signalled
+                mbar_wait(smem_u32(smem + MB_FULL) + 8 * ((k + 3) & 3), ((k + 3) >> 2) & 1);
+                TRACE(P, step, 7, tl);       // r tile of half B present
                 activations<1, FAST>(C, h[1], Sh, Sg, k + 3, step & 1);
+                TRACE(P, step, 8, tl);
                 f_prev = f;
             }
         if (step > 0) grub<1, FAST>(C, P, hb[1], k - 3, (step - 1) & 1, f_prev, s_fin[1], (step - 1) & 1);
@@ -510,6 +554,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
 #pragma unroll 1
                 for (int hh = 0; hh < 2; hh++) {
                     mbar_wait(mb_idx + 8 * hh, it & 1);                  // indices of this sample of the half are in idx_s
+                    TRACE(P, (int)it, 10 + 4 * hh, p == 0 ? lane : 1);
 #pragma unroll 1
                     for (int gi = 0; gi < 3; gi++, k++) {
                         const int gate = gi == 0 ? 1 : (gi == 1 ? 0 : 2);    // fill order r, z, h
@@ -517,6 +562,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
                         gather_half(reinterpret_cast<float *>(smem + SM_TILES + (k & 3) * TILE_BYTES), condA_f, n, cta_s0 + HALF * hh,
                                     P.emb_sig, P.emb_pred, P.emb_exc, idx_s + hh * 3 * HALF, gate, p, lane);
                         warp_arrive(mb_full + 8 * (k & 3), lane);
+                        TRACE(P, (int)it, 11 + 4 * hh + gi, p == 0 ? lane : 1);
                     }
                 }
         }
@@ -580,6 +626,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
                     thr[4] = logit[r1 & 0xFF]; thr[5] = logit[(r1 >> 8) & 0xFF]; thr[6] = logit[(r1 >> 16) & 0xFF]; thr[7] = logit[r1 >> 24];
                 }
                 bar_sync(BAR_HB + hh, CNT_HB);                           // GRU_B state of the half is in hBs (inside the half's candidate-gate tile)
+                TRACE(P, (int)(k / 6), 20 + 4 * hh, lane);
                 const float *hBs = reinterpret_cast<const float *>(smem + SM_TILES + ((k + 3 * hh + 2) & 3) * TILE_BYTES + T_HBS);
                 float hbv[NB];
 #pragma unroll
@@ -622,8 +669,10 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
                 if (pcm < -32767) pcm = -32767;
                 if (pcm > 32767) pcm = 32767;
                 if (live) pcm_out[(size_t)f * spf + t_] = (short)__double2int_rd(0.5 + (double)pcm);   // (int)floor(.5 + pcm)
+                TRACE(P, (int)(k / 6), 21 + 4 * hh, lane);
                 if (last_t && !last) load_lpc(f + 1);
                 if (!last) publish();                                    // indices of the half's next sample
+                TRACE(P, (int)(k / 6), 22 + 4 * hh, lane);
             }
         }
         if (live) {
