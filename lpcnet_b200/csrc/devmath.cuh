@@ -67,6 +67,35 @@ __device__ __forceinline__ float sigmoid_approx(float x, TAB tab16)
     return fmaxf(0.f, fminf(1.f, num));
 }
 
+// ---- Blackwell packed fp32 (two lanes per 64-bit register pair: FFMA2 / FMUL2 / FADD2) ----
+// Used for the pieces of the activations where both neurons of a lane run the same op.  ptxas contracts a packed
+// multiply followed by a packed add into one FFMA2 even with -fmad=false (observed), which would change the rounding,
+// so the packed forms are applied ONLY where the reference has an fma, a lone multiply, or an add whose result is
+// multiplied (add -> mul cannot be contracted); every mul -> add of the reference stays scalar.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 k2(float c) { return pk2(c, c); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// numerator * x and denominator of the rational approximations (before the reciprocal), two values at a time:
+// X2 = x*x; num = fma(fma(N2,X2,N1),X2,N0) * x; den = fma(fma(D2,X2,D1),X2,D0)          (vec_avx.h:393-440)
+__device__ __forceinline__ void rational2(f32x2 x, float N0, float N1, float N2, float D0, float D1, float D2, f32x2 &num, f32x2 &den)
+{
+    const f32x2 X2 = mul2(x, x);
+    num = fma2(fma2(k2(N2), X2, k2(N1)), X2, k2(N0));
+    den = fma2(fma2(k2(D2), X2, k2(D1)), X2, k2(D0));
+    num = mul2(num, x);
+}
+#define LPCNET_SIGMOID_COEF 238.13200378f, 6.02452230f, 0.00950985f, 952.72399902f, 103.34200287f, 0.74287558f
+#define LPCNET_TANH_COEF 952.52801514f, 96.39235687f, 0.60863042f, 952.72399902f, 413.36801147f, 11.88600922f
+// (float)acc * SCALE_1 for two biased accumulators (see acc_init_t below): add -> mul, safe to pack
+__device__ __forceinline__ f32x2 acc_finish2(int a0, int a1)
+{
+    return mul2(add2(pk2(__int_as_float(a0), __int_as_float(a1)), k2(-12582912.f)), k2(LPCNET_SCALE_1));
+}
+
 // vector_ps_to_epi8 (vec_avx.h:321-336): u8 = sat(rne(fma(x,127,127)))
 __device__ __forceinline__ uint32_t quant_u8(float x)
 {

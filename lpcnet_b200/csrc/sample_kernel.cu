@@ -282,13 +282,33 @@ __device__ __forceinline__ void activations(const ComputeCtx &C, float (&h)[GPW]
         for (int jj = 0; jj < 2; jj++) {
             const float2 gv = *reinterpret_cast<const float2 *>(tile_r + 8 * jj * GIN_ROW + C.gcol[sl]);
             const float gin[2] = {gv.x, gv.y};
+            if constexpr (FAST) {
+                // mul -> add pieces scalar, the rest two neurons at a time (devmath.cuh)
+                int a[2], ah[2];
 #pragma unroll
-            for (int i = 0; i < 2; i++) {
-                const float hv = h[sl][2 * jj + i];
-                const int acc = acc_init_t<FAST>(__fadd_rn(__fadd_rn(bri[i], __fmul_rn(dri[i], hv)), gin[i])) + Sg[sl][2 * jj + i];
-                const float r = sigmoid_approx(acc_finish_t<FAST>(acc), rcp);
-                const int acch = acc_init_t<FAST>(__fadd_rn(bhi[i], __fmul_rn(dhi[i], hv))) + Sh[sl][2 * jj + i];
-                Sh[sl][2 * jj + i] = __float_as_int(__fmul_rn(acc_finish_t<FAST>(acch), r));
+                for (int i = 0; i < 2; i++) {
+                    const float hv = h[sl][2 * jj + i];
+                    a[i] = acc_init_t<true>(__fadd_rn(__fadd_rn(bri[i], __fmul_rn(dri[i], hv)), gin[i])) + Sg[sl][2 * jj + i];
+                    ah[i] = acc_init_t<true>(__fadd_rn(bhi[i], __fmul_rn(dhi[i], hv))) + Sh[sl][2 * jj + i];
+                }
+                f32x2 num, den;
+                rational2(acc_finish2(a[0], a[1]), LPCNET_SIGMOID_COEF, num, den);
+                float n0, n1, d0, d1, rh0, rh1;
+                upk2(num, n0, n1); upk2(den, d0, d1);
+                const float r0 = fmaxf(0.f, fminf(1.f, __fmaf_rn(n0, rcp_emul(d0, rcp), 0.5f)));
+                const float r1 = fmaxf(0.f, fminf(1.f, __fmaf_rn(n1, rcp_emul(d1, rcp), 0.5f)));
+                upk2(acc_finish2(ah[0], ah[1]), rh0, rh1);
+                Sh[sl][2 * jj] = __float_as_int(__fmul_rn(rh0, r0));
+                Sh[sl][2 * jj + 1] = __float_as_int(__fmul_rn(rh1, r1));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    const float hv = h[sl][2 * jj + i];
+                    const int acc = acc_init_t<FAST>(__fadd_rn(__fadd_rn(bri[i], __fmul_rn(dri[i], hv)), gin[i])) + Sg[sl][2 * jj + i];
+                    const float r = sigmoid_approx(acc_finish_t<FAST>(acc), rcp);
+                    const int acch = acc_init_t<FAST>(__fadd_rn(bhi[i], __fmul_rn(dhi[i], hv))) + Sh[sl][2 * jj + i];
+                    Sh[sl][2 * jj + i] = __float_as_int(__fmul_rn(acc_finish_t<FAST>(acch), r));
+                }
             }
         }
     }
@@ -314,10 +334,23 @@ __device__ __forceinline__ void activations(const ComputeCtx &C, float (&h)[GPW]
         for (int jj = 0; jj < 2; jj++) {
             const float2 gv = *reinterpret_cast<const float2 *>(tile_z + 8 * jj * GIN_ROW + C.gcol[sl]);
             const float gin[2] = {gv.x, gv.y};
+            if constexpr (FAST) {
+                int a[2];
 #pragma unroll
-            for (int i = 0; i < 2; i++) {
-                const int acc = acc_init_t<FAST>(__fadd_rn(__fadd_rn(bzi[i], __fmul_rn(dzi[i], h[sl][2 * jj + i])), gin[i])) + Sg[sl][2 * jj + i];
-                Sg[sl][2 * jj + i] = __float_as_int(sigmoid_approx(acc_finish_t<FAST>(acc), rcp));
+                for (int i = 0; i < 2; i++)
+                    a[i] = acc_init_t<true>(__fadd_rn(__fadd_rn(bzi[i], __fmul_rn(dzi[i], h[sl][2 * jj + i])), gin[i])) + Sg[sl][2 * jj + i];
+                f32x2 num, den;
+                rational2(acc_finish2(a[0], a[1]), LPCNET_SIGMOID_COEF, num, den);
+                float n0, n1, d0, d1;
+                upk2(num, n0, n1); upk2(den, d0, d1);
+                Sg[sl][2 * jj] = __float_as_int(fmaxf(0.f, fminf(1.f, __fmaf_rn(n0, rcp_emul(d0, rcp), 0.5f))));
+                Sg[sl][2 * jj + 1] = __float_as_int(fmaxf(0.f, fminf(1.f, __fmaf_rn(n1, rcp_emul(d1, rcp), 0.5f))));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    const int acc = acc_init_t<FAST>(__fadd_rn(__fadd_rn(bzi[i], __fmul_rn(dzi[i], h[sl][2 * jj + i])), gin[i])) + Sg[sl][2 * jj + i];
+                    Sg[sl][2 * jj + i] = __float_as_int(sigmoid_approx(acc_finish_t<FAST>(acc), rcp));
+                }
             }
         }
     }
@@ -331,13 +364,33 @@ __device__ __forceinline__ void activations(const ComputeCtx &C, float (&h)[GPW]
             const float2 gv = *reinterpret_cast<const float2 *>(tile_h + 8 * jj * GIN_ROW + C.gcol[sl]);
             const float gin[2] = {gv.x, gv.y};
             uint32_t q[2];
+            if constexpr (FAST) {
+                f32x2 num, den;
+                rational2(add2(pk2(__int_as_float(Sh[sl][2 * jj]), __int_as_float(Sh[sl][2 * jj + 1])), pk2(gin[0], gin[1])), LPCNET_TANH_COEF, num, den);
+                float d0, d1, t0, t1;
+                upk2(den, d0, d1);
+                upk2(mul2(num, pk2(rcp_emul(d0, rcp), rcp_emul(d1, rcp))), t0, t1);
+                const float hh[2] = {fmaxf(-1.f, fminf(1.f, t0)), fmaxf(-1.f, fminf(1.f, t1))};
+                float hn[2];
 #pragma unroll
-            for (int i = 0; i < 2; i++) {
-                const float hh = tanh_approx(__fadd_rn(__int_as_float(Sh[sl][2 * jj + i]), gin[i]), rcp);
-                const float z = __int_as_float(Sg[sl][2 * jj + i]);
-                const float hn = __fadd_rn(__fmul_rn(z, h[sl][2 * jj + i]), __fmul_rn(__fsub_rn(1.f, z), hh));
-                h[sl][2 * jj + i] = hn;
-                q[i] = quant_u8_t<FAST>(hn);
+                for (int i = 0; i < 2; i++) {
+                    const float z = __int_as_float(Sg[sl][2 * jj + i]);
+                    hn[i] = __fadd_rn(__fmul_rn(z, h[sl][2 * jj + i]), __fmul_rn(__fsub_rn(1.f, z), hh[i]));
+                    h[sl][2 * jj + i] = hn[i];
+                }
+                // quantised bytes in the low bytes of the biased patterns: fma -> add, safe to pack
+                float q0, q1;
+                upk2(add2(fma2(pk2(hn[0], hn[1]), k2(127.f), k2(127.f)), k2(LPCNET_CVT_MAGIC)), q0, q1);
+                q[0] = __float_as_uint(q0); q[1] = __float_as_uint(q1);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    const float hh = tanh_approx(__fadd_rn(__int_as_float(Sh[sl][2 * jj + i]), gin[i]), rcp);
+                    const float z = __int_as_float(Sg[sl][2 * jj + i]);
+                    const float hn = __fadd_rn(__fmul_rn(z, h[sl][2 * jj + i]), __fmul_rn(__fsub_rn(1.f, z), hh));
+                    h[sl][2 * jj + i] = hn;
+                    q[i] = quant_u8_t<FAST>(hn);
+                }
             }
             // other buffer: readers of the old state are unaffected
             *reinterpret_cast<uint16_t *>(xs_nxt + (C.xoff[sl] ^ (H << 6)) + 4 * jj) = (uint16_t)__byte_perm(q[0], q[1], 0x0040);
