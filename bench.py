@@ -100,9 +100,9 @@ def ncu_traffic_per_sample():
     import glob
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
     if not files:
-        return None, None
+        return None, None, None
     d = json.load(open(files[-1]))
-    return float(d["dram_bytes"]) / float(d["samples_in_launch"]), os.path.basename(files[-1])
+    return float(d["dram_bytes"]) / float(d["samples_in_launch"]), os.path.basename(files[-1]), d.get("l1_data_pipe_pct_of_peak_active_sms")
 
 
 def measured_peaks():
@@ -311,11 +311,11 @@ def main():
         achieved = samples_launch * algo_total / (kms * 1e-3) / 1e9
         sm_mhz = clk.get("sm_mhz") or 1965.0
         smem_peak = 128.0 * 148 * sm_mhz * 1e6 / 1e9          # nominal 128 B/clk/SM at the clock observed under load
-        tps, tsrc = ncu_traffic_per_sample()
+        tps, tsrc, l1pct = ncu_traffic_per_sample()
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (fp16-stored weights)" if args.workload == "config2_float" else "u8*s8->s32 (dp4a) + f32", "data": "synthetic",
+            "dtype": "f32 (fp16-stored weights)" if args.workload == "config2_float" else "u8*s8->s32 (mma.sync IMMA) + f32", "data": "synthetic",
             "config": {"workload": {"config3_int8": "config3_int8: %d streams/GPU x %d frames x 160 samples per step, int8 block-sparse GRU_A, bit-exact vs reference build A",
                                     "config2_float": "config2_float: %d streams/GPU x %d frames x 160 samples per step, float GRU arithmetic with fp16-stored weights, bit-exact vs reference build B",
                                     "config5_decode": "config5_decode: %d streams/GPU x %d frames (8-byte packets -> lpcnet_decode), int8, synthetic VQ codebooks"}[args.workload] % (n, F),
@@ -329,6 +329,7 @@ def main():
                          "peak_source": peak_src, "kernel": "lpcnet_sample_kernel_f32" if args.workload == "config2_float" else "lpcnet_sample_kernel", "kernel_ms_per_launch": kms, "kernel_share_of_step": kms * args.steps / (dev_s * 1e3),
                          "algorithmic_bytes_per_sample": algo_total, "sparse_gemv_bytes_per_sample": algo_sparse,
                          "level_serving_the_bytes": "shared memory (weights resident per SM) + L2 (embedding rows)",
+                         "binding_unit": "L1/shared-memory data pipe (LSU wavefronts)", "binding_unit_pct_of_peak_ncu": l1pct,
                          "smem_peak_gbs_nominal": smem_peak, "frac_of_smem_peak": achieved / smem_peak,
                          "sparse_gemv_achieved_gbs": samples_launch * algo_sparse / (kms * 1e-3) / 1e9,
                          "sparse_gemv_frac_of_smem_peak": samples_launch * algo_sparse / (kms * 1e-3) / 1e9 / smem_peak},

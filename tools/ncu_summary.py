@@ -11,6 +11,7 @@ KEYS = ["gpu__time_duration.sum", "sm__cycles_elapsed.max", "launch__registers_p
         "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__throughput.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts.max.pct_of_peak_sustained_elapsed",
         "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sector_hit_rate.pct",
@@ -40,7 +41,10 @@ if os.path.exists(rep):
             grid = int(float(d["launch__grid_size"].replace(",", "")))
             frames = int(os.environ.get("NCU_FRAMES", "3"))
             json.dump({"dram_bytes": num("dram__bytes_read.sum") + num("dram__bytes_write.sum"), "grid": grid, "frames": frames,
-                       "samples_in_launch": 4096 * frames * 160, "note": "ncu --set full capture of lpcnet_sample_kernel at 4096 streams x %d frames" % frames},
+                       "samples_in_launch": 4096 * frames * 160,
+                       "l1_data_pipe_pct_of_peak_active_sms": float(d.get("l1tex__throughput.avg.pct_of_peak_sustained_active", "nan").replace(",", "")),
+                       "issue_active_pct": float(d.get("smsp__issue_active.avg.pct_of_peak_sustained_active", "nan").replace(",", "")),
+                       "note": "ncu --set full capture of lpcnet_sample_kernel at 4096 streams x %d frames" % frames},
                       open(os.path.join(out, "%s_traffic.json" % tag), "w"), indent=1)
         st = sorted(((float(d[h].replace(",", "")), h[len(STALL):-len("_per_issue_active.ratio")]) for h in hdr
                      if h.startswith(STALL) and h.endswith("_per_issue_active.ratio") and d[h]), reverse=True)
