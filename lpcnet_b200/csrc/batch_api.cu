@@ -201,6 +201,7 @@ static int synth_device(LPCNetB200Batch *b, const float *d_feat, long long strea
             SampleParams p;
             p.L = b->model.L; p.image = b->model.image;
             p.emb_sig = b->model.emb_sig; p.emb_pred = b->model.emb_pred; p.emb_exc = b->model.emb_exc; p.fcw = b->model.fcw;
+            p.spc = streams_per_cta_for(n);
             p.fast_cvt = b->model.fast_cvt && !getenv("LPCNET_B200_EXACT_CVT");   // env: force the conversion-unit path (tests)
 #ifdef LPCNET_TRACE
             { static long long *d_trace = nullptr; if (!d_trace) { CK(cudaMalloc(&d_trace, 8 * 32 * 8)); CK(cudaMemset(d_trace, 0, 8 * 32 * 8)); } p.trace = d_trace; g_trace = d_trace; }

@@ -22,7 +22,7 @@ constexpr int WINDOW_SIZE = 320;
 constexpr int FREQ_SIZE = 161;
 
 // ---- per-sample kernel geometry (warp-specialised CTA) ----
-constexpr int STREAMS_PER_CTA = 32;          // lane == stream
+constexpr int STREAMS_PER_CTA = 32;          // stream slots of a CTA; the launcher may leave some dead (SampleParams::spc) to spread a small batch over all SMs
 #ifndef LPCNET_NWC
 #define LPCNET_NWC 16
 #endif
@@ -197,6 +197,7 @@ struct SampleParams {
     long long pcm_stream_stride;
     int n_streams, nframes, spf;
     int fast_cvt;
+    int spc;                 // live streams per CTA (1..32): chosen by the launcher so that the grid covers the SMs
 #ifdef LPCNET_TRACE
     long long *trace;        // tuning builds only: clock64 stamps of CTA 0, [8 samples][32 events]
 #endif
@@ -223,5 +224,6 @@ void launch_decode_packets(const DeviceModel &m, const FrameState &fs, const uin
 cudaError_t launch_sample_kernel(const SampleParams &p, cudaStream_t st);
 cudaError_t launch_sample_kernel_f32(const SampleParams &p, cudaStream_t st);
 int sample_kernel_smem_ok(uint32_t bytes);
+int streams_per_cta_for(int n_streams);   // min(32, ceil(n / SM count)) on the current device
 
 }  // namespace lpcnet_b200

@@ -36,6 +36,7 @@
 // by TMA bulk copies (cp.async.bulk + mbarrier).  Roles hand data over with mbarriers; the compute warps synchronise
 // among themselves with two named barriers.
 #include <cstdint>
+#include <cstdlib>
 #include "engine.h"
 #include "devmath.cuh"
 
@@ -180,12 +181,21 @@ struct QuadPipe {
     }
 };
 
+// Stream slots of a CTA: slot (half hh, row si) holds stream  cta_s0 + 2*si + hh  of the batch, live while 2*si + hh < spc
+// (the halves share a partially filled CTA evenly).  Dead slots shadow the batch's last stream: loads valid, stores masked.
+__device__ __forceinline__ int slot_stream(int cta_s0, int hh, int si, int spc, int n, bool &live)
+{
+    const int c = 2 * si + hh, g = cta_s0 + c;
+    live = c < spc && g < n;
+    return min(g, n - 1);
+}
+
 // Producer warps: ONE gate's input term for the 16 streams of a half,
 //   G[si][k] = ((cond[s][k] + E_sig[a_s][k]) + E_pred[b_s][k]) + E_exc[c_s][k]        (nnet.c:484-491, left to right)
 // Producer p serves tile rows si = p, p+NWP, ...: per stream the four row pointers are formed once and the 384 columns
 // of the gate are covered by three 512-byte LDG.128 per row (4 L1 lines per request), i.e. 12 independent loads in
 // flight per lane, then 12 fp32 adds and three 512-byte conflict-free STS.128 into the [16][392] tile.
-__device__ __forceinline__ void gather_half(float *__restrict__ G, const float *__restrict__ cond_f, int n, int s_half0,
+__device__ __forceinline__ void gather_half(float *__restrict__ G, const float *__restrict__ cond_f, int n, int cta_s0, int hh, int spc,
                                             const float *__restrict__ emb_sig, const float *__restrict__ emb_pred,
                                             const float *__restrict__ emb_exc, const int *__restrict__ idx_h,
                                             int gate, int p, int lane)
@@ -193,7 +203,9 @@ __device__ __forceinline__ void gather_half(float *__restrict__ G, const float *
     const int col = gate * NA + lane * 4;
 #pragma unroll 1
     for (int si = p; si < HALF; si += NWP) {
-        const int sg = min(s_half0 + si, n - 1);
+        bool live;
+        const int sg = slot_stream(cta_s0, hh, si, spc, n, live);
+        if (!live) continue;                                     // dead slot: its tile row is never used for anything that is stored
         const float *c = cond_f + (size_t)sg * (3 * NA) + col;
         const float *e0 = emb_sig + idx_h[si] * (3 * NA) + col;
         const float *e1 = emb_pred + idx_h[HALF + si] * (3 * NA) + col;
@@ -478,7 +490,8 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
     const SmemLayout &L = P.L;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = P.n_streams;
-    const int cta_s0 = blockIdx.x * STREAMS_PER_CTA;
+    const int spc = P.spc;
+    const int cta_s0 = blockIdx.x * spc;
     const int spf = P.spf;
 
     // ---- mbarriers; stage the constant image with TMA bulk copies ----
@@ -518,10 +531,10 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
         C.parB = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_PARB);
         C.wBrec = smem + SM_IMAGE + IM_WBREC;
         C.xs0 = smem_u32(smem + SM_XS);
-        // the streams of this lane: cta_s0 + 16*half + gid + 8*jj; dead streams shadow the last one, stores masked
+        // the stream slots of this lane: half j>>1, row gid + 8*(j&1)
         int sj[4]; bool livej[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) { const int r = cta_s0 + C.gid + 8 * j; livej[j] = r < n; sj[j] = livej[j] ? r : n - 1; }
+        for (int j = 0; j < 4; j++) sj[j] = slot_stream(cta_s0, j >> 1, C.gid + 8 * (j & 1), spc, n, livej[j]);
 
         float h[2][GPW][4];                                              // fp32 state: [half][group][stream jj][neuron i] at 2jj+i
 #pragma unroll
@@ -540,8 +553,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
         float hb[2];
 #pragma unroll
         for (int hh = 0; hh < 2; hh++) {
-            const int r = cta_s0 + HALF * hh + (lane & 15);
-            live_fin[hh] = r < n; s_fin[hh] = live_fin[hh] ? r : n - 1;
+            s_fin[hh] = slot_stream(cta_s0, hh, lane & 15, spc, n, live_fin[hh]);
             hb[hh] = P.hB[(size_t)jb_fin * n + s_fin[hh]];
         }
         // quantised copies of the restored state: xs buffer 0 <- q(hA), xb[half][0] <- q(hB)
@@ -612,7 +624,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
                     for (int gi = 0; gi < 3; gi++, k++) {
                         const int gate = gi == 0 ? 1 : (gi == 1 ? 0 : 2);    // fill order r, z, h
                         mbar_wait(mb_empty + 8 * (k & 3), ((k >> 2) & 1) ^ 1);  // previous contents of the tile consumed
-                        gather_half(reinterpret_cast<float *>(smem + SM_TILES + (k & 3) * TILE_BYTES), condA_f, n, cta_s0 + HALF * hh,
+                        gather_half(reinterpret_cast<float *>(smem + SM_TILES + (k & 3) * TILE_BYTES), condA_f, n, cta_s0, hh, spc,
                                     P.emb_sig, P.emb_pred, P.emb_exc, idx_s + hh * 3 * HALF, gate, p, lane);
                         warp_arrive(mb_full + 8 * (k & 3), lane);
                         TRACE(P, (int)it, 11 + 4 * hh + gi, p == 0 ? lane : 1);
@@ -626,9 +638,9 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
         // channel-1 lane issues no stores.
         mbar_wait(bar, 0);
         const int hh = warp - NWC - NWP, ch = lane >> 4, si = lane & 15;
-        const int s_raw = cta_s0 + HALF * hh + si;
-        const bool live = s_raw < n && ch == 0;
-        const int s = min(s_raw, n - 1);             // dead lanes shadow the last stream (all loads valid), stores masked
+        bool live;
+        const int s = slot_stream(cta_s0, hh, si, spc, n, live);
+        live = live && ch == 0;
         const float *logit = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_LOGIT);
         const float *u2l = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_U2L);
         const float *fcw = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_FCW) + ch * NB;
@@ -738,6 +750,17 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
     }
 }
 
+// Live streams per CTA: a batch smaller than 32 x SM count is spread over all SMs (one CTA per SM, fewer live slots each)
+// instead of filling a few SMs completely: the time of a CTA-step barely depends on how many of its slots are live.
+int streams_per_cta_for(int n_streams)
+{
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    int spc = (n_streams + sms - 1) / sms;
+    if (const char *e = getenv("LPCNET_B200_STREAMS_PER_CTA")) spc = atoi(e);
+    return spc < 1 ? 1 : spc > STREAMS_PER_CTA ? STREAMS_PER_CTA : spc;
+}
+
 int sample_kernel_smem_ok(uint32_t bytes)
 {
     return bytes <= 227u * 1024u;
@@ -749,7 +772,7 @@ cudaError_t launch_sample_kernel(const SampleParams &p, cudaStream_t st)
     auto kern = p.fast_cvt ? lpcnet_sample_kernel<true> : lpcnet_sample_kernel<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    const int ctas = (p.n_streams + STREAMS_PER_CTA - 1) / STREAMS_PER_CTA;
+    const int ctas = (p.n_streams + p.spc - 1) / p.spc;
     kern<<<ctas, SAMPLE_THREADS, p.L.total_bytes, st>>>(p);
     return cudaGetLastError();
 }

@@ -82,8 +82,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) lpcnet_sample_kernel_f32(const _
     const SmemLayout &L = P.L;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = P.n_streams;
-    const int s_raw = blockIdx.x * STREAMS_PER_CTA + lane;
-    const bool live = s_raw < n;
+    const int s_raw = blockIdx.x * P.spc + lane;                 // lanes >= spc are dead slots (shadow the last stream, stores masked)
+    const bool live = lane < P.spc && s_raw < n;
     const int s = live ? s_raw : n - 1;
 
     const uint32_t bar = smem_u32(smem + F_MBAR);
@@ -303,7 +303,7 @@ cudaError_t launch_sample_kernel_f32(const SampleParams &p, cudaStream_t st)
 {
     cudaError_t e = cudaFuncSetAttribute(lpcnet_sample_kernel_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    const int ctas = (p.n_streams + STREAMS_PER_CTA - 1) / STREAMS_PER_CTA;
+    const int ctas = (p.n_streams + p.spc - 1) / p.spc;
     lpcnet_sample_kernel_f32<<<ctas, F_THREADS, p.L.total_bytes, st>>>(p);
     return cudaGetLastError();
 }
