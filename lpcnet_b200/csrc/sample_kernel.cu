@@ -89,13 +89,21 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// one arrival per warp: the lanes' shared-memory accesses are ordered before it by the fence + warp barrier
+// one arrival per warp: the lanes' shared-memory accesses are ordered before it by the fence + warp barrier.
+// -DLPCNET_ARRIVE_ALL (checking builds): every lane arrives itself, so that compute-sanitizer's racecheck, which does not
+// chain a warp barrier with an mbarrier, can follow the hand-over.
+#ifdef LPCNET_ARRIVE_ALL
+constexpr int ARRIVALS_PER_WARP = 32;
+__device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) { (void)lane; mbar_arrive(bar); }
+#else
+constexpr int ARRIVALS_PER_WARP = 1;
 __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane)
 {
     __threadfence_block();
     __syncwarp();
     if (lane == 0) mbar_arrive(bar);
 }
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     asm volatile(
@@ -498,8 +506,8 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
     const uint32_t bar = smem_u32(smem + MB_IMAGE);
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
-        for (int b = 0; b < NTILE; b++) { mbar_init(smem_u32(smem + MB_FULL) + 8 * b, NWP); mbar_init(smem_u32(smem + MB_EMPTY) + 8 * b, NWC); }
-        for (int hh = 0; hh < 2; hh++) { mbar_init(smem_u32(smem + MB_IDX) + 8 * hh, 1); mbar_init(smem_u32(smem + MB_X) + 8 * hh, NWC); mbar_init(smem_u32(smem + MB_ACCB) + 8 * hh, NWB); }
+        for (int b = 0; b < NTILE; b++) { mbar_init(smem_u32(smem + MB_FULL) + 8 * b, NWP * ARRIVALS_PER_WARP); mbar_init(smem_u32(smem + MB_EMPTY) + 8 * b, NWC * ARRIVALS_PER_WARP); }
+        for (int hh = 0; hh < 2; hh++) { mbar_init(smem_u32(smem + MB_IDX) + 8 * hh, ARRIVALS_PER_WARP); mbar_init(smem_u32(smem + MB_X) + 8 * hh, NWC * ARRIVALS_PER_WARP); mbar_init(smem_u32(smem + MB_ACCB) + 8 * hh, NWB * ARRIVALS_PER_WARP); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
