@@ -9,6 +9,7 @@
 #include <cstring>
 #include <vector>
 #include "engine.h"
+#include "devmath.cuh"
 #include "../../include/lpcnet_b200.h"
 
 namespace lpcnet_b200 { const char *get_error(); }
@@ -420,6 +421,30 @@ int lpcnet_b200_debug_image(const unsigned char *blob, int len, unsigned char *o
     layout[9] = IM_PARA; layout[10] = IM_DIRA; layout[11] = IM_GRPA; layout[12] = IM_DIRB; layout[13] = IM_WBREC; layout[14] = IM_PARB;
     layout[15] = IM_FCW; layout[16] = NWC; layout[17] = GPW; layout[18] = FCW_SMEM_NODES; layout[19] = KPARTS;
     return r;
+}
+
+// Test hook: the two device implementations of the reference's _mm256_rcp_ps (table in memory / table-free arithmetic)
+// on n host floats.
+__global__ void debug_rcp_kernel(const float *x, float *out_table, float *out_arith, int n, const uint16_t *tab16)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out_table[i] = rcp_emul(x[i], tab16);
+    out_arith[i] = rcp_emul(x[i], RcpArith());
+}
+int lpcnet_b200_debug_rcp(LPCNetB200Batch *b, const float *x, float *out_table, float *out_arith, int n)
+{
+    if (!b || n <= 0) { set_error("debug_rcp: bad arguments"); return -1; }
+    CK(cudaSetDevice(b->device));
+    float *d = nullptr;
+    CK(cudaMalloc(&d, (size_t)3 * n * sizeof(float)));
+    CK(cudaMemcpy(d, x, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+    debug_rcp_kernel<<<(n + 255) / 256, 256, 0, b->stream>>>(d, d + n, d + 2 * n, n, b->model.rcp16);
+    CK(cudaStreamSynchronize(b->stream));
+    CK(cudaMemcpy(out_table, d + n, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out_arith, d + 2 * n, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return 0;
 }
 
 // Pinned host memory helpers for callers that want true async H2D/D2H (the benchmark's e2e leg).

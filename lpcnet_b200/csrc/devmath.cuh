@@ -37,6 +37,27 @@ __device__ __forceinline__ float rcp_emul(float x, RcpShared tab)
     return __uint_as_float(t - (u & 0x7F800000u));
 }
 
+// The same function WITHOUT a table (no shared-memory traffic: the look-up above costs ~3.4 bank-conflicted wavefronts
+// per warp, the binding unit of the per-sample kernel).  The table has the closed form T[k] = rint(2^25/d) * 2^-13 with
+// d = 2k + 4097 (tests/test_oracle.py): d is formed exactly as a float from the top 11 mantissa bits, MUFU.RCP gives
+// 2^25/d to within +-1 after rounding, and the EXACT residual q*d - 2^25 (an integer below 2^24, so one FMA computes
+// it without error) decides the +-1 correction; d is odd, so there are no ties.  Checked against the table for every
+// k, exponent and sign of the low bits by tests/test_gpu_parity.py::test_arithmetic_rcpps_matches_table.
+struct RcpArith {};
+__device__ __forceinline__ float rcp_emul(float x, RcpArith)
+{
+    const uint32_t u = __float_as_uint(x);
+    const float d = __uint_as_float((u & 0x007FF000u) | 0x45800800u);        // 4097 + 2k, exact
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(d));
+    float q = __fsub_rn(__fmaf_rn(y, 33554432.f, 12582912.f), 12582912.f);   // rint(y * 2^25)
+    const float e = __fmaf_rn(q, d, -33554432.f);                           // q*d - 2^25, exact
+    const float dh = __fmul_rn(d, 0.5f);
+    q = __fadd_rn(__fsub_rn(q, e > dh ? 1.f : 0.f), e < -dh ? 1.f : 0.f);
+    // T[k] + 0x3f800000 - exponent(x):  q in [4097, 8191] is 0x45800000 + ((q - 4096) << 11) as a float pattern
+    return __uint_as_float(__float_as_uint(q) + 0x39000000u - (u & 0x7F800000u));
+}
+
 // tanh8_approx (vec_avx.h:393-411)
 template <typename TAB>
 __device__ __forceinline__ float tanh_approx(float x, TAB tab16)

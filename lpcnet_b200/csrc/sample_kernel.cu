@@ -40,6 +40,9 @@
 #include "engine.h"
 #include "devmath.cuh"
 
+#ifndef LPCNET_RCP_ARITH
+#define LPCNET_RCP_ARITH 0     // 1: GRU_A activations use the table-free RCPPS of devmath.cuh (exact, but measured 5 % slower: 8 more instructions per look-up outweigh the saved wavefronts)
+#endif
 #ifndef LPCNET_GATHER_NOALLOC
 #define LPCNET_GATHER_NOALLOC 0
 #endif
@@ -279,7 +282,11 @@ __device__ __forceinline__ void activations(const ComputeCtx &C, float (&h)[GPW]
 {
     uint8_t *smem = C.smem;
     const int gid = C.gid, t = C.t, lane = C.lane, warp = C.warp;
+#if LPCNET_RCP_ARITH
+    const RcpArith rcp = RcpArith();
+#else
     const RcpShared rcp = C.rcp;
+#endif
     const int nxt = cur ^ 1;
     const uint32_t xs_cur = C.xs0 + cur * XS_BYTES, lc = C.gid8 | (H << 6);
     uint8_t *xs_nxt = smem + SM_XS + nxt * XS_BYTES;

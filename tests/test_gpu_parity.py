@@ -73,6 +73,28 @@ def test_conversion_unit_path_matches_golden_too(eng, monkeypatch):
     assert _first_diff(got, gold) is None
 
 
+def test_arithmetic_rcpps_matches_table(eng):
+    """The GRU_A activations use a table-free _mm256_rcp_ps emulation (devmath.cuh, RcpArith: MUFU.RCP + exact residual
+    correction).  It must equal the table (= the reference's RCPPS, tests/golden/rcpps_table.bin) for every one of the
+    2048 mantissa classes, at many exponents and for random low mantissa bits."""
+    rng = np.random.default_rng(5)
+    k = np.arange(2048, dtype=np.uint32)
+    xs = []
+    for e in list(range(100, 160)):                      # biased exponents 2^-27 .. 2^32
+        for low in (0, 0xFFF, None, None):
+            lo = rng.integers(0, 4096, 2048, dtype=np.uint32) if low is None else np.uint32(low)
+            xs.append(((np.uint32(e) << 23) | (k << 12) | lo).astype(np.uint32))
+    x = np.concatenate(xs).view(np.float32)
+    b = _batch(eng, 1)
+    tab, ari = b.debug_rcp(x)
+    b.close()
+    ref = H.rcp_table().astype(np.uint32)                # T[k]: rcp(2^e * 1.m) bits = T[m >> 12] - (e << 23)
+    u = x.view(np.uint32)
+    want = (ref[(u >> 12) & 0x7FF] - ((u & np.uint32(0x7F800000)) - np.uint32(0x3F800000))).astype(np.uint32)
+    np.testing.assert_array_equal(tab.view(np.uint32), want)
+    np.testing.assert_array_equal(ari.view(np.uint32), want)
+
+
 def test_synthesis_matches_oracle_ragged_batch(eng):
     """70 streams (two full CTAs + a 6-lane tail), 36-float feature stride, distinct features per stream."""
     n, T = 70, 10
