@@ -28,3 +28,5 @@ d=json.loads(open("gpurun_out/bench_${W}_${TAG}.json").read().strip().splitlines
 print("$W", {k:d[k] for k in ("value","ms_per_step")}, "e2e", d["e2e"]["value"], d["config"]["workload"][:60])
 PY
 done
+# throughput vs batch size (device-resident, kernel-only and wall): the grid follows the SM count
+timeout 600 python tools/probe_bench.py 14 256 1024 4096 4736 9472 2>&1 | tail -6 | tee gpurun_out/probe_${TAG}.txt
