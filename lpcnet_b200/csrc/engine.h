@@ -198,6 +198,8 @@ struct SampleParams {
     int n_streams, nframes, spf;
     int fast_cvt;
     int spc;                 // live streams per CTA (1..32): chosen by the launcher so that the grid covers the SMs
+    int one_half;            // spc <= 16: all live streams sit in half A and half B is not stepped at all (a small batch is bound by the
+                             // latency of one sample, which the second half would only lengthen)
 #ifdef LPCNET_TRACE
     long long *trace;        // tuning builds only: clock64 stamps of CTA 0, [8 samples][32 events]
 #endif

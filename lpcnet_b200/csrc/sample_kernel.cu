@@ -193,9 +193,16 @@ struct QuadPipe {
 };
 
 // Stream slots of a CTA: slot (half hh, row si) holds stream  cta_s0 + 2*si + hh  of the batch, live while 2*si + hh < spc
-// (the halves share a partially filled CTA evenly).  Dead slots shadow the batch's last stream: loads valid, stores masked.
+// (the halves share a partially filled CTA evenly); in the half-A-only schedule (ONE, spc <= 16) slot (0, si) holds stream
+// cta_s0 + si and half B is dead.  Dead slots shadow the batch's last stream: loads valid, stores masked.
+template <bool ONE>
 __device__ __forceinline__ int slot_stream(int cta_s0, int hh, int si, int spc, int n, bool &live)
 {
+    if (ONE) {
+        const int g = cta_s0 + si;
+        live = hh == 0 && si < spc && g < n;
+        return min(g, n - 1);
+    }
     const int c = 2 * si + hh, g = cta_s0 + c;
     live = c < spc && g < n;
     return min(g, n - 1);
@@ -206,6 +213,7 @@ __device__ __forceinline__ int slot_stream(int cta_s0, int hh, int si, int spc, 
 // Producer p serves tile rows si = p, p+NWP, ...: per stream the four row pointers are formed once and the 384 columns
 // of the gate are covered by three 512-byte LDG.128 per row (4 L1 lines per request), i.e. 12 independent loads in
 // flight per lane, then 12 fp32 adds and three 512-byte conflict-free STS.128 into the [16][392] tile.
+template <bool ONE>
 __device__ __forceinline__ void gather_half(float *__restrict__ G, const float *__restrict__ cond_f, int n, int cta_s0, int hh, int spc,
                                             const float *__restrict__ emb_sig, const float *__restrict__ emb_pred,
                                             const float *__restrict__ emb_exc, const int *__restrict__ idx_h,
@@ -215,7 +223,7 @@ __device__ __forceinline__ void gather_half(float *__restrict__ G, const float *
 #pragma unroll 1
     for (int si = p; si < HALF; si += NWP) {
         bool live;
-        const int sg = slot_stream(cta_s0, hh, si, spc, n, live);
+        const int sg = slot_stream<ONE>(cta_s0, hh, si, spc, n, live);
         if (!live) continue;                                     // dead slot: its tile row is never used for anything that is stored
         const float *c = cond_f + (size_t)sg * (3 * NA) + col;
         const float *e0 = emb_sig + idx_h[si] * (3 * NA) + col;
@@ -498,13 +506,14 @@ __device__ __forceinline__ void grub(const ComputeCtx &C, const SampleParams &P,
 
 }  // namespace
 
-template <bool FAST>
+template <bool FAST, bool ONE>
 __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const __grid_constant__ SampleParams P)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const SmemLayout &L = P.L;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = P.n_streams;
+    constexpr bool one = ONE;                                     // spc <= 16: half-A-only schedule (SampleParams::one_half)
     const int spc = P.spc;
     const int cta_s0 = blockIdx.x * spc;
     const int spf = P.spf;
@@ -549,7 +558,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
         // the stream slots of this lane: half j>>1, row gid + 8*(j&1)
         int sj[4]; bool livej[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) sj[j] = slot_stream(cta_s0, j >> 1, C.gid + 8 * (j & 1), spc, n, livej[j]);
+        for (int j = 0; j < 4; j++) sj[j] = slot_stream<ONE>(cta_s0, j >> 1, C.gid + 8 * (j & 1), spc, n, livej[j]);
 
         float h[2][GPW][4];                                              // fp32 state: [half][group][stream jj][neuron i] at 2jj+i
 #pragma unroll
@@ -568,7 +577,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
         float hb[2];
 #pragma unroll
         for (int hh = 0; hh < 2; hh++) {
-            s_fin[hh] = slot_stream(cta_s0, hh, lane & 15, spc, n, live_fin[hh]);
+            s_fin[hh] = slot_stream<ONE>(cta_s0, hh, lane & 15, spc, n, live_fin[hh]);
             hb[hh] = P.hB[(size_t)jb_fin * n + s_fin[hh]];
         }
         // quantised copies of the restored state: xs buffer 0 <- q(hA), xb[half][0] <- q(hB)
@@ -586,6 +595,16 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
         bar_sync(BAR_X, CNT_C);                                          // restored quantised state visible to all compute warps
 
         uint32_t k = 0; int step = 0, f_prev = 0;
+        if constexpr (ONE) {
+            // small batch: half A alone, strictly in program order (nothing to overlap with)
+            for (int f = 0; f < P.nframes; f++)
+                for (int t_ = 0; t_ < spf; t_++, step++, k += 3) {
+                    int Sh[GPW][4], Sg[GPW][4];
+                    gemv_rh<0>(C, Sh, Sg, step & 1);
+                    activations<0, FAST>(C, h[0], Sh, Sg, k, step & 1);
+                    grub<0, FAST>(C, P, hb[0], k, step & 1, f, s_fin[0], step & 1, step);
+                }
+        } else {
         for (int f = 0; f < P.nframes; f++)
             for (int t_ = 0; t_ < spf; t_++, step++, k += 6) {
                 int Sh[GPW][4], Sg[GPW][4];                              // candidate-gate sums (later rec_h * r) / r-gate, then z-gate sums (later z)
@@ -610,6 +629,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
                 f_prev = f;
             }
         if (step > 0) grub<1, FAST>(C, P, hb[1], k - 3, (step - 1) & 1, f_prev, s_fin[1], (step - 1) & 1);
+        }
         // ---- save the recurrent state ----
 #pragma unroll
         for (int sl = 0; sl < GPW; sl++)
@@ -632,14 +652,14 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
             const float *condA_f = P.condA + (size_t)f * n * (3 * NA);
             for (int t_ = 0; t_ < spf; t_++, it++)
 #pragma unroll 1
-                for (int hh = 0; hh < 2; hh++) {
+                for (int hh = 0; hh < (one ? 1 : 2); hh++) {
                     mbar_wait(mb_idx + 8 * hh, it & 1);                  // indices of this sample of the half are in idx_s
                     TRACE(P, (int)it, 10 + 4 * hh, p == 0 ? lane : 1);
 #pragma unroll 1
                     for (int gi = 0; gi < 3; gi++, k++) {
                         const int gate = gi == 0 ? 1 : (gi == 1 ? 0 : 2);    // fill order r, z, h
                         mbar_wait(mb_empty + 8 * (k & 3), ((k >> 2) & 1) ^ 1);  // previous contents of the tile consumed
-                        gather_half(reinterpret_cast<float *>(smem + SM_TILES + (k & 3) * TILE_BYTES), condA_f, n, cta_s0, hh, spc,
+                        gather_half<ONE>(reinterpret_cast<float *>(smem + SM_TILES + (k & 3) * TILE_BYTES), condA_f, n, cta_s0, hh, spc,
                                     P.emb_sig, P.emb_pred, P.emb_exc, idx_s + hh * 3 * HALF, gate, p, lane);
                         warp_arrive(mb_full + 8 * (k & 3), lane);
                         TRACE(P, (int)it, 11 + 4 * hh + gi, p == 0 ? lane : 1);
@@ -653,8 +673,9 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
         // channel-1 lane issues no stores.
         mbar_wait(bar, 0);
         const int hh = warp - NWC - NWP, ch = lane >> 4, si = lane & 15;
+        if (one && hh) return;                                           // small batch: half B is not stepped
         bool live;
-        const int s = slot_stream(cta_s0, hh, si, spc, n, live);
+        const int s = slot_stream<ONE>(cta_s0, hh, si, spc, n, live);
         live = live && ch == 0;
         const float *logit = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_LOGIT);
         const float *u2l = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_U2L);
@@ -696,7 +717,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
         publish();
         uint32_t k = 0;
         for (int f = 0; f < P.nframes; f++) {
-            for (int t_ = 0; t_ < spf; t_++, k += 6) {
+            for (int t_ = 0; t_ < spf; t_++, k += one ? 3 : 6) {
                 const bool last_t = t_ == spf - 1, last = last_t && f == P.nframes - 1;
                 // thresholds (nnet.c:178-184): two RNG words -> 8 logits; does not depend on the network
                 float thr[8];
@@ -769,6 +790,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
 // instead of filling a few SMs completely: the time of a CTA-step barely depends on how many of its slots are live.
 int streams_per_cta_for(int n_streams)
 {
+    // (spc <= 16 additionally selects the half-A-only schedule, launch_sample_kernel)
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
     int spc = (n_streams + sms - 1) / sms;
@@ -784,11 +806,15 @@ int sample_kernel_smem_ok(uint32_t bytes)
 cudaError_t launch_sample_kernel(const SampleParams &p, cudaStream_t st)
 {
     // per-device attribute; cheap enough to set on every launch (one launch covers >= 160 x n_streams samples)
-    auto kern = p.fast_cvt ? lpcnet_sample_kernel<true> : lpcnet_sample_kernel<false>;
+    const bool one = p.spc <= HALF && !getenv("LPCNET_B200_TWO_HALVES");
+    auto kern = p.fast_cvt ? (one ? lpcnet_sample_kernel<true, true> : lpcnet_sample_kernel<true, false>)
+                           : (one ? lpcnet_sample_kernel<false, true> : lpcnet_sample_kernel<false, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     const int ctas = (p.n_streams + p.spc - 1) / p.spc;
-    kern<<<ctas, SAMPLE_THREADS, p.L.total_bytes, st>>>(p);
+    SampleParams q = p;
+    q.one_half = one;
+    kern<<<ctas, SAMPLE_THREADS, q.L.total_bytes, st>>>(q);
     return cudaGetLastError();
 }
 

@@ -95,6 +95,21 @@ def test_arithmetic_rcpps_matches_table(eng):
     np.testing.assert_array_equal(ari.view(np.uint32), want)
 
 
+@pytest.mark.parametrize("spc,two", [("32", "0"), ("5", "1"), ("16", "0"), ("17", "0")])
+def test_grid_shapes_do_not_change_results(eng, monkeypatch, spc, two):
+    """The launcher spreads a batch over the SMs (live stream slots per CTA) and steps small batches with one half only;
+    every shape must give the same PCM: full 32-slot CTAs + a ragged one, dead slots in both halves of the two-half
+    schedule, the largest one-half CTA and the smallest two-half CTA."""
+    n, T = 70, 7
+    f = make_feature_batch(range(200, 200 + n), T)
+    b = _batch(eng, n); want = b.synthesize(f); b.close()
+    monkeypatch.setenv("LPCNET_B200_STREAMS_PER_CTA", spc)
+    if two == "1":
+        monkeypatch.setenv("LPCNET_B200_TWO_HALVES", "1")
+    b = _batch(eng, n); got = b.synthesize(f); b.close()
+    assert _first_diff(got, want) is None
+
+
 def test_synthesis_matches_oracle_ragged_batch(eng):
     """70 streams (two full CTAs + a 6-lane tail), 36-float feature stride, distinct features per stream."""
     n, T = 70, 10
