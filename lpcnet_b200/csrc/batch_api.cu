@@ -219,7 +219,11 @@ static int synth_device(LPCNetB200Batch *b, const float *d_feat, long long strea
                 while ((int)b->kev->size() < b->kev_used + 2) { cudaEvent_t e; CK(cudaEventCreate(&e)); b->kev->push_back(e); }
                 CK(cudaEventRecord((*b->kev)[b->kev_used], st));
             }
-            CK(b->model.is_float ? launch_sample_kernel_f32(p, st) : launch_sample_kernel(p, st));
+            if (b->model.is_float && p.spc <= FN_S && !getenv("LPCNET_B200_FLOAT_LANE_STREAM")) {
+                p.L = b->model.Ln; p.image = b->model.image_n;       // small batch: neuron-per-lane float kernel
+                CK(launch_sample_kernel_f32n(p, st));
+            } else
+                CK(b->model.is_float ? launch_sample_kernel_f32(p, st) : launch_sample_kernel(p, st));
             launches += 1;
             if (time_it) { CK(cudaEventRecord((*b->kev)[b->kev_used + 1], st)); b->kev_used += 2; }
         }

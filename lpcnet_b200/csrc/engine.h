@@ -133,6 +133,32 @@ constexpr uint32_t FI_DIRB  = FI_GRPA + F_NWC * F_GPW * 4;         // uint32 [6*
 constexpr uint32_t FI_PARB  = FI_DIRB + F_NWB * 2 * 4;               // float [96]: input-side bias[48], recurrent-side bias[48]
 constexpr uint32_t FI_VAR   = al128(FI_PARB + 6 * NB * 4);
 
+// ---- FLOAT flavour, small batches: neuron-per-lane kernel (sample_kernel_f32n.cu) ----
+// With only a few streams per SM the lane==stream mapping leaves the lanes idle and every lane walks all chains of its
+// warp's neurons.  Here a compute lane owns ONE GRU_A neuron (its z, r and h rows: three sequential fp32 FMA chains in the
+// reference's block order) for up to FN_S streams of the CTA; the latency of a sample is then set by the longest chain
+// (the 384-term rows of GRU_B), not by the work of a whole warp.
+constexpr int FN_S = 4;                                             // streams per CTA (live slots: SampleParams::spc <= FN_S)
+constexpr int FN_NWC = NA / 32;                                     // 12 compute warps: 384 lanes = 384 neurons
+constexpr int FN_THREADS = (FN_NWC + 1) * 32;                       // + sampler warp (lane == stream)
+constexpr uint32_t FN_X     = 0;                                    // float [2][FN_S][NA]: GRU_A state (double-buffered)
+constexpr uint32_t FN_HB    = FN_X + 2 * FN_S * NA * 4;             // float [2][NB][FN_S]: GRU_B state (double-buffered)
+constexpr uint32_t FN_ACCB  = FN_HB + 2 * NB * FN_S * 4;            // float [48][FN_S]: GRU_B input-side pre-activations
+constexpr uint32_t FN_IDX   = FN_ACCB + 3 * NB * FN_S * 4;          // int32 [3][FN_S]
+constexpr uint32_t FN_MBAR  = al128(FN_IDX + 3 * FN_S * 4);
+constexpr uint32_t FN_IMAGE = FN_MBAR + 128;
+constexpr uint32_t FNI_RCP   = 0;                                   // u16 [2048]
+constexpr uint32_t FNI_LOGIT = FNI_RCP + 2048 * 2;
+constexpr uint32_t FNI_U2L   = FNI_LOGIT + 256 * 4;
+constexpr uint32_t FNI_FCW   = FNI_U2L + 256 * 4;                   // float [256][FCW_ROW]: all dual_fc rows (weights, biases, factors)
+constexpr uint32_t FNI_NEUR  = FNI_FCW + 256 * FCW_ROW * 4;                   // u16 [384]: neuron of compute lane (warp*32 + lane); groups sorted by list length
+constexpr uint32_t FNI_DIRA  = FNI_NEUR + NA * 2;                   // u32 [48 groups][3 gates][2] = {first block, block count}
+constexpr uint32_t FNI_PARA  = FNI_DIRA + NGRP * 3 * 2 * 4;         // float [3 gates][2][384]: recurrent bias, diag per neuron
+constexpr uint32_t FNI_DIRB  = FNI_PARA + 3 * 2 * NA * 4;           // u32 [6][2]
+constexpr uint32_t FNI_PARB  = FNI_DIRB + 64;                       // float [96]
+constexpr uint32_t FNI_WBREC = FNI_PARB + 6 * NB * 4;               // float [16 in][48 out]
+constexpr uint32_t FNI_VAR   = al128(FNI_WBREC + 3 * NB * NB * 4);  // blocks: fp16 [8 rows][4 cols] (64 B), u16 meta = 4 * pos
+
 // offsets used by the (flavour-agnostic) image builder
 struct ImageMap { uint32_t sm_image, rcp, logit, u2l, fcw, fcb, fcf, parA, dirA, grpA, dirB, wBrec, parB, var; };
 constexpr ImageMap MAP_INT8 = {SM_IMAGE, IM_RCP, IM_LOGIT, IM_U2L, IM_FCW, 0xFFFFFFFFu, 0xFFFFFFFFu, IM_PARA, IM_DIRA, IM_GRPA, IM_DIRB, IM_WBREC, IM_PARB, IM_VAR};
@@ -157,6 +183,8 @@ struct DeviceModel {
     float lpc_gamma;
     SmemLayout L;
     uint8_t *image;                  // [L.image_bytes] global copy of the SMEM image
+    SmemLayout Ln;                   // float flavour: layout / image of the neuron-per-lane kernel (small batches)
+    uint8_t *image_n;
     // per-sample gathers (L2-resident): [256][3*NA] each
     float *emb_sig, *emb_pred, *emb_exc;
     float *fcw;                      // dual_fc rows [256][FCW_ROW] = 32 weights, 2 biases, 2 factors (the lower tree levels are read from here)
@@ -225,6 +253,7 @@ void launch_decode_packets(const DeviceModel &m, const FrameState &fs, const uin
                            float *d_features /* [n][4*npackets][20] */, cudaStream_t st);
 cudaError_t launch_sample_kernel(const SampleParams &p, cudaStream_t st);
 cudaError_t launch_sample_kernel_f32(const SampleParams &p, cudaStream_t st);
+cudaError_t launch_sample_kernel_f32n(const SampleParams &p, cudaStream_t st);   // p.L / p.image = DeviceModel::Ln / image_n, p.spc <= FN_S
 int sample_kernel_smem_ok(uint32_t bytes);
 int streams_per_cta_for(int n_streams);   // min(32, ceil(n / SM count)) on the current device
 

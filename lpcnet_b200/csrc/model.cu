@@ -98,6 +98,7 @@ uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
 struct HostModel {               // everything model_load needs after parsing, before any CUDA call
     std::vector<uint8_t> img;
+    std::vector<uint8_t> img_n;  // float flavour: image of the neuron-per-lane kernel
     std::vector<float> fc_rows;  // [256][FCW_ROW]
     const float *embed_pitch, *conv1_w, *conv1_b, *conv2_w, *conv2_b, *dense1_w, *dense1_b, *dense2_w, *dense2_b;
     const float *gad_w, *gad_b, *gbd_w, *gbd_b, *emb_sig, *emb_pred, *emb_exc;
@@ -362,6 +363,65 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
         const double bound = (bmax + dmax + cmax + 3 * emax) * 1.01 * (128.0 * 127.0) + 255.0 * smax + 2;
         m->fast_cvt = bound < 4194304.0 * 0.99;
     }
+    // ---------------- float flavour: second image for the neuron-per-lane kernel (small batches) ----------------
+    if (is_float) {
+        SmemLayout &Ln = m->Ln;
+        memset(&Ln, 0, sizeof(Ln));
+        uint32_t o = FN_IMAGE + FNI_VAR;
+        auto takeN = [&](uint32_t bytes, uint32_t align) { o = align_up(o, align); uint32_t r = o; o += bytes; return r; };
+        Ln.wA = takeN((uint32_t)(nblkA + 1) * 64, 128);          // (+1 block / +8 meta entries of slack: the pipelined chains read ahead)
+        Ln.metaA = takeN((uint32_t)(nblkA + 8) * 2, 16);
+        Ln.wB = takeN((uint32_t)(nblkB + 1) * 64, 128);
+        Ln.metaB = takeN((uint32_t)(nblkB + 8) * 2, 16);
+        Ln.total_bytes = align_up(o, 128);
+        Ln.sm_image = FN_IMAGE;
+        Ln.image_bytes = Ln.total_bytes - FN_IMAGE;
+        Ln.nblkA_padded = (uint32_t)nblkA; Ln.nblkB_padded = (uint32_t)nblkB;
+        if (!sample_kernel_smem_ok(Ln.total_bytes)) { set_error("model: %u bytes of shared memory needed by the small-batch float kernel", Ln.total_bytes); return -1; }
+        std::vector<uint8_t> &im = hm.img_n;
+        im.assign(Ln.image_bytes, 0);
+        memcpy(&im[FNI_RCP], kRcpTable, sizeof(kRcpTable));
+        memcpy(&im[FNI_LOGIT], &img[M.logit], 256 * 4);
+        memcpy(&im[FNI_U2L], &img[M.u2l], 256 * 4);
+        memcpy(&im[FNI_FCW], hm.fc_rows.data(), (size_t)256 * FCW_ROW * 4);
+        // lanes: groups sorted by the length of their longest (candidate-gate) list so that the four groups sharing a warp are alike
+        std::vector<int> ord(NGRP);
+        std::iota(ord.begin(), ord.end(), 0);
+        std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return rowsA[2 * NGRP + a].size() > rowsA[2 * NGRP + b].size(); });
+        uint16_t *neur = reinterpret_cast<uint16_t *>(&im[FNI_NEUR]);
+        for (int l = 0; l < NA; l++) neur[l] = (uint16_t)(8 * ord[l / 8] + (l & 7));
+        // blocks: [8 rows][4 cols] fp16 (the blob holds [4 cols][8 rows] fp32), lists in blob order (gate, group), idx order inside
+        auto put_t = [](uint8_t *dst, const unsigned char *src) {
+            const float *f = reinterpret_cast<const float *>(src);
+            __half *h = reinterpret_cast<__half *>(dst);
+            for (int r = 0; r < 8; r++) for (int c = 0; c < 4; c++) h[r * 4 + c] = __float2half_rn(f[c * 8 + r]);
+        };
+        uint32_t *dA = reinterpret_cast<uint32_t *>(&im[FNI_DIRA]);
+        uint16_t *mA = reinterpret_cast<uint16_t *>(&im[Ln.metaA - FN_IMAGE]);
+        uint32_t bk = 0;
+        for (int g = 0; g < NGRP; g++) for (int q = 0; q < 3; q++) {
+            const auto &lst = rowsA[q * NGRP + g];
+            dA[(g * 3 + q) * 2 + 0] = bk; dA[(g * 3 + q) * 2 + 1] = (uint32_t)lst.size();
+            for (size_t j = 0; j < lst.size(); j++) { put_t(&im[Ln.wA - FN_IMAGE + (size_t)(bk + j) * 64], lst[j].w); mA[bk + j] = (uint16_t)(lst[j].pos * 4); }
+            bk += (uint32_t)lst.size();
+        }
+        float *pa = reinterpret_cast<float *>(&im[FNI_PARA]);
+        for (int q = 0; q < 3; q++) for (int j = 0; j < NA; j++) {
+            pa[(q * 2 + 0) * NA + j] = ga_bias[3 * NA + q * NA + j];            // recurrent bias (nnet.c:425-430)
+            pa[(q * 2 + 1) * NA + j] = ga_diag[q * NA + j];
+        }
+        uint32_t *dB = reinterpret_cast<uint32_t *>(&im[FNI_DIRB]);
+        uint16_t *mB = reinterpret_cast<uint16_t *>(&im[Ln.metaB - FN_IMAGE]);
+        bk = 0;
+        for (int rg = 0; rg < 6; rg++) {
+            const auto &lst = rowsB[rg];
+            dB[rg * 2 + 0] = bk; dB[rg * 2 + 1] = (uint32_t)lst.size();
+            for (size_t j = 0; j < lst.size(); j++) { put_t(&im[Ln.wB - FN_IMAGE + (size_t)(bk + j) * 64], lst[j].w); mB[bk + j] = (uint16_t)(lst[j].pos * 4); }
+            bk += (uint32_t)lst.size();
+        }
+        memcpy(&im[FNI_PARB], gb_bias, 6 * NB * 4);
+        memcpy(&im[FNI_WBREC], wBrec->data, 3 * NB * NB * 4);
+    }
     hm.embed_pitch = embed_pitch; hm.conv1_w = conv1_w; hm.conv1_b = conv1_b; hm.conv2_w = conv2_w; hm.conv2_b = conv2_b;
     hm.dense1_w = dense1_w; hm.dense1_b = dense1_b; hm.dense2_w = dense2_w; hm.dense2_b = dense2_b;
     hm.gad_w = gad_w; hm.gad_b = gad_b; hm.gbd_w = gbd_w; hm.gbd_b = gbd_b;
@@ -402,6 +462,7 @@ int model_load(DeviceModel *m, const unsigned char *blob, int len, float lpc_gam
     bool ok = true;
 #define UP(field, src, count) ok = ok && ((m->field = to_device(src, (size_t)(count))) != nullptr);
     UP(image, img.data(), img.size())
+    if (m->is_float) { UP(image_n, hm.img_n.data(), hm.img_n.size()) }
     UP(emb_sig, emb_sig, 256 * 3 * NA) UP(emb_pred, emb_pred, 256 * 3 * NA) UP(emb_exc, emb_exc, 256 * 3 * NA)
     UP(fcw, hm.fc_rows.data(), hm.fc_rows.size())
     UP(embed_pitch, embed_pitch, 256 * PITCH_EMBED)
@@ -449,7 +510,7 @@ int model_load(DeviceModel *m, const unsigned char *blob, int len, float lpc_gam
 
 void model_free(DeviceModel *m)
 {
-    void *ptrs[] = {m->image, m->fcw, m->emb_sig, m->emb_pred, m->emb_exc, m->embed_pitch, m->conv1_w, m->conv1_b, m->conv2_w, m->conv2_b,
+    void *ptrs[] = {m->image, m->image_n, m->fcw, m->emb_sig, m->emb_pred, m->emb_exc, m->embed_pitch, m->conv1_w, m->conv1_b, m->conv2_w, m->conv2_b,
                     m->dense1_w, m->dense1_b, m->dense2_w, m->dense2_b, m->gad_w, m->gad_b, m->gbd_w, m->gbd_b, m->rcp16, m->dct,
                     m->twiddles, m->bitrev, m->gamma_pow, m->pitch_pow, m->codebooks};
     for (void *p : ptrs) if (p) cudaFree(p);

@@ -294,6 +294,21 @@ def test_device_pointer_api_matches_host_api(eng):
     b1.close(); b2.close()
 
 
+@pytest.mark.parametrize("spc", ["1", "2", "3", "32"])
+def test_float_flavour_kernels_agree_with_oracle(eng, monkeypatch, spc):
+    """Float flavour: the neuron-per-lane kernel (1, 2 or 4 stream slots per CTA, incl. a ragged last CTA) and the
+    lane==stream kernel (32 slots) against the float oracle on 7 fresh streams."""
+    monkeypatch.setenv("LPCNET_B200_STREAMS_PER_CTA", spc)
+    n = 7
+    f = make_feature_batch(range(300, 300 + n), 6)
+    b = eng.Batch(n, H.blob("float"), lpc_gamma=H.LPC_GAMMA)
+    got = b.synthesize(f[:, :4])
+    got2 = b.synthesize(f[:, 4:])                       # second call: state carried through the kernel's save/restore
+    b.close()
+    want = H.oracle_synth(f, kind="float")
+    assert _first_diff(np.concatenate([got, got2], axis=1), want) is None
+
+
 def test_float_flavour_matches_reference_golden(eng):
     """BASELINE config 2 arithmetic: the DISABLE_DOT_PROD (float) model flavour with fp16-stored recurrent weights must
     reproduce the reference's float build (pinned oracle build B) bit for bit — order-sensitive FMA chains included."""
