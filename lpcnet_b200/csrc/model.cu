@@ -369,9 +369,9 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
         memset(&Ln, 0, sizeof(Ln));
         uint32_t o = FN_IMAGE + FNI_VAR;
         auto takeN = [&](uint32_t bytes, uint32_t align) { o = align_up(o, align); uint32_t r = o; o += bytes; return r; };
-        Ln.wA = takeN((uint32_t)(nblkA + 1) * 64, 128);          // (+1 block / +8 meta entries of slack: the pipelined chains read ahead)
+        Ln.wA = takeN((uint32_t)(nblkA + 4) * 64, 128);          // (+4 blocks / +8 meta entries of slack: the pipelined chains read ahead)
         Ln.metaA = takeN((uint32_t)(nblkA + 8) * 2, 16);
-        Ln.wB = takeN((uint32_t)(nblkB + 1) * 64, 128);
+        Ln.wB = takeN((uint32_t)(nblkB + 4) * 64, 128);
         Ln.metaB = takeN((uint32_t)(nblkB + 8) * 2, 16);
         Ln.total_bytes = align_up(o, 128);
         Ln.sm_image = FN_IMAGE;

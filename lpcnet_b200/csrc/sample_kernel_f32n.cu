@@ -43,26 +43,30 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 // Blocks go in pairs through a software pipeline: while pair p is multiplied, the operands of pair p+1 and the meta entries
 // of pair p+2 are in flight (lanes past the end of their list re-read its last block; those values are never used).
 template <int S> struct BlkOps { uint2 w; float4 xv[S]; };
+// the four FMAs of one block; `take` = the block belongs to this lane's list (a select, not a branch: a branch per block
+// would fence the loads of the software pipeline)
 template <int S>
-__device__ __forceinline__ void fma_block(float (&y)[FN_S], const BlkOps<S> &o)
+__device__ __forceinline__ void fma_block(float (&y)[FN_S], const BlkOps<S> &o, bool take)
 {
     const float2 w01 = __half22float2(*reinterpret_cast<const __half2 *>(&o.w.x)), w23 = __half22float2(*reinterpret_cast<const __half2 *>(&o.w.y));
 #pragma unroll
     for (int s = 0; s < S; s++) {
-        y[s] = __fmaf_rn(w01.x, o.xv[s].x, y[s]);
-        y[s] = __fmaf_rn(w01.y, o.xv[s].y, y[s]);
-        y[s] = __fmaf_rn(w23.x, o.xv[s].z, y[s]);
-        y[s] = __fmaf_rn(w23.y, o.xv[s].w, y[s]);
+        float v = __fmaf_rn(w01.x, o.xv[s].x, y[s]);
+        v = __fmaf_rn(w01.y, o.xv[s].y, v);
+        v = __fmaf_rn(w23.x, o.xv[s].z, v);
+        v = __fmaf_rn(w23.y, o.xv[s].w, v);
+        y[s] = take ? v : y[s];
     }
 }
-template <int S>
+// UNIFORM: every lane of the warp has the same list length (GRU_B: dense rows), no clamping, no select
+template <int S, bool UNIFORM>
 __device__ __forceinline__ void chain(float (&y)[FN_S], const uint8_t *__restrict__ w, const uint16_t *__restrict__ meta, int nb, int nbmax,
                                       const uint8_t *__restrict__ x /* state buffer, stream 0 */)
 {
     const int last = max(nb - 1, 0);
-    auto ldm = [&](int b) { return (uint32_t)meta[min(b, last)]; };
+    auto ldm = [&](int b) { return (uint32_t)meta[UNIFORM ? b : min(b, last)]; };
     auto ldb = [&](int b, uint32_t m, BlkOps<S> &o) {
-        o.w = *reinterpret_cast<const uint2 *>(w + (size_t)min(b, last) * 64);
+        o.w = *reinterpret_cast<const uint2 *>(w + (size_t)(UNIFORM ? b : min(b, last)) * 64);
 #pragma unroll
         for (int s = 0; s < S; s++) o.xv[s] = *reinterpret_cast<const float4 *>(x + m + s * NA * 4);
     };
@@ -74,8 +78,8 @@ __device__ __forceinline__ void chain(float (&y)[FN_S], const uint8_t *__restric
         BlkOps<S> B0, B1;
         ldb(b + 2, m2, B0); ldb(b + 3, m3, B1);
         m2 = ldm(b + 4); m3 = ldm(b + 5);
-        if (b < nb) fma_block<S>(y, A0);
-        if (b + 1 < nb) fma_block<S>(y, A1);
+        fma_block<S>(y, A0, b < nb);
+        fma_block<S>(y, A1, b + 1 < nb);
         A0 = B0; A1 = B1;
     }
 }
@@ -121,7 +125,7 @@ __device__ __forceinline__ void run(const SampleParams &P, uint8_t *smem)
         const int fz = (int)dirA[0], nz = (int)dirA[1], fr = (int)dirA[2], nr = (int)dirA[3], fh = (int)dirA[4], nh = (int)dirA[5];
         const int mz = __reduce_max_sync(0xffffffffu, nz), mr = __reduce_max_sync(0xffffffffu, nr), mh = __reduce_max_sync(0xffffffffu, nh);
         // GRU_B input rows: lanes 0..47 of the compute warps 0,1
-        const int rowB = cl < 3 * NB ? cl : 0;
+        const int rowB = cl % (3 * NB);                               // (lanes 48..63 of warp 1 repeat rows 0..15: same list length for the whole warp; not stored)
         const uint32_t *dirB = reinterpret_cast<const uint32_t *>(smem + FN_IMAGE + FNI_DIRB) + (rowB >> 3) * 2;
         const uint8_t *wB = smem + L.wB + (rowB & 7) * 8;
         const uint16_t *metaB = reinterpret_cast<const uint16_t *>(smem + L.metaB);
@@ -164,19 +168,19 @@ __device__ __forceinline__ void run(const SampleParams &P, uint8_t *smem)
                 // reset gate (nnet.c:431-435): chain starts from bias + diag*h + gin
 #pragma unroll
                 for (int s = 0; s < S; s++) y[s] = __fadd_rn(__fadd_rn(br, __fmul_rn(dr, h[s])), gr[s]);
-                chain<S>(y, wA + (size_t)fr * 64, metaA + fr, nr, mr, xc);
+                chain<S, false>(y, wA + (size_t)fr * 64, metaA + fr, nr, mr, xc);
 #pragma unroll
                 for (int s = 0; s < S; s++) r[s] = sigmoid_approx(y[s], rcp);
                 // candidate (nnet.c:436-445)
 #pragma unroll
                 for (int s = 0; s < S; s++) y[s] = __fadd_rn(bh, __fmul_rn(dh, h[s]));
-                chain<S>(y, wA + (size_t)fh * 64, metaA + fh, nh, mh, xc);
+                chain<S, false>(y, wA + (size_t)fh * 64, metaA + fh, nh, mh, xc);
 #pragma unroll
                 for (int s = 0; s < S; s++) hc[s] = tanh_approx(__fadd_rn(__fmul_rn(y[s], r[s]), gh[s]), rcp);
                 // update gate and new state (nnet.c:446-447)
 #pragma unroll
                 for (int s = 0; s < S; s++) y[s] = __fadd_rn(__fadd_rn(bz, __fmul_rn(dz, h[s])), gz[s]);
-                chain<S>(y, wA + (size_t)fz * 64, metaA + fz, nz, mz, xc);
+                chain<S, false>(y, wA + (size_t)fz * 64, metaA + fz, nz, mz, xc);
 #pragma unroll
                 for (int s = 0; s < S; s++) {
                     const float z = sigmoid_approx(y[s], rcp);
@@ -186,11 +190,13 @@ __device__ __forceinline__ void run(const SampleParams &P, uint8_t *smem)
                 bar_sync(NB_X, CNT_CMP);
                 // GRU_B input side (nnet.c:346-352): one 384-term chain per row, lanes 0..47
                 if (warp < 2) {
-                    const int nbB = cl < 3 * NB ? (int)dirB[1] : 0, mB = __reduce_max_sync(0xffffffffu, nbB);
+                    const int nbB = (int)dirB[1], mB = __reduce_max_sync(0xffffffffu, nbB), uB = __reduce_min_sync(0xffffffffu, nbB) == mB;
                     const float *condBp = P.condB + (size_t)f * n * (3 * NB) + rowB;
 #pragma unroll
                     for (int s = 0; s < S; s++) y[s] = __fadd_rn(parB[rowB], __ldg(condBp + (size_t)gs[s] * (3 * NB)));
-                    chain<S>(y, wB + (size_t)dirB[0] * 64, metaB + dirB[0], nbB, mB, reinterpret_cast<const uint8_t *>(xs + nxt * FN_S * NA));
+                    const uint8_t *xn = reinterpret_cast<const uint8_t *>(xs + nxt * FN_S * NA);
+                    if (uB) chain<S, true>(y, wB + (size_t)dirB[0] * 64, metaB + dirB[0], nbB, mB, xn);     // dense rows: all lists alike
+                    else chain<S, false>(y, wB + (size_t)dirB[0] * 64, metaB + dirB[0], nbB, mB, xn);
                     if (cl < 3 * NB) {
 #pragma unroll
                         for (int s = 0; s < S; s++) accB[rowB * FN_S + s] = y[s];
