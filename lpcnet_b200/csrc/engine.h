@@ -173,6 +173,7 @@ struct SmemLayout {          // run-time part; offsets are absolute (from the st
     uint32_t sm_image;  // where the image starts (SM_IMAGE for int8, F_IMAGE for the float flavour)
     uint32_t image_bytes;
     uint32_t total_bytes;
+    uint32_t dense_b;   // neuron-per-lane float image: 1 if every GRU_B row group lists all 96 column blocks in order (offsets need no meta)
     uint32_t nblkA_padded, nblkB_padded;   // units in wA / wB: quads (int8 flavour) or blocks (float flavour)
 };
 

@@ -58,13 +58,14 @@ __device__ __forceinline__ void fma_block(float (&y)[FN_S], const BlkOps<S> &o, 
         y[s] = take ? v : y[s];
     }
 }
-// UNIFORM: every lane of the warp has the same list length (GRU_B: dense rows), no clamping, no select
-template <int S, bool UNIFORM>
+// UNIFORM: every lane of the warp has the same list length (GRU_B rows), no clamping, no select; DENSE: the list is all
+// column blocks in order, the state offset of block b is 16*b (no meta look-up in front of the state load)
+template <int S, bool UNIFORM, bool DENSE = false>
 __device__ __forceinline__ void chain(float (&y)[FN_S], const uint8_t *__restrict__ w, const uint16_t *__restrict__ meta, int nb, int nbmax,
                                       const uint8_t *__restrict__ x /* state buffer, stream 0 */)
 {
     const int last = max(nb - 1, 0);
-    auto ldm = [&](int b) { return (uint32_t)meta[UNIFORM ? b : min(b, last)]; };
+    auto ldm = [&](int b) { return DENSE ? (uint32_t)(16 * min(b, NA / 4 - 1)) : (uint32_t)meta[UNIFORM ? b : min(b, last)]; };
     auto ldb = [&](int b, uint32_t m, BlkOps<S> &o) {
         o.w = *reinterpret_cast<const uint2 *>(w + (size_t)(UNIFORM ? b : min(b, last)) * 64);
 #pragma unroll
@@ -164,19 +165,21 @@ __device__ __forceinline__ void run(const SampleParams &P, uint8_t *smem)
                     gr[s] = __fadd_rn(__fadd_rn(__fadd_rn(cr[s], __ldg(e0 + NA)), __ldg(e1 + NA)), __ldg(e2 + NA));
                     gh[s] = __fadd_rn(__fadd_rn(__fadd_rn(ch[s], __ldg(e0 + 2 * NA)), __ldg(e1 + 2 * NA)), __ldg(e2 + 2 * NA));
                 }
-                float y[FN_S], r[S], hc[S];
+                float y[FN_S], yh[FN_S], r[S], hc[S];
+                // candidate pre-activation first (nnet.c:436-440): its chain starts from bias + diag*h and does not need the
+                // gathered inputs, so it runs while those loads are in flight
+#pragma unroll
+                for (int s = 0; s < S; s++) yh[s] = __fadd_rn(bh, __fmul_rn(dh, h[s]));
+                chain<S, false>(yh, wA + (size_t)fh * 64, metaA + fh, nh, mh, xc);
                 // reset gate (nnet.c:431-435): chain starts from bias + diag*h + gin
 #pragma unroll
                 for (int s = 0; s < S; s++) y[s] = __fadd_rn(__fadd_rn(br, __fmul_rn(dr, h[s])), gr[s]);
                 chain<S, false>(y, wA + (size_t)fr * 64, metaA + fr, nr, mr, xc);
 #pragma unroll
                 for (int s = 0; s < S; s++) r[s] = sigmoid_approx(y[s], rcp);
-                // candidate (nnet.c:436-445)
+                // candidate (nnet.c:441-445)
 #pragma unroll
-                for (int s = 0; s < S; s++) y[s] = __fadd_rn(bh, __fmul_rn(dh, h[s]));
-                chain<S, false>(y, wA + (size_t)fh * 64, metaA + fh, nh, mh, xc);
-#pragma unroll
-                for (int s = 0; s < S; s++) hc[s] = tanh_approx(__fadd_rn(__fmul_rn(y[s], r[s]), gh[s]), rcp);
+                for (int s = 0; s < S; s++) hc[s] = tanh_approx(__fadd_rn(__fmul_rn(yh[s], r[s]), gh[s]), rcp);
                 // update gate and new state (nnet.c:446-447)
 #pragma unroll
                 for (int s = 0; s < S; s++) y[s] = __fadd_rn(__fadd_rn(bz, __fmul_rn(dz, h[s])), gz[s]);
@@ -195,7 +198,8 @@ __device__ __forceinline__ void run(const SampleParams &P, uint8_t *smem)
 #pragma unroll
                     for (int s = 0; s < S; s++) y[s] = __fadd_rn(parB[rowB], __ldg(condBp + (size_t)gs[s] * (3 * NB)));
                     const uint8_t *xn = reinterpret_cast<const uint8_t *>(xs + nxt * FN_S * NA);
-                    if (uB) chain<S, true>(y, wB + (size_t)dirB[0] * 64, metaB + dirB[0], nbB, mB, xn);     // dense rows: all lists alike
+                    if (uB && L.dense_b) chain<S, true, true>(y, wB + (size_t)dirB[0] * 64, metaB + dirB[0], nbB, mB, xn);
+                    else if (uB) chain<S, true>(y, wB + (size_t)dirB[0] * 64, metaB + dirB[0], nbB, mB, xn);     // all lists alike
                     else chain<S, false>(y, wB + (size_t)dirB[0] * 64, metaB + dirB[0], nbB, mB, xn);
                     if (cl < 3 * NB) {
 #pragma unroll
