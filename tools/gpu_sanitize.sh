@@ -6,8 +6,8 @@ import sys, os
 sys.path.insert(0, "."); sys.path.insert(0, "tests"); sys.path.insert(0, "oracle")
 import numpy as np, helpers as H, lpcnet_b200
 from fixtures import make_feature_batch
-for kind, spc in (("int8", "32"), ("int8", "5"), ("float", "32")):
-    os.environ["LPCNET_B200_STREAMS_PER_CTA"] = spc     # 32: one full CTA + a ragged one; 5: dead slots in both halves
+for kind, spc in (("int8", "32"), ("int8", "17"), ("int8", "5"), ("float", "32"), ("float", "2"), ("float", "3")):
+    os.environ["LPCNET_B200_STREAMS_PER_CTA"] = spc     # int8: 32 = full CTA + ragged one, 17 = two halves with dead slots, 5 = half-A-only schedule; float: 32 = lane==stream kernel, 2/3 = neuron-per-lane kernel
     f = make_feature_batch(range(40), 4)
     b = lpcnet_b200.Batch(40, H.blob(kind), lpc_gamma=H.LPC_GAMMA)
     got = b.synthesize(f, samples_per_frame=24)           # 2 active frames x 24 samples: enough to exercise every phase
