@@ -169,11 +169,11 @@ struct SmemLayout {          // run-time part; offsets are absolute (from the st
     uint32_t metaA;     // int8: 4 x u16 per quad (xs_offset of each slot's column block); float: u16 per block
     uint32_t wB;        // GRU_B input weights, ordered (row group, K part)
     uint32_t metaB;
-    uint32_t wBrecF;    // float flavour only: fp32 [16 in][48 out] GRU_B recurrent weights
+    uint32_t wBrecF;    // float flavour, lane==stream image: fp32 [16 in][48 out] GRU_B recurrent weights.  Neuron-per-lane image (its
+                        // recurrent weights sit at FNI_WBREC): 1 if every GRU_B row group lists all 96 column blocks in order
     uint32_t sm_image;  // where the image starts (SM_IMAGE for int8, F_IMAGE for the float flavour)
     uint32_t image_bytes;
     uint32_t total_bytes;
-    uint32_t dense_b;   // neuron-per-lane float image: 1 if every GRU_B row group lists all 96 column blocks in order (offsets need no meta)
     uint32_t nblkA_padded, nblkB_padded;   // units in wA / wB: quads (int8 flavour) or blocks (float flavour)
 };
 

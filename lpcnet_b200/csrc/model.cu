@@ -419,8 +419,8 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
             for (size_t j = 0; j < lst.size(); j++) { put_t(&im[Ln.wB - FN_IMAGE + (size_t)(bk + j) * 64], lst[j].w); mB[bk + j] = (uint16_t)(lst[j].pos * 4); }
             bk += (uint32_t)lst.size();
         }
-        Ln.dense_b = 1;
-        for (int rg = 0; rg < 6; rg++) { if (rowsB[rg].size() != NA / 4) Ln.dense_b = 0; else for (size_t j = 0; j < rowsB[rg].size(); j++) if (rowsB[rg][j].pos != (int)(4 * j)) Ln.dense_b = 0; }
+        Ln.wBrecF = 1;
+        for (int rg = 0; rg < 6; rg++) { if (rowsB[rg].size() != NA / 4) Ln.wBrecF = 0; else for (size_t j = 0; j < rowsB[rg].size(); j++) if (rowsB[rg][j].pos != (int)(4 * j)) Ln.wBrecF = 0; }
         memcpy(&im[FNI_PARB], gb_bias, 6 * NB * 4);
         memcpy(&im[FNI_WBREC], wBrec->data, 3 * NB * NB * 4);
     }

@@ -198,7 +198,7 @@ __device__ __forceinline__ void run(const SampleParams &P, uint8_t *smem)
 #pragma unroll
                     for (int s = 0; s < S; s++) y[s] = __fadd_rn(parB[rowB], __ldg(condBp + (size_t)gs[s] * (3 * NB)));
                     const uint8_t *xn = reinterpret_cast<const uint8_t *>(xs + nxt * FN_S * NA);
-                    if (uB && L.dense_b) chain<S, true, true>(y, wB + (size_t)dirB[0] * 64, metaB + dirB[0], nbB, mB, xn);
+                    if (uB && L.wBrecF) chain<S, true, true>(y, wB + (size_t)dirB[0] * 64, metaB + dirB[0], nbB, mB, xn);
                     else if (uB) chain<S, true>(y, wB + (size_t)dirB[0] * 64, metaB + dirB[0], nbB, mB, xn);     // all lists alike
                     else chain<S, false>(y, wB + (size_t)dirB[0] * 64, metaB + dirB[0], nbB, mB, xn);
                     if (cl < 3 * NB) {
