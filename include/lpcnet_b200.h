@@ -108,6 +108,9 @@ LPCNET_EXPORT int lpcnet_b200_debug_frame_network(LPCNetB200Batch *b, const floa
 LPCNET_EXPORT int lpcnet_b200_debug_image(const unsigned char *blob, int len, unsigned char *out, size_t cap,
                                           uint32_t *layout);
 
+/* Same for the second image of float models (the neuron-per-lane kernel used for small batches); layout[17]. */
+LPCNET_EXPORT int lpcnet_b200_debug_image_n(const unsigned char *blob, int len, unsigned char *out, size_t cap,
+                                            uint32_t *layout);
 /* Test hook: evaluate the engine's two implementations of the reference's _mm256_rcp_ps emulation (memory table /
  * table-free arithmetic) on n host floats. */
 LPCNET_EXPORT int lpcnet_b200_debug_rcp(LPCNetB200Batch *b, const float *x, float *out_table, float *out_arith, int n);

@@ -451,6 +451,19 @@ int lpcnet_b200_debug_rcp(LPCNetB200Batch *b, const float *x, float *out_table, 
     return 0;
 }
 
+// Test hook (host only): image of the neuron-per-lane float kernel.  layout = {wA, metaA, wB, metaB, image_bytes, total_bytes,
+// nblkA, nblkB, FN_IMAGE, FNI_NEUR, FNI_DIRA, FNI_PARA, FNI_DIRB, FNI_PARB, FNI_WBREC, FNI_FCW, dense flag}
+int lpcnet_b200_debug_image_n(const unsigned char *blob, int len, unsigned char *out, size_t cap, uint32_t *layout)
+{
+    SmemLayout L;
+    int r = debug_build_image_n(blob, len, out, cap, &L);
+    if (r < 0) return r;
+    layout[0] = L.wA; layout[1] = L.metaA; layout[2] = L.wB; layout[3] = L.metaB; layout[4] = L.image_bytes; layout[5] = L.total_bytes;
+    layout[6] = L.nblkA_padded; layout[7] = L.nblkB_padded; layout[8] = FN_IMAGE; layout[9] = FNI_NEUR; layout[10] = FNI_DIRA; layout[11] = FNI_PARA;
+    layout[12] = FNI_DIRB; layout[13] = FNI_PARB; layout[14] = FNI_WBREC; layout[15] = FNI_FCW; layout[16] = L.wBrecF;
+    return r;
+}
+
 // Pinned host memory helpers for callers that want true async H2D/D2H (the benchmark's e2e leg).
 void *lpcnet_b200_host_alloc(size_t bytes)
 {

@@ -238,6 +238,7 @@ struct SampleParams {
 int model_load(DeviceModel *m, const unsigned char *blob, int len, float lpc_gamma);   // 0 / -1 (sets error)
 void model_free(DeviceModel *m);
 int debug_build_image(const unsigned char *blob, int len, unsigned char *out, size_t cap, SmemLayout *L);
+int debug_build_image_n(const unsigned char *blob, int len, unsigned char *out, size_t cap, SmemLayout *L);
 void set_error(const char *fmt, ...);
 
 struct FrameState {           // per-batch persistent state of the 100 Hz path

@@ -451,6 +451,18 @@ int debug_build_image(const unsigned char *blob, int len, unsigned char *out, si
     return (int)hm.img.size();
 }
 
+// Same for the second image of float models (neuron-per-lane kernel).
+int debug_build_image_n(const unsigned char *blob, int len, unsigned char *out, size_t cap, SmemLayout *L)
+{
+    DeviceModel m; HostModel hm;
+    if (build_host_model(&m, hm, blob, len, 1.0f) != 0) return -1;
+    if (!m.is_float) { set_error("debug image: not a float blob"); return -1; }
+    *L = m.Ln;
+    if (hm.img_n.size() > cap) { set_error("debug image: buffer too small"); return -1; }
+    memcpy(out, hm.img_n.data(), hm.img_n.size());
+    return (int)hm.img_n.size();
+}
+
 int model_load(DeviceModel *m, const unsigned char *blob, int len, float lpc_gamma)
 {
     HostModel hm;

@@ -151,6 +151,64 @@ def test_smem_image_replays_to_the_dense_model(L):
     np.testing.assert_array_equal(fcw[:, 34:36], arrs["dual_fc_factor"].reshape(2, 256).T[:FCN])
 
 
+def test_float_neuron_image_replays_to_the_dense_model(L):
+    """Image of the neuron-per-lane float kernel: every compute lane owns one neuron, the fp16 blocks are transposed to
+    [8 rows][4 cols]; walking it like the kernel must reproduce the dense float matrices (the weights are fp16-exact)."""
+    import gen_model
+    common, _, onlyf = gen_model.make_model()
+    arrs = {n: a for n, _, a in common + onlyf}
+    blob = H.blob("float")
+    out = np.zeros(300000, np.uint8); lay = (ctypes.c_uint32 * 32)()
+    L.lpcnet_b200_debug_image_n.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    r = L.lpcnet_b200_debug_image_n(blob, len(blob), out.ctypes.data, out.size, lay)
+    wA, metaA, wB, metaB, image_bytes, total, nA, nB, IMG, NEUR, DIRA, PARA, DIRB, PARB, WBREC, FCW, dense = [int(v) for v in lay[:17]]
+    assert r == image_bytes and total <= 227 * 1024 and total == IMG + image_bytes
+    img = out[:image_bytes]
+    rel = lambda o: o - IMG
+
+    def dense_from_sparse(w, idx, nrows, ncols):
+        M = np.zeros((nrows, ncols), np.float64); p = 0; wp = 0
+        for rg in range(nrows // 8):
+            nb = idx[p]; p += 1
+            for _ in range(nb):
+                pos = idx[p]; p += 1
+                M[rg * 8:rg * 8 + 8, pos:pos + 4] = w[wp:wp + 32].reshape(4, 8).T; wp += 32      # blob block = [4 cols][8 rows]
+        return M
+    MA = dense_from_sparse(arrs["sparse_gru_a_recurrent_weights"].astype(np.float64), arrs["sparse_gru_a_recurrent_weights_idx"], 1152, 384)
+    MB = dense_from_sparse(arrs["gru_b_weights"].astype(np.float64), arrs["gru_b_weights_idx"], 48, 384)
+    neur = img[NEUR:NEUR + 768].view(np.uint16)
+    assert sorted(neur.tolist()) == list(range(384))                       # every neuron owned by exactly one lane
+    assert all((neur[8 * k:8 * k + 8] == neur[8 * k] + np.arange(8)).all() and neur[8 * k] % 8 == 0 for k in range(48))
+    dirA = img[DIRA:DIRA + 48 * 3 * 2 * 4].view(np.uint32).reshape(48, 3, 2)
+    blkA = img[rel(wA):rel(wA) + nA * 64].view(np.float16).astype(np.float64).reshape(nA, 8, 4)
+    mA = img[rel(metaA):rel(metaA) + nA * 2].view(np.uint16)
+    got = np.zeros((1152, 384))
+    for g in range(48):
+        for q in range(3):
+            b0, nb = int(dirA[g, q, 0]), int(dirA[g, q, 1])
+            for b in range(b0, b0 + nb):
+                pos = int(mA[b]) // 4
+                assert mA[b] % 16 == 0
+                got[q * 384 + 8 * g:q * 384 + 8 * g + 8, pos:pos + 4] += blkA[b]
+    np.testing.assert_array_equal(got, MA)
+    dirB = img[DIRB:DIRB + 48].view(np.uint32).reshape(6, 2)
+    blkB = img[rel(wB):rel(wB) + nB * 64].view(np.float16).astype(np.float64).reshape(nB, 8, 4)
+    mB = img[rel(metaB):rel(metaB) + nB * 2].view(np.uint16)
+    gotB = np.zeros((48, 384))
+    for rg in range(6):
+        b0, nb = int(dirB[rg, 0]), int(dirB[rg, 1])
+        for k, b in enumerate(range(b0, b0 + nb)):
+            pos = int(mB[b]) // 4
+            assert not dense or pos == 4 * k                               # dense flag: offsets are 16 * block index
+            gotB[rg * 8:rg * 8 + 8, pos:pos + 4] += blkB[b]
+    np.testing.assert_array_equal(gotB, MB)
+    para = img[PARA:PARA + 6 * 384 * 4].view(np.float32).reshape(3, 2, 384)
+    np.testing.assert_array_equal(para[:, 0], arrs["sparse_gru_a_bias"][1].reshape(3, 384))
+    np.testing.assert_array_equal(para[:, 1], arrs["sparse_gru_a_recurrent_weights_diag"].reshape(3, 384))
+    fcw = img[FCW:FCW + 256 * 36 * 4].view(np.float32).reshape(256, 36)
+    np.testing.assert_array_equal(fcw[:, :32], arrs["dual_fc_weights"].reshape(256, 32))
+
+
 def test_python_mirror_matches_reference_operator_names():
     for name in ("LPCNet", "LPCNetDecoder", "Batch"):
         assert hasattr(lpcnet_b200, name)
