@@ -120,12 +120,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 
-__device__ __forceinline__ int4 lds128(uint32_t addr)
-{
-    int4 v;
-    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-    return v;
-}
 __device__ __forceinline__ uint32_t lds32(uint32_t addr)
 {
     uint32_t v;
@@ -608,7 +602,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
         for (int f = 0; f < P.nframes; f++)
             for (int t_ = 0; t_ < spf; t_++, step++, k += 6) {
                 int Sh[GPW][4], Sg[GPW][4];                              // candidate-gate sums (later rec_h * r) / r-gate, then z-gate sums (later z)
-                const int tl = warp == 0 ? lane : 1;
+                const int tl = warp == 0 ? lane : 1; (void)tl;    // (lane selector of the TRACE stamps)
                 TRACE(P, step, 0, tl);
                 gemv_rh<0>(C, Sh, Sg, step & 1);
                 TRACE(P, step, 1, tl);

@@ -3,9 +3,14 @@
 import os, subprocess, sys
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, ROOT)
+# geometry / option variants of the int8 per-sample kernel (compile-time macros of sample_kernel.cu / engine.h).  Measured in
+# round 1: 16 compute warps + 6 producers is the best geometry (12 and 24 compute warps are within 5 %).
 VARIANTS = {
-    "alloc": ["LPCNET_GATHER_NOALLOC=0"],
-    "noalloc": ["LPCNET_GATHER_NOALLOC=1"],
+    "default": [],
+    "c12": ["LPCNET_NWC=12"],
+    "c24": ["LPCNET_NWC=24"],
+    "rcp_arith": ["LPCNET_RCP_ARITH=1"],
+    "gather_noalloc": ["LPCNET_GATHER_NOALLOC=1"],
 }
 if sys.argv[1] == "build":
     from lpcnet_b200 import build
