@@ -423,7 +423,7 @@ int lpcnet_b200_debug_image(const unsigned char *blob, int len, unsigned char *o
     layout[0] = L.wA; layout[1] = L.metaA; layout[2] = L.wB; layout[3] = L.metaB; layout[4] = L.image_bytes; layout[5] = L.total_bytes;
     layout[6] = L.nblkA_padded; layout[7] = L.nblkB_padded; layout[8] = L.sm_image;
     layout[9] = IM_PARA; layout[10] = IM_DIRA; layout[11] = IM_GRPA; layout[12] = IM_DIRB; layout[13] = IM_WBREC; layout[14] = IM_PARB;
-    layout[15] = IM_FCW; layout[16] = NWC; layout[17] = GPW; layout[18] = FCW_SMEM_NODES; layout[19] = KPARTS;
+    layout[15] = IM_FCW; layout[16] = NWC; layout[17] = GPW; layout[18] = *reinterpret_cast<const uint32_t *>(out + IM_FCWN); layout[19] = KPARTS;
     return r;
 }
 

@@ -41,7 +41,8 @@ constexpr int SAMPLE_THREADS = (NWC + NWP + 2) * 32;   // + 2 sampler warps, one
 constexpr int XS_BYTES = (NA / 4) * 32 * 4;  // quantised GRU_A state of 32 streams: [96 column blocks][32 words], see xs_offset()
 constexpr int FCW_ROW = 36;                  // dual_fc row: 32 weights (16 per channel) + {bias0, bias1, factor0, factor1}; 144 B stride = 16 mod 128, so the
                                              // per-lane LDS.128 row reads of lanes on different nodes mostly land in different 4-bank groups
-constexpr int FCW_SMEM_NODES = 64;           // tree levels 0..5 (nodes 1..63) live in shared memory, levels 6,7 are read from global (L2)
+constexpr int FCW_SMEM_NODES = 64;           // at most the tree levels 0..5 (nodes 1..63) live in shared memory, the rest is read from global (L2);
+                                             // a model whose block lists need the room keeps fewer (32, 16, 8: model.cu), the count travels in the image
 constexpr int KPARTS = (NWC >= 24) ? 4 : 2;  // K split of the GRU_B input GEMV
 constexpr int NWB = 6 * KPARTS;              // warps used by the GRU_B input GEMV: (row group 0..5) x (K part)
 static_assert(NWB <= NWC, "one (row group, K part) of GRU_B per compute warp");
@@ -105,11 +106,13 @@ constexpr uint32_t IM_PRE_END = IM_DIRB + NWB * 2 * 4;
 // 8 KB-aligned so that the entry address is table | index (no add)
 constexpr uint32_t IM_RCP   = IM_PRE_END + (8192u - (SMEM_RESERVED + SM_IMAGE + IM_PRE_END) % 8192u) % 8192u;
 static_assert((SMEM_RESERVED + SM_IMAGE + IM_RCP) % 8192u == 0, "rcp table alignment");
-constexpr uint32_t IM_FCW   = IM_RCP + 2048 * 4;                   // float [FCW_SMEM_NODES][FCW_ROW] dual_fc rows of the upper tree levels
-constexpr uint32_t IM_PARA  = IM_FCW + FCW_SMEM_NODES * FCW_ROW * 4;   // float [NWC][GPW][3 gates][16] = recurrent su-bias[8], diag[8]
+constexpr uint32_t IM_FCWN  = IM_PRE_END;                          // u32: number of dual_fc rows present at IM_FCW (lives in the alignment gap in front of the table)
+static_assert(IM_RCP - IM_PRE_END >= 4, "room for the dual_fc row count");
+constexpr uint32_t IM_PARA  = IM_RCP + 2048 * 4;                   // float [NWC][GPW][3 gates][16] = recurrent su-bias[8], diag[8]
 constexpr uint32_t IM_WBREC = IM_PARA + NWC * GPW * 3 * 16 * 4;    // int8 [6][4][8][4] GRU_B recurrent blocks
 constexpr uint32_t IM_PARB  = IM_WBREC + 3 * NB * NB;              // float [96]: input-side su-bias[48], recurrent-side su-bias[48]
-constexpr uint32_t IM_VAR   = al128(IM_PARB + 6 * NB * 4);         // start of the variable-size arrays
+constexpr uint32_t IM_FCW   = al128(IM_PARB + 6 * NB * 4);         // float [<= FCW_SMEM_NODES][FCW_ROW] dual_fc rows of the upper tree levels
+constexpr uint32_t IM_VAR   = IM_FCW + FCW_SMEM_NODES * FCW_ROW * 4;   // start of the variable-size arrays when all FCW_SMEM_NODES rows are kept
 
 // ---- shared-memory map of the FLOAT-flavour per-sample kernel (sample_kernel_f32.cu) ----
 // fp32 GRU_A state tile instead of the u8 one, no gather tiles (per-lane gather), fp16 weights (64 B per block),

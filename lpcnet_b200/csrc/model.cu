@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -197,16 +198,23 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
         }
     }
     const ImageMap M = is_float ? MAP_F32 : MAP_INT8;
-    uint32_t off = M.sm_image + M.var;
-    auto take = [&](uint32_t bytes, uint32_t align = 16) { off = align_up(off, align); uint32_t o = off; off += bytes; return o; };
-    // readable slack behind every array: the pipelined GEMVs prefetch past the list end (values never used)
-    const uint32_t unit_w = is_float ? img_blk : QUAD_BYTES, unit_m = is_float ? 2 : QUAD_META_BYTES, slack_w = is_float ? 2 : 4, slack_m = is_float ? 4 : 6;
-    L.wA = take((nA_pad + slack_w) * unit_w, 128);
-    L.metaA = take((nA_pad + slack_m) * unit_m);
-    L.wB = take((nB_pad + slack_w) * unit_w, 128);
-    L.metaB = take((nB_pad + slack_m) * unit_m);
-    L.wBrecF = is_float ? take(3 * NB * NB * 4, 16) : 0;
-    L.total_bytes = align_up(off, 128);
+    // int8 flavour: the dual_fc rows of the upper tree levels sit right in front of the variable arrays; keep as many (64, 32, 16,
+    // 8) as the model's block lists leave room for
+    int fcw_nodes = FCW_SMEM_NODES;
+    if (const char *e = getenv("LPCNET_B200_FCW_NODES")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32) fcw_nodes = v; }   // (tests)
+    for (;; fcw_nodes /= 2) {
+        uint32_t off = M.sm_image + (is_float ? M.var : M.fcw + align_up((uint32_t)fcw_nodes * FCW_ROW * 4, 128));
+        auto take = [&](uint32_t bytes, uint32_t align = 16) { off = align_up(off, align); uint32_t o = off; off += bytes; return o; };
+        // readable slack behind every array: the pipelined GEMVs prefetch past the list end (values never used)
+        const uint32_t unit_w = is_float ? img_blk : QUAD_BYTES, unit_m = is_float ? 2 : QUAD_META_BYTES, slack_w = is_float ? 2 : 4, slack_m = is_float ? 4 : 6;
+        L.wA = take((nA_pad + slack_w) * unit_w, 128);
+        L.metaA = take((nA_pad + slack_m) * unit_m);
+        L.wB = take((nB_pad + slack_w) * unit_w, 128);
+        L.metaB = take((nB_pad + slack_m) * unit_m);
+        L.wBrecF = is_float ? take(3 * NB * NB * 4, 16) : 0;
+        L.total_bytes = align_up(off, 128);
+        if (sample_kernel_smem_ok(L.total_bytes) || is_float || fcw_nodes <= 8) break;
+    }
     L.sm_image = M.sm_image;
     L.image_bytes = L.total_bytes - M.sm_image;
     L.nblkA_padded = nA_pad; L.nblkB_padded = nB_pad;
@@ -337,7 +345,10 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
             for (int j = 0; j < 32; j++) r[j] = fc_w[i * 32 + j];
             r[32] = fc_b[i]; r[33] = fc_b[256 + i]; r[34] = fc_f[i]; r[35] = fc_f[256 + i];
         }
-        if (!is_float) memcpy(&img[M.fcw], hm.fc_rows.data(), (size_t)FCW_SMEM_NODES * FCW_ROW * 4);
+        if (!is_float) {
+            memcpy(&img[M.fcw], hm.fc_rows.data(), (size_t)fcw_nodes * FCW_ROW * 4);
+            *reinterpret_cast<uint32_t *>(&img[IM_FCWN]) = (uint32_t)fcw_nodes;
+        }
         else { memcpy(&img[M.fcb], fc_b, 512 * 4); memcpy(&img[M.fcf], fc_f, 512 * 4); }
     }
 

@@ -675,6 +675,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
         const float *u2l = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_U2L);
         const float *fcw = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_FCW) + ch * NB;
         const float *fcw_g = P.fcw + ch * NB;
+        const int fcw_nodes = *reinterpret_cast<const int *>(smem + SM_IMAGE + IM_FCWN);    // dual_fc rows kept in shared memory (64 unless the model needed the room)
         const uint32_t mb_idx = smem_u32(smem + MB_IDX) + 8 * hh;
         int *idx_h = idx_s + hh * 3 * HALF;
 
@@ -732,7 +733,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
                     const int i = (1 << b) | val;
                     // this lane's channel: a sequential 16-term chain
                     float w16[16], sum, fac;
-                    if (b < 6) {                                         // nodes < 64: rows in shared memory
+                    if (b < 3 || (b < 6 && i < fcw_nodes)) {             // upper levels: rows in shared memory (8 nodes always, up to 64: model.cu)
                         const float *wr = fcw + i * FCW_ROW;
                         const float4 a0 = *reinterpret_cast<const float4 *>(wr), a1 = *reinterpret_cast<const float4 *>(wr + 4);
                         const float4 a2 = *reinterpret_cast<const float4 *>(wr + 8), a3 = *reinterpret_cast<const float4 *>(wr + 12);

@@ -73,6 +73,18 @@ def test_conversion_unit_path_matches_golden_too(eng, monkeypatch):
     assert _first_diff(got, gold) is None
 
 
+@pytest.mark.parametrize("nodes", ["8", "32"])
+def test_fewer_dual_fc_rows_in_shared_memory(eng, monkeypatch, nodes):
+    """A model that needs the room keeps fewer dual_fc rows in shared memory (model.cu); the sampler then reads the other
+    tree levels from global memory: same PCM."""
+    gold = np.load(os.path.join(H.GOLDEN, "synth_A.npz"))["pcm"]
+    monkeypatch.setenv("LPCNET_B200_FCW_NODES", nodes)
+    b = _batch(eng, 4)
+    got = b.synthesize(make_feature_batch(range(4), 40))
+    b.close()
+    assert _first_diff(got, gold) is None
+
+
 def test_arithmetic_rcpps_matches_table(eng):
     """The GRU_A activations use a table-free _mm256_rcp_ps emulation (devmath.cuh, RcpArith: MUFU.RCP + exact residual
     correction).  It must equal the table (= the reference's RCPPS, tests/golden/rcpps_table.bin) for every one of the

@@ -151,6 +151,25 @@ def test_smem_image_replays_to_the_dense_model(L):
     np.testing.assert_array_equal(fcw[:, 34:36], arrs["dual_fc_factor"].reshape(2, 256).T[:FCN])
 
 
+def test_denser_model_trades_dual_fc_rows_for_weight_room(L, tmp_path, monkeypatch):
+    """The int8 image is sized for the default 5/5/20 % block densities with 64 dual_fc rows in shared memory; a model
+    with more blocks must still load (fewer dual_fc rows kept, the sampler reads the others from L2) until the weights
+    themselves no longer fit, which is refused with a message."""
+    import gen_model
+    def image_for(density):
+        monkeypatch.setattr(gen_model, "DENSITY", density)
+        common, only8, _ = gen_model.make_model()
+        path = str(tmp_path / "m.bin")
+        gen_model.write_blob(path, common + only8)
+        return _image(L, open(path, "rb").read())
+    r, img, lay = image_for((0.05, 0.05, 0.20))
+    assert r > 0 and int(lay[18]) == 64 and int(lay[5]) <= 227 * 1024
+    r, img, lay = image_for((0.06, 0.06, 0.22))
+    assert r > 0 and int(lay[18]) in (8, 16, 32) and int(lay[5]) <= 227 * 1024
+    r, img, lay = image_for((0.15, 0.15, 0.40))
+    assert r < 0 and b"shared memory" in L.lpcnet_b200_last_error()
+
+
 def test_float_neuron_image_replays_to_the_dense_model(L):
     """Image of the neuron-per-lane float kernel: every compute lane owns one neuron, the fp16 blocks are transposed to
     [8 rows][4 cols]; walking it like the kernel must reproduce the dense float matrices (the weights are fp16-exact)."""
