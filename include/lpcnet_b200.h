@@ -89,6 +89,11 @@ LPCNET_EXPORT int lpcnet_b200_memcpy_d2h(void *dst, const void *src, size_t byte
 LPCNET_EXPORT void *lpcnet_b200_host_alloc(size_t bytes);                 /* pinned */
 LPCNET_EXPORT void lpcnet_b200_host_free(void *p);
 
+/* Measured peak of the unit that bounds the per-sample kernel, the L1/shared-memory data pipe: every SM streams
+ * conflict-free LDS out of shared memory (lpcnet_b200/csrc/microbench.cu).  out[7] = {LDS.128 GB/s whole chip,
+ * LDS.128 bytes/clk/SM, LDS.64 GB/s, LDS.64 B/clk/SM, LDS.32 GB/s, LDS.32 B/clk/SM, SM count}. */
+LPCNET_EXPORT int lpcnet_b200_measure_smem_peak(int device, double *out);
+
 /* Algorithmic bytes one synthesized sample of one stream must read: total and the
  * sparse-GEMV-only subset (GRU_A weights + indices). */
 LPCNET_EXPORT int lpcnet_b200_batch_algorithmic_bytes(const LPCNetB200Batch *b, long *total, long *sparse_gemv);
@@ -120,6 +125,12 @@ LPCNET_EXPORT int lpcnet_b200_debug_rcp(LPCNetB200Batch *b, const float *x, floa
  * paths) and LPCNET_B200_LPC_GAMMA. */
 LPCNET_EXPORT int lpcnet_b200_set_default_model(const unsigned char *blob, int len, float lpc_gamma);
 LPCNET_EXPORT int lpcnet_b200_set_default_codebooks(const float *cb, size_t n_floats);
+/* Release the device resources behind a state that was set up with lpcnet_init() / lpcnet_decoder_init() on
+ * caller-owned memory (reference include/lpcnet.h:160-169: get_size + init, no matching deinit).  Without this call they
+ * are released at process exit, or when the same memory is initialised again.  `st` is the LPCNetState* (a
+ * LPCNetDecState* may be passed as well: it starts with its LPCNetState, src/lpcnet_private.h:50-53). */
+struct LPCNetState;
+LPCNET_EXPORT void lpcnet_b200_deinit(struct LPCNetState *st);
 
 #ifdef __cplusplus
 }

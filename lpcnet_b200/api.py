@@ -55,6 +55,7 @@ def lib():
     L.lpcnet_b200_host_alloc.restype = c_p
     L.lpcnet_b200_host_alloc.argtypes = [ctypes.c_size_t]
     L.lpcnet_b200_host_free.argtypes = [c_p]
+    L.lpcnet_b200_measure_smem_peak.argtypes = [ctypes.c_int, c_p]
     # reference API (include/lpcnet.h)
     L.lpcnet_create.restype = c_p
     L.lpcnet_destroy.argtypes = [c_p]
@@ -77,6 +78,15 @@ def _err():
 
 def device_count():
     return lib().lpcnet_b200_device_count()
+
+
+def measure_smem_peak(device=0):
+    """Measured shared-memory streaming peak (conflict-free LDS on every SM): dict of GB/s and bytes/clk/SM per width."""
+    out = (ctypes.c_double * 7)()
+    if lib().lpcnet_b200_measure_smem_peak(int(device), out) != 0:
+        raise LPCNetB200Error("measure_smem_peak: " + _err())
+    return {"lds128_gbs": out[0], "lds128_bytes_per_clk_sm": out[1], "lds64_gbs": out[2], "lds64_bytes_per_clk_sm": out[3],
+            "lds32_gbs": out[4], "lds32_bytes_per_clk_sm": out[5], "sms": int(out[6])}
 
 
 class Batch:

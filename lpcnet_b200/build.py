@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "liblpcnet_b200.so")
-SOURCES = ["model.cu", "frame_kernels.cu", "sample_kernel.cu", "sample_kernel_f32.cu", "sample_kernel_f32n.cu", "batch_api.cu", "lpcnet_api.cu"]
+SOURCES = ["model.cu", "frame_kernels.cu", "sample_kernel.cu", "sample_kernel_f32.cu", "sample_kernel_f32n.cu", "batch_api.cu", "lpcnet_api.cu", "microbench.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-fmad=false",                    # never contract a*b+c: the pinned oracle build uses -ffp-contract=off

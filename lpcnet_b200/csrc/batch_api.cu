@@ -32,19 +32,66 @@ struct LPCNetB200Batch {
     short *d_pcm; size_t d_pcm_cap;
     uint8_t *d_packets; size_t d_packets_cap;
     cudaStream_t stream;
+    // Ordering of the engine state across CUDA streams: every call that enqueues work records `order_ev` on the stream it
+    // used; the next call makes ITS stream wait for that event first (and host-side readers synchronise on it).  A caller
+    // may therefore pass a different cuda_stream to every `_device` call, or mix them with the host-pointer calls.
+    cudaEvent_t order_ev; cudaStream_t last_stream; bool has_order;
+    bool env_exact_cvt, env_float_lane_stream;    // LPCNET_B200_EXACT_CVT / _FLOAT_LANE_STREAM, read once at create time (tests)
     cudaEvent_t ev0, ev1;                         // user timer (lpcnet_b200_batch_timer_*)
     std::vector<cudaEvent_t> *kev;                // event pairs around every per-sample kernel launch of the last call
     int kev_used;
     int last_launches;
 };
 
-static int ensure(void **p, size_t *cap, size_t bytes)
+static int order_sync(LPCNetB200Batch *b);
+// grow a staging buffer; work on any stream may still be using the old one, so wait for it before freeing
+static int ensure(LPCNetB200Batch *b, void **p, size_t *cap, size_t bytes)
 {
     if (*cap >= bytes) return 0;
+    if (order_sync(b)) return -1;
     if (*p) cudaFree(*p);
     *p = nullptr; *cap = 0;
     CK(cudaMalloc(p, bytes));
     *cap = bytes;
+    return 0;
+}
+
+// stream hand-over (see LPCNetB200Batch::order_ev)
+static int order_enter(LPCNetB200Batch *b, cudaStream_t st)
+{
+    if (b->has_order && b->last_stream != st) CK(cudaStreamWaitEvent(st, b->order_ev, 0));
+    return 0;
+}
+static int order_leave(LPCNetB200Batch *b, cudaStream_t st)
+{
+    CK(cudaEventRecord(b->order_ev, st));
+    b->last_stream = st; b->has_order = true;
+    return 0;
+}
+static int order_sync(LPCNetB200Batch *b)       // host-side readers / writers of the state: wait for whatever ran last
+{
+    if (b->has_order) CK(cudaEventSynchronize(b->order_ev));
+    return 0;
+}
+
+// The RCPPS look-up of the per-sample kernel forms its table address as `table | index` (devmath.cuh), which needs the
+// table 8 KB-aligned in the SHARED WINDOW; the image offsets assume dynamic shared memory starts at SMEM_RESERVED.
+// Probed once per device at create time so that a driver with a different reservation fails here with a message,
+// not with a trap inside the kernel.
+__global__ void smem_base_probe_kernel(uint32_t *out)
+{
+    extern __shared__ __align__(128) uint8_t probe_smem[];
+    *out = (uint32_t)__cvta_generic_to_shared(probe_smem);
+}
+static int probe_smem_base(uint32_t *base)
+{
+    uint32_t *d = nullptr;
+    CK(cudaMalloc(&d, 4));
+    CK(cudaFuncSetAttribute(smem_base_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    smem_base_probe_kernel<<<1, 32, 227 * 1024>>>(d);
+    cudaError_t e = cudaMemcpy(base, d, 4, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) { set_error("shared-memory probe failed: %s", cudaGetErrorString(e)); return -1; }
     return 0;
 }
 
@@ -95,6 +142,7 @@ int lpcnet_b200_batch_reset(LPCNetB200Batch *b)
 {
     if (!b) { set_error("null batch"); return -1; }
     CK(cudaSetDevice(b->device));
+    if (order_enter(b, b->stream)) return -1;
     const size_t n = b->n;
     CK(cudaMemsetAsync(b->hA, 0, sizeof(float) * NA * n, b->stream));
     CK(cudaMemsetAsync(b->hB, 0, sizeof(float) * NB * n, b->stream));
@@ -111,6 +159,7 @@ int lpcnet_b200_batch_reset(LPCNetB200Batch *b)
     std::vector<int> le(n, 128);                       // last_exc = lin2ulaw(0.f) = 128 (lpcnet.c:180)
     CK(cudaMemcpyAsync(b->rng, r.data(), sizeof(uint32_t) * 4 * n, cudaMemcpyHostToDevice, b->stream));
     CK(cudaMemcpyAsync(b->last_exc, le.data(), sizeof(int) * n, cudaMemcpyHostToDevice, b->stream));
+    if (order_leave(b, b->stream)) return -1;
     CK(cudaStreamSynchronize(b->stream));
     b->frame_count = 0;
     return 0;
@@ -139,6 +188,17 @@ LPCNetB200Batch *lpcnet_b200_batch_create(int n_streams, const unsigned char *bl
     al((void **)&b->lpc_raw, sizeof(float) * (size_t)(CHUNK + 2) * n * LPC_ORDER);
     if (ok && cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) ok = false;
     if (ok && (cudaEventCreate(&b->ev0) != cudaSuccess || cudaEventCreate(&b->ev1) != cudaSuccess)) ok = false;
+    if (ok && cudaEventCreateWithFlags(&b->order_ev, cudaEventDisableTiming) != cudaSuccess) ok = false;
+    b->env_exact_cvt = getenv("LPCNET_B200_EXACT_CVT") != nullptr;
+    b->env_float_lane_stream = getenv("LPCNET_B200_FLOAT_LANE_STREAM") != nullptr;
+    if (ok && !b->model.is_float) {
+        uint32_t base = 0;
+        if (probe_smem_base(&base)) { lpcnet_b200_batch_destroy(b); return nullptr; }
+        if ((base + SM_IMAGE + IM_RCP) % 8192u != 0) {
+            set_error("dynamic shared memory starts at window offset %u on this driver, the image layout assumes %u (engine.h SMEM_RESERVED)", base, SMEM_RESERVED);
+            lpcnet_b200_batch_destroy(b); return nullptr;
+        }
+    }
     if (!ok) { set_error("device allocation failed: %s", cudaGetErrorString(cudaGetLastError())); lpcnet_b200_batch_destroy(b); return nullptr; }
     if (lpcnet_b200_batch_reset(b) != 0) { lpcnet_b200_batch_destroy(b); return nullptr; }
     return b;
@@ -156,6 +216,7 @@ void lpcnet_b200_batch_destroy(LPCNetB200Batch *b)
     model_free(&b->model);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
+    if (b->order_ev) { if (b->has_order) cudaEventSynchronize(b->order_ev); cudaEventDestroy(b->order_ev); }
     if (b->stream) cudaStreamDestroy(b->stream);
     free(b);
 }
@@ -186,6 +247,7 @@ static int synth_device(LPCNetB200Batch *b, const float *d_feat, long long strea
     const long long pcm_stride = (long long)nframes * spf;
     int launches = 0;
     b->kev_used = 0;
+    if (order_enter(b, st)) return -1;
     for (int c0 = 0; c0 < nframes; c0 += CHUNK) {
         const int nf = nframes - c0 < CHUNK ? nframes - c0 : CHUNK;
         launch_frame_network(b->model, b->fs, d_feat + (size_t)c0 * frame_stride, stream_stride, frame_stride, n, nf,
@@ -199,11 +261,11 @@ static int synth_device(LPCNetB200Batch *b, const float *d_feat, long long strea
         if (silent > 0)
             CK(cudaMemset2DAsync(d_pcm + (size_t)c0 * spf, pcm_stride * sizeof(short), 0, (size_t)silent * spf * sizeof(short), n, st));
         if (nf > silent) {
-            SampleParams p;
+            SampleParams p = {};
             p.L = b->model.L; p.image = b->model.image;
             p.emb_sig = b->model.emb_sig; p.emb_pred = b->model.emb_pred; p.emb_exc = b->model.emb_exc; p.fcw = b->model.fcw;
             p.spc = streams_per_cta_for(n);
-            p.fast_cvt = b->model.fast_cvt && !getenv("LPCNET_B200_EXACT_CVT");   // env: force the conversion-unit path (tests)
+            p.fast_cvt = b->model.fast_cvt && !b->env_exact_cvt;   // env LPCNET_B200_EXACT_CVT: force the conversion-unit path (tests)
 #ifdef LPCNET_TRACE
             { static long long *d_trace = nullptr; if (!d_trace) { CK(cudaMalloc(&d_trace, 8 * 32 * 8)); CK(cudaMemset(d_trace, 0, 8 * 32 * 8)); } p.trace = d_trace; g_trace = d_trace; }
 #endif
@@ -219,7 +281,7 @@ static int synth_device(LPCNetB200Batch *b, const float *d_feat, long long strea
                 while ((int)b->kev->size() < b->kev_used + 2) { cudaEvent_t e; CK(cudaEventCreate(&e)); b->kev->push_back(e); }
                 CK(cudaEventRecord((*b->kev)[b->kev_used], st));
             }
-            if (b->model.is_float && p.spc <= FN_S && !getenv("LPCNET_B200_FLOAT_LANE_STREAM")) {
+            if (b->model.is_float && p.spc <= FN_S && !b->env_float_lane_stream) {
                 p.L = b->model.Ln; p.image = b->model.image_n;       // small batch: neuron-per-lane float kernel
                 CK(launch_sample_kernel_f32n(p, st));
             } else
@@ -231,6 +293,7 @@ static int synth_device(LPCNetB200Batch *b, const float *d_feat, long long strea
         if (b->frame_count > 1000) b->frame_count = 1000;
     }
     CK(cudaGetLastError());
+    if (order_leave(b, st)) return -1;
     b->last_launches = launches;
     return 0;
 }
@@ -255,9 +318,11 @@ int lpcnet_b200_batch_synthesize(LPCNetB200Batch *b, const float *features, int 
     CK(cudaSetDevice(b->device));
     const size_t fbytes = sizeof(float) * (size_t)b->n * nframes * feature_stride;
     const size_t pbytes = sizeof(short) * (size_t)b->n * nframes * samples_per_frame;
-    if (ensure((void **)&b->d_features, &b->d_features_cap, fbytes)) return -1;
-    if (ensure((void **)&b->d_pcm, &b->d_pcm_cap, pbytes)) return -1;
+    if (ensure(b, (void **)&b->d_features, &b->d_features_cap, fbytes)) return -1;
+    if (ensure(b, (void **)&b->d_pcm, &b->d_pcm_cap, pbytes)) return -1;
+    if (order_enter(b, b->stream)) return -1;       // the staging buffers may still be read by work on another stream
     CK(cudaMemcpyAsync(b->d_features, features, fbytes, cudaMemcpyHostToDevice, b->stream));
+    if (order_leave(b, b->stream)) return -1;
     if (synth_device(b, b->d_features, (long long)nframes * feature_stride, feature_stride, nframes, samples_per_frame, b->d_pcm, b->stream, true)) return -1;
     CK(cudaMemcpyAsync(pcm, b->d_pcm, pbytes, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaStreamSynchronize(b->stream));
@@ -268,8 +333,10 @@ static int decode_device(LPCNetB200Batch *b, const uint8_t *d_packets, int npack
 {
     if (!b->model.codebooks) { set_error("decode: no VQ codebooks loaded (lpcnet_b200_batch_set_codebooks)"); return -1; }
     const size_t fbytes = sizeof(float) * (size_t)b->n * npackets * 4 * NB_FEAT;
-    if (ensure((void **)&b->d_features, &b->d_features_cap, fbytes)) return -1;
+    if (ensure(b, (void **)&b->d_features, &b->d_features_cap, fbytes)) return -1;
+    if (order_enter(b, st)) return -1;
     launch_decode_packets(b->model, b->fs, d_packets, b->n, npackets, b->d_features, st);
+    if (order_leave(b, st)) return -1;
     int r = synth_device(b, b->d_features, (long long)npackets * 4 * NB_FEAT, NB_FEAT, npackets * 4, FRAME_SIZE, d_pcm, st, true);
     b->last_launches += 1;
     return r;
@@ -293,9 +360,11 @@ int lpcnet_b200_batch_decode(LPCNetB200Batch *b, const unsigned char *packets, i
     if (!packets || !pcm) { set_error("null buffer"); return -1; }
     CK(cudaSetDevice(b->device));
     const size_t kbytes = (size_t)b->n * npackets * 8, pbytes = sizeof(short) * (size_t)b->n * npackets * 640;
-    if (ensure((void **)&b->d_packets, &b->d_packets_cap, kbytes)) return -1;
-    if (ensure((void **)&b->d_pcm, &b->d_pcm_cap, pbytes)) return -1;
+    if (ensure(b, (void **)&b->d_packets, &b->d_packets_cap, kbytes)) return -1;
+    if (ensure(b, (void **)&b->d_pcm, &b->d_pcm_cap, pbytes)) return -1;
+    if (order_enter(b, b->stream)) return -1;
     CK(cudaMemcpyAsync(b->d_packets, packets, kbytes, cudaMemcpyHostToDevice, b->stream));
+    if (order_leave(b, b->stream)) return -1;
     if (decode_device(b, b->d_packets, npackets, b->d_pcm, b->stream)) return -1;
     CK(cudaMemcpyAsync(pcm, b->d_pcm, pbytes, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaStreamSynchronize(b->stream));
@@ -348,6 +417,7 @@ int lpcnet_b200_batch_sync(LPCNetB200Batch *b)
 {
     if (!b) { set_error("null batch"); return -1; }
     CK(cudaSetDevice(b->device));
+    if (order_sync(b)) return -1;
     CK(cudaStreamSynchronize(b->stream));
     return 0;
 }
@@ -374,7 +444,7 @@ int lpcnet_b200_batch_get_state(LPCNetB200Batch *b, int s, float *gru_a, float *
 {
     if (!b || s < 0 || s >= b->n) { set_error("bad stream index"); return -1; }
     CK(cudaSetDevice(b->device));
-    CK(cudaStreamSynchronize(b->stream));
+    if (order_sync(b)) return -1;
     const size_t n = b->n;
     if (gru_a) CK(cudaMemcpy2D(gru_a, sizeof(float), b->hA + s, n * sizeof(float), sizeof(float), NA, cudaMemcpyDeviceToHost));
     if (gru_b) CK(cudaMemcpy2D(gru_b, sizeof(float), b->hB + s, n * sizeof(float), sizeof(float), NB, cudaMemcpyDeviceToHost));
@@ -394,7 +464,8 @@ int lpcnet_b200_debug_frame_network(LPCNetB200Batch *b, const float *features, i
     CK(cudaSetDevice(b->device));
     const int n = b->n;
     const size_t fbytes = sizeof(float) * (size_t)n * nframes * feature_stride;
-    if (ensure((void **)&b->d_features, &b->d_features_cap, fbytes)) return -1;
+    if (order_sync(b)) return -1;
+    if (ensure(b, (void **)&b->d_features, &b->d_features_cap, fbytes)) return -1;
     CK(cudaMemcpyAsync(b->d_features, features, fbytes, cudaMemcpyHostToDevice, b->stream));
     launch_frame_network(b->model, b->fs, b->d_features, (long long)nframes * feature_stride, feature_stride, n, nframes,
                          b->frame_count, b->condA, b->condB, b->lpc_raw, b->stream);

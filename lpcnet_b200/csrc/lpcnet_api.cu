@@ -56,10 +56,19 @@ void check_env()     // caller holds g_mu
 }
 int device_id() { const char *d = getenv("LPCNET_B200_DEVICE"); return d ? atoi(d) : 0; }
 
-void forget(LPCNetB200Batch *b)
+// Remove a batch from the registry; true if it was registered (i.e. it is alive and owned by the caller's state).  A state
+// whose batch was already released — by drain() at exit, or because the caller's memory only LOOKS initialised — fails the
+// look-up and must not free it again.
+bool forget(LPCNetB200Batch *b)
 {
     std::lock_guard<std::mutex> l(g_mu);
-    for (size_t i = 0; i < g_registry.size(); i++) if (g_registry[i] == b) { g_registry.erase(g_registry.begin() + i); break; }
+    for (size_t i = 0; i < g_registry.size(); i++) if (g_registry[i] == b) { g_registry.erase(g_registry.begin() + i); return true; }
+    return false;
+}
+void release(LPCNetState *st)
+{
+    if (st->magic == MAGIC && st->batch && forget(st->batch)) lpcnet_b200_batch_destroy(st->batch);
+    st->batch = nullptr;
 }
 int attach_model(LPCNetState *st, const unsigned char *blob, int len, float gamma)
 {
@@ -71,7 +80,7 @@ int attach_model(LPCNetState *st, const unsigned char *blob, int len, float gamm
         g_registry.push_back(nb);
         if (!g_atexit) { atexit(drain); g_atexit = true; }
     }
-    if (st->batch) { forget(st->batch); lpcnet_b200_batch_destroy(st->batch); }
+    release(st);
     st->batch = nb;
     return 0;
 }
@@ -99,6 +108,10 @@ int lpcnet_get_size(void) { return (int)sizeof(LPCNetState); }
 int lpcnet_init(LPCNetState *st)
 {
     if (!st) return -1;
+    // re-initialising a live state (the reference allows lpcnet_init on the same memory again, src/lpcnet.c:184): release
+    // the device batch it owns first.  Uninitialised caller memory that happens to carry the magic is harmless: its batch
+    // pointer is not in the registry.
+    release(st);
     st->magic = MAGIC; st->flags = 0; st->batch = nullptr;
     std::vector<unsigned char> model; float gamma;
     { std::lock_guard<std::mutex> l(g_mu); check_env(); model = g_model; gamma = g_gamma; }
@@ -118,9 +131,13 @@ LPCNetState *lpcnet_create(void)
 void lpcnet_destroy(LPCNetState *st)
 {
     if (!st) return;
-    if (st->magic == MAGIC && st->batch) { forget(st->batch); lpcnet_b200_batch_destroy(st->batch); }
+    release(st);
     free(st);
 }
+
+/* Explicit counterpart of lpcnet_init()/lpcnet_decoder_init() on caller-owned memory (the reference needs none because
+ * its state owns no resources): frees the device batch now instead of at process exit. */
+void lpcnet_b200_deinit(LPCNetState *st) { if (st) release(st); }
 
 int lpcnet_load_model(LPCNetState *st, const unsigned char *data, int len)
 {
@@ -151,14 +168,13 @@ int lpcnet_decoder_get_size(void) { return (int)sizeof(LPCNetDecState); }
 int lpcnet_decoder_init(LPCNetDecState *st)
 {
     if (!st) return -1;
-    memset(st, 0, sizeof(*st));
-    lpcnet_init(&st->lpcnet_state);
+    lpcnet_init(&st->lpcnet_state);              // (releases a batch a previous init of this memory created)
     return 0;
 }
 
 LPCNetDecState *lpcnet_decoder_create(void)
 {
-    LPCNetDecState *st = (LPCNetDecState *)malloc(sizeof(LPCNetDecState));
+    LPCNetDecState *st = (LPCNetDecState *)calloc(1, sizeof(LPCNetDecState));
     if (!st) return nullptr;
     if (lpcnet_b200_device_count() <= 0) { set_error("lpcnet_decoder_create: no CUDA device (no CPU fallback)"); free(st); return nullptr; }
     lpcnet_decoder_init(st);
@@ -168,7 +184,7 @@ LPCNetDecState *lpcnet_decoder_create(void)
 void lpcnet_decoder_destroy(LPCNetDecState *st)
 {
     if (!st) return;
-    if (st->lpcnet_state.magic == MAGIC && st->lpcnet_state.batch) { forget(st->lpcnet_state.batch); lpcnet_b200_batch_destroy(st->lpcnet_state.batch); }
+    release(&st->lpcnet_state);
     free(st);
 }
 

@@ -166,6 +166,25 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
         p = idxB; w = wB->data;
         for (int rg = 0; rg < 3 * NB / 8; rg++) { int nb = *p++; for (int j = 0; j < nb; j++) { rowsB[rg].push_back({*p++, w}); w += src_blk; } }
     }
+    // int8 flavour: the reference multiplies pairs of inputs with _mm256_maddubs_epi16 (vec_avx.h:811-812), whose int16 pair sum
+    // SATURATES; the exact integer sums of IMMA/dp4a equal it only while no pair can saturate, i.e. (u8 activations <= 255)
+    // 255 * (|w0| + |w1|) <= 32767 for same-sign pairs and 255 * max|w| <= 32768 otherwise.  Quantisation-aware models satisfy
+    // it by construction (WeightClip, training_tf2/lpcnet.py:216-232); a blob that does not would silently diverge from the
+    // reference, so it is refused here.
+    if (!m->is_float) {
+        auto pair_ok = [](const unsigned char *w, size_t bytes) {
+            const signed char *q = reinterpret_cast<const signed char *>(w);
+            for (size_t i = 0; i + 1 < bytes; i += 2) {
+                const int a = q[i], b = q[i + 1];
+                if ((a >= 0) == (b >= 0) && 255 * (abs(a) + abs(b)) > 32767) return false;
+            }
+            return true;
+        };
+        if (!pair_ok(wA->data, wA->size) || !pair_ok(wB->data, wB->size) || !pair_ok(wBrec->data, wBrec->size)) {
+            set_error("model: int8 weights violate the pair constraint |w0|+|w1| <= 128 (maddubs would saturate in the reference; the exact integer GEMV would differ)");
+            return -1;
+        }
+    }
     // geometry of the kernel that will consume the image
     const bool is_float = m->is_float != 0;
     const int nwc = is_float ? F_NWC : NWC, gpw = NGRP / nwc, kparts = is_float ? F_KPARTS : KPARTS, nwb = 6 * kparts;

@@ -100,8 +100,13 @@ def _sparse_pack(A, have_diag):
                 idx=np.array(idx, dtype=np.int32), AQ=AQ)
 
 
-def make_model(seed=1234):
-    """Returns (arrays_common, arrays_int8, arrays_float): ordered lists of (name, type, ndarray)."""
+def make_model(seed=1234, na=None, variant=""):
+    """Returns (arrays_common, arrays_int8, arrays_float): ordered lists of (name, type, ndarray).
+    na      : GRU_A units (default 384; other sizes are the `--grua-size` models of training_tf2/train_lpcnet.py)
+    variant : "" | "clamp" (sampling tree biased towards large excitation so that the output runs into the +-32767 clamp of
+              lpcnet.c:265-269) | "dense" (GRU_A block densities 10/10/30 %)"""
+    N_A = int(na or globals()["N_A"])
+    DENSITY = (0.10, 0.10, 0.30) if variant == "dense" else globals()["DENSITY"]
     rng = np.random.default_rng(seed)
     f32 = np.float32
     common, only8, onlyf = [], [], []
@@ -167,10 +172,12 @@ def make_model(seed=1234):
         mag = 1.4 - 0.15 * b
         kern[i, :, :] *= min(1.0, 0.15 + 0.17 * b)   # coarse (large-amplitude) decisions depend less on the state
         bias[i, :] *= min(1.0, 0.15 + 0.17 * b)
-        bias[i, :] += (-mag if first else mag)
+        bias[i, :] += (-mag if first else mag) * (-0.25 if variant == "clamp" else 1.0)
     # the sign decision (node 1) must be unbiased or the output drifts to a rail through the 1/(1-0.85z^-1) de-emphasis
     kern[1, :, :] *= 0.15
     bias[1, :] = rng.normal(0.0, 0.01, size=2)
+    # (variant "clamp": the level biases above push AWAY from the centre instead: large excitation, the de-emphasised
+    # output runs into both rails)
     fl("dual_fc_weights", kern.transpose(0, 2, 1))
     fl("dual_fc_bias", bias.transpose(1, 0))
     fl("dual_fc_factor", factor.transpose(1, 0))
@@ -247,8 +254,7 @@ NNET_DATA_H = """/* Generated by oracle/gen_model.py in the format of training_t
 
 #include "nnet.h"
 
-/* This is *not* an end-to-end model */
-/* #define END2END */
+{e2e_lines}
 
 /* LPC weighting factor */
 #define LPC_GAMMA {gamma}f
@@ -358,9 +364,12 @@ DRED_H = """/* stub: nnet.c:41 includes dred_rdovae_constants.h; DRED is out of 
 """
 
 
-def write_c_sources(out):
-    fmt = dict(gamma=repr(LPC_GAMMA), delay=FEATURES_DELAY, n3a=3 * N_A, n3b=3 * N_B, embed=EMBED,
-               pembed=PITCH_EMBED, cond=COND, fin=FRAME_IN, na=N_A, nb=N_B, maxconv=3 * COND)
+def write_c_sources(out, na=None, e2e=False, delay=None, gamma=None):
+    na = int(na or N_A)
+    e2e_lines = ("/* This is an end-to-end model */\n#define END2END" if e2e
+                 else "/* This is *not* an end-to-end model */\n/* #define END2END */")
+    fmt = dict(gamma=repr(LPC_GAMMA if gamma is None else gamma), delay=FEATURES_DELAY if delay is None else delay, n3a=3 * na, n3b=3 * N_B,
+               embed=EMBED, pembed=PITCH_EMBED, cond=COND, fin=FRAME_IN, na=na, nb=N_B, maxconv=3 * COND, e2e_lines=e2e_lines)
     open(os.path.join(out, "nnet_data.h"), "w").write(NNET_DATA_H.format(**fmt))
     open(os.path.join(out, "nnet_data.c"), "w").write(NNET_DATA_C.format(**fmt))
     open(os.path.join(out, "plc_data.h"), "w").write(PLC_DATA_H)
@@ -386,17 +395,32 @@ def write_codebook_c(path, cbs):
             f.write("};\n")
 
 
-def generate(out, seed=1234, c_sources=True):
+# Model variants used by the tests (tag -> generator arguments).  Tags whose header differs from the default one
+# (sizes, END2END, FEATURES_DELAY) get their own directory oracle/_gen_<tag> and their own compiled reference
+# oracle/_ref/liblpcnet_ref_{A,B}_<tag>.so (oracle/Makefile, target `ref`).
+VARIANTS = {
+    "na256":  dict(na=256),                               # --grua-size 256
+    "na128":  dict(na=128),
+    "e2e":    dict(e2e=True, delay=2, gamma=1.0),         # END2END: LPC from the network's reflection coefficients (lpcnet.c:57-78,107-108)
+    "delay0": dict(delay=0),                              # FEATURES_DELAY 0: no look-ahead, LPC of the current frame (lpcnet.c:113-115)
+    "na256e2e": dict(na=256, e2e=True, delay=0, gamma=0.95),
+}
+
+
+def generate(out, seed=1234, c_sources=True, na=None, e2e=False, delay=None, gamma=None):
     os.makedirs(out, exist_ok=True)
-    common, only8, onlyf = make_model(seed)
+    common, only8, onlyf = make_model(seed, na=na)
     write_blob(os.path.join(out, "model_int8.bin"), common + only8)
     write_blob(os.path.join(out, "model_float.bin"), common + onlyf)
+    if na is None:      # same header, other weights: the +-32767 clamp fixture
+        c2, o8, _ = make_model(seed, variant="clamp")
+        write_blob(os.path.join(out, "model_int8_clamp.bin"), c2 + o8)
     cbs = make_codebooks()
     with open(os.path.join(out, "codebooks.bin"), "wb") as f:
         for a in cbs:
             f.write(a.tobytes())
     if c_sources:
-        write_c_sources(out)
+        write_c_sources(out, na=na, e2e=e2e, delay=delay, gamma=gamma)
         write_codebook_c(os.path.join(out, "ceps_codebooks.c"), cbs)
     return out
 
@@ -406,6 +430,11 @@ if __name__ == "__main__":
     ap.add_argument("--out", default=os.path.join(os.path.dirname(os.path.abspath(__file__)), "_gen"))
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--no-c", action="store_true")
+    ap.add_argument("--variant", default="", help="one of VARIANTS (default: the 384/16 model); output goes to <out>_<variant>")
     a = ap.parse_args()
-    generate(a.out, a.seed, not a.no_c)
-    print("generated into", a.out)
+    if a.variant:
+        generate(a.out + "_" + a.variant, a.seed, not a.no_c, **VARIANTS[a.variant])
+        print("generated into", a.out + "_" + a.variant)
+    else:
+        generate(a.out, a.seed, not a.no_c)
+        print("generated into", a.out)

@@ -86,6 +86,123 @@ int ref_frame_network(const unsigned char *blob, int len, const float *features,
     return 0;
 }
 
+/* ---- many streams on a pool of host threads (golden generation at BASELINE sizes; work queue over streams) ---- */
+typedef struct {
+    const unsigned char *blob; int len; const float *features; int stride; int nframes; short *pcm;
+    const unsigned char *packets; int npackets; int n_streams; volatile int *next; int rc;
+} pool_t;
+
+static void *pool_worker(void *arg)
+{
+    pool_t *p = (pool_t *)arg;
+    for (;;) {
+        int s = __sync_fetch_and_add(p->next, 1);
+        if (s >= p->n_streams) break;
+        if (p->packets) {
+            if (ref_decode_stream(p->blob, p->len, p->packets + (size_t)s * p->npackets * LPCNET_COMPRESSED_SIZE, p->npackets,
+                                  p->pcm + (size_t)s * p->npackets * LPCNET_PACKET_SAMPLES)) p->rc = -1;
+        } else {
+            if (ref_synth_stream(p->blob, p->len, p->features + (size_t)s * p->nframes * p->stride, p->stride, p->nframes,
+                                 p->pcm + (size_t)s * p->nframes * LPCNET_FRAME_SIZE)) p->rc = -1;
+        }
+    }
+    return NULL;
+}
+
+static int run_pool(pool_t *proto, int nthreads)
+{
+    pthread_t *th = malloc(sizeof(*th) * nthreads);
+    pool_t *ps = malloc(sizeof(*ps) * nthreads);
+    volatile int next = 0;
+    int i, rc = 0;
+    for (i = 0; i < nthreads; i++) { ps[i] = *proto; ps[i].next = &next; ps[i].rc = 0; pthread_create(&th[i], NULL, pool_worker, &ps[i]); }
+    for (i = 0; i < nthreads; i++) { pthread_join(th[i], NULL); rc |= ps[i].rc; }
+    free(th); free(ps);
+    return rc;
+}
+
+/* features [n_streams][nframes][stride] -> pcm [n_streams][nframes*160], every stream from a fresh lpcnet_create() */
+int ref_synth_batch(const unsigned char *blob, int len, const float *features, int stride, int nframes, int n_streams,
+                    int nthreads, short *pcm)
+{
+    pool_t p; memset(&p, 0, sizeof(p));
+    p.blob = blob; p.len = len; p.features = features; p.stride = stride; p.nframes = nframes; p.pcm = pcm; p.n_streams = n_streams;
+    return run_pool(&p, nthreads);
+}
+
+/* packets [n_streams][npackets][8] -> pcm [n_streams][npackets*640] */
+int ref_decode_batch(const unsigned char *blob, int len, const unsigned char *packets, int npackets, int n_streams,
+                     int nthreads, short *pcm)
+{
+    pool_t p; memset(&p, 0, sizeof(p));
+    p.blob = blob; p.len = len; p.packets = packets; p.npackets = npackets; p.pcm = pcm; p.n_streams = n_streams;
+    return run_pool(&p, nthreads);
+}
+
+/* ---- CPU baseline timing: `nthreads` independent streams, one per host thread.  State creation and
+ * model loading happen BEFORE the clock starts (all threads meet at a barrier); the timed region is the
+ * lpcnet_synthesize / lpcnet_decode calls only.  Returns wall seconds from the barrier to the last thread's finish. ---- */
+typedef struct {
+    const unsigned char *blob; int len; const float *features; int stride; int nframes; short *pcm;
+    const unsigned char *packets; pthread_barrier_t *bar; struct timespec t0, t1; int rc;
+} tjob_t;
+
+static void *timed_worker(void *arg)
+{
+    tjob_t *j = (tjob_t *)arg;
+    int i;
+    if (j->packets) {
+        LPCNetDecState *st = lpcnet_decoder_create();
+        j->rc = lpcnet_load_model((LPCNetState *)st, j->blob, j->len);
+        pthread_barrier_wait(j->bar);
+        clock_gettime(CLOCK_MONOTONIC, &j->t0);
+        if (!j->rc) for (i = 0; i < j->nframes; i++)
+            lpcnet_decode(st, j->packets + (size_t)i * LPCNET_COMPRESSED_SIZE, j->pcm + (size_t)i * LPCNET_PACKET_SAMPLES);
+        clock_gettime(CLOCK_MONOTONIC, &j->t1);
+        lpcnet_decoder_destroy(st);
+    } else {
+        LPCNetState *st = lpcnet_create();
+        j->rc = lpcnet_load_model(st, j->blob, j->len);
+        pthread_barrier_wait(j->bar);
+        clock_gettime(CLOCK_MONOTONIC, &j->t0);
+        if (!j->rc) for (i = 0; i < j->nframes; i++)
+            lpcnet_synthesize(st, j->features + (size_t)i * j->stride, j->pcm + (size_t)i * LPCNET_FRAME_SIZE, LPCNET_FRAME_SIZE);
+        clock_gettime(CLOCK_MONOTONIC, &j->t1);
+        lpcnet_destroy(st);
+    }
+    return NULL;
+}
+
+/* features: [nthreads][nframes][stride] (or packets: [nthreads][nframes][8] when `packets` != NULL, nframes = packets per
+ * stream); pcm: [nthreads][nframes*160] (or *640) */
+double ref_time_streams(const unsigned char *blob, int len, const float *features, int stride, const unsigned char *packets,
+                        int nframes, int nthreads, short *pcm)
+{
+    pthread_t *th = malloc(sizeof(*th) * nthreads);
+    tjob_t *jobs = malloc(sizeof(*jobs) * nthreads);
+    pthread_barrier_t bar;
+    double first = 0, last = 0;
+    int i;
+    pthread_barrier_init(&bar, NULL, nthreads);
+    for (i = 0; i < nthreads; i++) {
+        memset(&jobs[i], 0, sizeof(jobs[i]));
+        jobs[i].blob = blob; jobs[i].len = len; jobs[i].stride = stride; jobs[i].nframes = nframes; jobs[i].bar = &bar;
+        if (packets) { jobs[i].packets = packets + (size_t)i * nframes * LPCNET_COMPRESSED_SIZE; jobs[i].pcm = pcm + (size_t)i * nframes * LPCNET_PACKET_SAMPLES; }
+        else { jobs[i].features = features + (size_t)i * nframes * stride; jobs[i].pcm = pcm + (size_t)i * nframes * LPCNET_FRAME_SIZE; }
+        pthread_create(&th[i], NULL, timed_worker, &jobs[i]);
+    }
+    for (i = 0; i < nthreads; i++) pthread_join(th[i], NULL);
+    for (i = 0; i < nthreads; i++) {
+        double a = jobs[i].t0.tv_sec + 1e-9 * jobs[i].t0.tv_nsec, b = jobs[i].t1.tv_sec + 1e-9 * jobs[i].t1.tv_nsec;
+        if (i == 0 || a < first) first = a;
+        if (i == 0 || b > last) last = b;
+        if (jobs[i].rc) { last = first - 1; break; }
+    }
+    pthread_barrier_destroy(&bar);
+    free(th); free(jobs);
+    return last - first;     /* negative on error */
+}
+
 /* ---- CPU baseline timing: `nthreads` independent streams, each synthesising the same nframes. ---- */
 typedef struct {
     const unsigned char *blob; int len; const float *features; int stride; int nframes; short *pcm; int decode;

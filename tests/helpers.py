@@ -19,18 +19,30 @@ c_p = ctypes.c_void_p
 
 
 @functools.lru_cache(None)
-def gen_dir():
-    """Deterministically (re)generate the synthetic model files."""
-    need = ["model_int8.bin", "model_float.bin", "codebooks.bin"]
-    if not all(os.path.exists(os.path.join(GEN, n)) for n in need):
-        import gen_model
-        gen_model.generate(GEN, c_sources=os.path.isdir("/root/reference/src"))
-    return GEN
+def gen_dir(tag=""):
+    """Deterministically (re)generate the synthetic model files.  tag: "" (the default 384/16 model) or one of
+    gen_model.VARIANTS (other GRU_A sizes, END2END, FEATURES_DELAY) -> oracle/_gen_<tag>."""
+    import gen_model
+    d = GEN + ("_" + tag if tag else "")
+    need = ["model_int8.bin", "model_float.bin", "codebooks.bin"] + ([] if tag else ["model_int8_clamp.bin"])
+    if not all(os.path.exists(os.path.join(d, n)) for n in need):
+        gen_model.generate(d, c_sources=os.path.isdir("/root/reference/src"), **(gen_model.VARIANTS[tag] if tag else {}))
+    return d
 
 
 @functools.lru_cache(None)
-def blob(kind="int8"):
-    return open(os.path.join(gen_dir(), "model_%s.bin" % kind), "rb").read()
+def blob(kind="int8", tag=""):
+    """kind: int8 | float | int8_clamp (default model only)."""
+    return open(os.path.join(gen_dir(tag), "model_%s.bin" % kind), "rb").read()
+
+
+def model_config(tag=""):
+    """(lpc_gamma, features_delay, end2end) the reference bakes into nnet_data.h for this variant."""
+    import gen_model
+    v = gen_model.VARIANTS[tag] if tag else {}
+    g = v.get("gamma")
+    d = v.get("delay")
+    return (LPC_GAMMA if g is None else g, gen_model.FEATURES_DELAY if d is None else d, bool(v.get("e2e", False)))
 
 
 @functools.lru_cache(None)
@@ -104,14 +116,18 @@ def oracle_decode(packets, kind="int8", nthreads=8):
     return pcm
 
 
-def have_ref():
-    return os.path.exists(os.path.join(ORACLE, "_ref", "liblpcnet_ref_A.so"))
+def have_ref(build="A", tag=""):
+    return os.path.exists(os.path.join(ORACLE, "_ref", "liblpcnet_ref_%s%s.so" % (build, "_" + tag if tag else "")))
 
 
 @functools.lru_cache(None)
-def ref_lib(build="A"):
-    """The UNTOUCHED reference compiled by oracle/Makefile (`make ref`)."""
-    L = ctypes.CDLL(os.path.join(ORACLE, "_ref", "liblpcnet_ref_%s.so" % build))
+def ref_lib(build="A", tag=""):
+    """The UNTOUCHED reference compiled by oracle/Makefile (`make ref`); tag selects a model variant's build."""
+    L = ctypes.CDLL(os.path.join(ORACLE, "_ref", "liblpcnet_ref_%s%s.so" % (build, "_" + tag if tag else "")))
+    L.ref_synth_batch.argtypes = [ctypes.c_char_p, ctypes.c_int, c_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_p]
+    L.ref_decode_batch.argtypes = [ctypes.c_char_p, ctypes.c_int, c_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_p]
+    L.ref_time_streams.restype = ctypes.c_double
+    L.ref_time_streams.argtypes = [ctypes.c_char_p, ctypes.c_int, c_p, ctypes.c_int, c_p, ctypes.c_int, ctypes.c_int, c_p]
     L.ref_synth_stream.argtypes = [ctypes.c_char_p, ctypes.c_int, c_p, ctypes.c_int, ctypes.c_int, c_p]
     L.ref_decode_stream.argtypes = [ctypes.c_char_p, ctypes.c_int, c_p, ctypes.c_int, c_p]
     L.ref_decode_packet.argtypes = [c_p, c_p, c_p]
@@ -127,23 +143,28 @@ def ref_lib(build="A"):
     return L
 
 
-def ref_synth(features, build="A"):
-    L = ref_lib(build)
-    b = blob("float" if build == "B" else "int8")
+def ref_synth(features, build="A", tag="", kind=None, nthreads=None):
+    """features [n][T][stride] -> pcm [n][T*160] through the compiled reference (fresh lpcnet_create() per stream)."""
+    L = ref_lib(build, tag)
+    b = blob(kind or ("float" if build in ("B", "TB") else "int8"), tag)
     f = np.ascontiguousarray(features, dtype=np.float32)
     n, T, stride = f.shape
     pcm = np.zeros((n, T * 160), dtype=np.int16)
-    for s in range(n):
-        assert L.ref_synth_stream(b, len(b), f[s].ctypes.data, stride, T, pcm[s].ctypes.data) == 0
+    assert L.ref_synth_batch(b, len(b), f.ctypes.data, stride, T, n, nthreads or min(n, os.cpu_count() or 1), pcm.ctypes.data) == 0
     return pcm
 
 
-def ref_decode(packets, build="A"):
-    L = ref_lib(build)
-    b = blob("float" if build == "B" else "int8")
+def ref_decode(packets, build="A", tag="", nthreads=None):
+    L = ref_lib(build, tag)
+    b = blob("float" if build in ("B", "TB") else "int8", tag)
     p = np.ascontiguousarray(packets, dtype=np.uint8)
     n, P, _ = p.shape
     pcm = np.zeros((n, P * 640), dtype=np.int16)
-    for s in range(n):
-        assert L.ref_decode_stream(b, len(b), p[s].ctypes.data, P, pcm[s].ctypes.data) == 0
+    assert L.ref_decode_batch(b, len(b), p.ctypes.data, P, n, nthreads or min(n, os.cpu_count() or 1), pcm.ctypes.data) == 0
     return pcm
+
+
+def stream_digests(pcm):
+    """First 8 bytes of sha256 of every stream's PCM as uint64 [n] (a failing comparison names the stream)."""
+    import hashlib
+    return np.array([int.from_bytes(hashlib.sha256(np.ascontiguousarray(r).tobytes()).digest()[:8], "little") for r in pcm], dtype=np.uint64)

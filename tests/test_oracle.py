@@ -161,3 +161,35 @@ def test_rcpps_table_closed_form():
     m13 = (2 ** 25 + (2 * k + 4097) // 2) // (2 * k + 4097)            # rint(2^25 / d), d odd => no ties
     want = (np.float32(1.0) * (m13.astype(np.float64) / 8192.0)).astype(np.float32).view(np.uint32).astype(np.int64)
     np.testing.assert_array_equal(t, want)
+
+
+def test_oracle_port_matches_at_size_digests_on_a_sample_of_streams():
+    """The per-stream digests of the reference at BASELINE sizes (tests/golden/at_size_digests.npz) also pin the CPU
+    restatement: a few streams of every workload, full duration (1000 frames => frame_count saturation, lpcnet.c:119)."""
+    import os
+    from fixtures import make_feature_batch, make_packets
+    dig = np.load(os.path.join(H.GOLDEN, "at_size_digests.npz"))
+    ids = [0, 777, 4095]
+    got = H.oracle_synth(make_feature_batch(ids, 100), "int8")
+    np.testing.assert_array_equal(H.stream_digests(got), dig["config3_int8"][ids])
+    ids = [3, 255]
+    got = H.oracle_synth(make_feature_batch(ids, 1000), "float")
+    np.testing.assert_array_equal(H.stream_digests(got), dig["config2_float"][ids])
+    ids = [5, 1023]
+    got = H.oracle_decode(np.stack([make_packets(s, 250) for s in ids]), "int8")
+    np.testing.assert_array_equal(H.stream_digests(got), dig["config5_decode"][ids])
+
+
+def test_oracle_port_clamp_fixture():
+    """+-32767 clamp branch (lpcnet.c:265-269): golden from the reference with the large-excitation model."""
+    import os
+    from fixtures import make_feature_batch
+    gold = np.load(os.path.join(H.GOLDEN, "clamp_A.npz"))["pcm"]
+    assert (gold == 32767).sum() > 100 and (gold == -32767).sum() > 100
+    L = H.oracle_lib()
+    b = H.blob("int8_clamp")
+    m = L.oracle_model_create(b, len(b), H.rcp_table().ctypes.data, H.LPC_GAMMA, H.codebooks().ctypes.data)
+    f = make_feature_batch(range(4), 40)
+    pcm = np.zeros((4, 40 * 160), np.int16)
+    L.oracle_synthesize_batch(m, f.ctypes.data, 20, 4, 40, 4, pcm.ctypes.data)
+    np.testing.assert_array_equal(pcm, gold)
