@@ -11,13 +11,17 @@ A "step" = one pass of the hot path over one batch of synthetic feature frames:
 `value`  : inputs already resident in HBM, PCM left in HBM, CUDA events on the engine's stream, max over ranks.
 `e2e`    : the same step through the host-pointer C-ABI call (lpcnet_b200_batch_synthesize): pinned host features
            -> H2D -> kernels -> D2H PCM, all inside the timed region.
-`roofline`: per-sample kernel (the dominant kernel), algorithmic bytes/sample x samples per launch / its measured
-           duration.  The weights are resident in SHARED MEMORY, so the algorithmic bytes are served by SMEM/L2, not HBM:
-           `frac` is reported against the measured HBM copy peak as the contract requires and additionally against the
-           nominal aggregate SMEM bandwidth at the SM clock observed under load (`frac_of_smem_peak`).
-`cpu_baseline`: the untouched reference compiled by oracle/Makefile (oracle/_ref, build T = -Ofast AVX2/FMA) timed on
-           this box's host cores on a bounded sample of the same workload (kind "reference"); falls back to the oracle
-           port (kind "port") only if the compiled reference did not travel.
+`roofline`: per-sample kernel (the dominant kernel).  Every weight is resident in SHARED MEMORY, so the bound is the
+           L1/shared-memory data pipe, not HBM: `bound` = "smem", `achieved` = algorithmic bytes/sample (everything
+           run_sample_network must read once per sample) x samples per launch / the kernel's measured duration, `peak` = the
+           shared-memory streaming rate MEASURED in this run by the library's micro-kernel (conflict-free LDS.128 on all
+           SMs, lpcnet_b200/csrc/microbench.cu).  Because one MMA fetch serves 16 streams the algorithmic figure may exceed the
+           physical one; the physical evidence (ncu LSU-pipe %) is quoted beside it.  `sparse_gemv_frac` is the north star's
+           own measure (GRU_A weights + indices only).  HBM traffic per sample (ncu) vs the 2.5 B algorithmic is reported too.
+`cpu_baseline`: the untouched reference compiled by oracle/Makefile (oracle/_ref, timing builds T / TB = -Ofast AVX2/FMA,
+           int8 / float) on this box's host cores, one independent stream per usable hardware thread (affinity mask and
+           cgroup quota respected), state creation + model load OUTSIDE the timer; plus the 1-core figure.  Falls back to
+           the oracle port (kind "port") only if the compiled reference did not travel.
 The oracle/reference are used here ONLY as the timed CPU baseline, never as the thing measured for `value`/`e2e`.
 """
 import argparse
@@ -44,10 +48,42 @@ UNIT = "samples/s"
 
 
 def features_for(n, frames, first_stream=0):
-    """Distinct synthetic features per stream (seed 1000+s); 64 distinct trajectories tiled so set-up stays cheap."""
+    """DISTINCT synthetic features per stream (seed 1000+s), n streams starting at id `first_stream`."""
     from fixtures import make_feature_batch
-    base = make_feature_batch(range(first_stream, first_stream + 64), frames)
-    return np.ascontiguousarray(base[np.arange(n) % 64])
+    return np.ascontiguousarray(make_feature_batch(range(first_stream, first_stream + n), frames))
+
+
+def packets_for(n, npackets, first_stream=0):
+    """DISTINCT random 8-byte packets per stream (seed 2000+s)."""
+    from fixtures import make_packets
+    return np.ascontiguousarray(np.stack([make_packets(first_stream + s, npackets) for s in range(n)]))
+
+
+def host_cpu_info():
+    """What the CPU baseline can actually use: affinity mask, cgroup CPU quota, CPU model."""
+    try:
+        aff = len(os.sched_getaffinity(0))
+    except AttributeError:
+        aff = os.cpu_count() or 1
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()); per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    model = "?"
+    try:
+        model = [l.split(":")[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")][0]
+    except Exception:
+        pass
+    usable = aff if quota is None else max(1, min(aff, int(quota + 0.999)))
+    return {"os_cpu_count": os.cpu_count(), "sched_affinity": aff, "cgroup_cpu_quota": quota, "threads_used": usable, "cpu_model": model}
 
 
 class ClockSampler:
@@ -114,50 +150,79 @@ def measured_peaks():
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_reference_run(frames, nthreads, repeat=1):
-    """Times the reference's own CPU implementation (oracle/_ref build T, README flags restricted to AVX2/FMA) with one
-    independent stream per host thread.  Returns (samples_per_s, kind, cores, sample_description)."""
+CPU_WORK = {  # workload -> (reference timing build, blob kind, description)
+    "config3_int8": ("T", "int8", "lpcnet_synthesize, int8 AVX2 path (-Ofast -mavx2 -mfma)"),
+    "config2_float": ("TB", "float", "lpcnet_synthesize, float path -DDISABLE_DOT_PROD (-Ofast -mavx2 -mfma)"),
+    "config5_decode": ("T", "int8", "lpcnet_decode (8-byte packets), int8 AVX2 path (-Ofast -mavx2 -mfma)"),
+}
+
+
+def cpu_reference_run(workload, frames, nthreads):
+    """Times the reference's own CPU implementation with one independent stream per thread; state creation and model
+    load happen before the clock starts (oracle/ref_shim.c ref_time_streams).  Returns (samples_per_s, kind)."""
     import helpers as H
-    blob = H.blob("int8")
-    feats = features_for(nthreads, frames)
-    pcm = np.zeros((nthreads, frames * 160), np.int16)
-    so = os.path.join(ROOT, "oracle", "_ref", "liblpcnet_ref_T.so")
-    if os.path.exists(so):
-        L = H.ref_lib("T")
-        best = None
-        for _ in range(repeat):
-            sec = L.ref_time_synthesis(blob, len(blob), feats.ctypes.data, 20, frames, nthreads, pcm.ctypes.data)
-            best = sec if best is None else min(best, sec)
-        kind = "reference"
+    build, kind, _ = CPU_WORK[workload]
+    decode = workload == "config5_decode"
+    blob = H.blob(kind)
+    if decode:
+        npk = max(1, frames // 4)
+        pk = packets_for(nthreads, npk)
+        pcm = np.zeros((nthreads, npk * 640), np.int16)
+        samples = nthreads * max(0, npk * 4 - 2) * 160
     else:
-        L = H.oracle_lib()
-        best = L.oracle_synthesize_batch(H.oracle_model("int8"), feats.ctypes.data, 20, nthreads, frames, nthreads, pcm.ctypes.data)
-        kind = "port"
-    samples = nthreads * max(0, frames - 2) * 160          # the first two frames are silent warm-up (no network evaluation)
-    return samples / best, kind, nthreads, "%d independent streams (1 per host thread) x %d frames, lpcnet_synthesize, int8 AVX2 path" % (nthreads, frames)
+        feats = features_for(nthreads, frames)
+        pcm = np.zeros((nthreads, frames * 160), np.int16)
+        samples = nthreads * max(0, frames - 2) * 160       # the first two frames are silent warm-up (no network evaluation)
+    if H.have_ref(build):
+        L = H.ref_lib(build)
+        sec = (L.ref_time_streams(blob, len(blob), None, 0, pk.ctypes.data, npk, nthreads, pcm.ctypes.data) if decode
+               else L.ref_time_streams(blob, len(blob), feats.ctypes.data, 20, None, frames, nthreads, pcm.ctypes.data))
+        if sec <= 0:
+            raise RuntimeError("reference timing run failed")
+        return samples / sec, "reference"
+    L = H.oracle_lib()
+    if decode:
+        sec = L.oracle_decode_batch(H.oracle_model(kind), pk.ctypes.data, nthreads, npk, nthreads, pcm.ctypes.data)
+    else:
+        sec = L.oracle_synthesize_batch(H.oracle_model(kind), feats.ctypes.data, 20, nthreads, frames, nthreads, pcm.ctypes.data)
+    return samples / sec, "port"
+
+
+def cpu_baseline_record(workload, frames=250):
+    """All usable host threads + the 1-core figure on a bounded sample of the workload."""
+    info = host_cpu_info()
+    nt = info["threads_used"]
+    v1, kind = cpu_reference_run(workload, frames, 1)
+    vall, kind = cpu_reference_run(workload, frames, nt)
+    return {"value": vall, "unit": UNIT, "cores": nt, "kind": kind, "one_core_value": v1,
+            "sample": "%d independent streams (1 per usable host thread) x %d frames, %s; create/load_model outside the timer" % (nt, frames, CPU_WORK[workload][2]),
+            "host": info}
 
 
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    ncores = os.cpu_count() or 1
+    info = host_cpu_info()
+    nt = info["threads_used"]
     frames = 250                                            # ~0.15 s of CPU per thread-step at ~2.7e5 samples/s/core
     for _ in range(args.warmup):
-        cpu_reference_run(40, ncores)
+        cpu_reference_run(args.workload, 40, nt)
     t0 = time.time()
     vals = []
     for _ in range(args.steps):
-        v, kind, cores, sample = cpu_reference_run(frames, ncores)
+        v, kind = cpu_reference_run(args.workload, frames, nt)
         vals.append(v)
     total_s = time.time() - t0
     value = float(np.mean(vals))
+    v1, _ = cpu_reference_run(args.workload, frames, 1)
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total_s / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u8*s8->s32 (int8 DOT_PROD path) + f32", "data": "synthetic",
-        "config": {"workload": "config3_int8 on host CPU: one stream per host thread, reference src/ compiled -Ofast -mavx2 -mfma", "frames_per_step": frames,
-                   "streams": ncores},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "dtype": "f32" if args.workload == "config2_float" else "u8*s8->s32 (int8 DOT_PROD path) + f32", "data": "synthetic",
+        "config": {"workload": "%s on host CPU: one stream per usable host thread, reference src/ compiled by oracle/Makefile; %s" % (args.workload, CPU_WORK[args.workload][2]),
+                   "frames_per_step": frames, "streams": nt},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nt, "kind": kind, "one_core_value": v1, "host": info,
+                         "sample": "%d independent streams x %d frames per step; create/load_model outside the timer" % (nt, frames)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -210,11 +275,9 @@ def main():
     algo_total, algo_sparse = batch.algorithmic_bytes()
 
     if decode:
-        from fixtures import make_packets
-        base = np.stack([make_packets(2000 + 64 * rank + k, F // 4) for k in range(64)])
-        feats = np.ascontiguousarray(base[np.arange(n) % 64])          # "features" = packets [n][F/4][8] uint8
+        feats = packets_for(n, F // 4, first_stream=n * rank)       # "features" = packets [n][F/4][8] uint8, distinct per stream
     else:
-        feats = features_for(n, F, first_stream=64 * rank)
+        feats = features_for(n, F, first_stream=n * rank)           # distinct per stream (and per rank)
     fbytes, pbytes = feats.nbytes, n * F * 160 * 2
     d_feat = L.lpcnet_b200_device_alloc(fbytes)
     if dist is not None:                                      # under torchrun the PCM buffer is a torch tensor so NCCL can gather it
@@ -305,13 +368,17 @@ def main():
         samples_step = world * n * F * 160
         value = samples_step * args.steps / dev_s
         e2e_value = samples_step * args.steps / e2e_s
-        peak, peak_src = measured_peaks()
+        hbm_peak, hbm_src = measured_peaks()
         kms = float(np.mean(kern_ms))                        # per-sample kernel duration per launch (one launch per step here)
         samples_launch = n * F * 160
         achieved = samples_launch * algo_total / (kms * 1e-3) / 1e9
+        sparse_achieved = samples_launch * algo_sparse / (kms * 1e-3) / 1e9
         sm_mhz = clk.get("sm_mhz") or 1965.0
-        smem_peak = 128.0 * 148 * sm_mhz * 1e6 / 1e9          # nominal 128 B/clk/SM at the clock observed under load
-        tps, tsrc, l1pct = ncu_traffic_per_sample()
+        smem_nominal = 128.0 * 148 * sm_mhz * 1e6 / 1e9       # 128 B/clk/SM at the clock observed under load
+        smem = lpcnet_b200.measure_smem_peak(local)          # measured in this run (microbench.cu)
+        smem_peak = smem["lds128_gbs"]
+        tps, tsrc, l1pct = ncu_traffic_per_sample() if args.workload == "config3_int8" else (None, None, None)
+        algo_hbm = 2.0 + 20 * 4 / 160.0                        # PCM out + features in per sample
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -320,27 +387,31 @@ def main():
                                     "config2_float": "config2_float: %d streams/GPU x %d frames x 160 samples per step, float GRU arithmetic with fp16-stored weights, bit-exact vs reference build B",
                                     "config5_decode": "config5_decode: %d streams/GPU x %d frames (8-byte packets -> lpcnet_decode), int8, synthetic VQ codebooks"}[args.workload] % (n, F),
                        "streams_per_gpu": n, "frames_per_step": F, "samples_per_step": samples_step, "parallelism": "streams sharded across GPUs (dp%d), no data-path collective" % world,
-                       "l2": "256 MiB memset between timed steps (outside the event bracket)", "x_realtime_per_stream": value / world / n / 16000.0},
+                       "l2": "256 MiB memset between timed steps (outside the event bracket)", "inputs": "distinct features/packets per stream (seed 1000+s / 2000+s), every stream starts from the reference RNG seed", "x_realtime_per_stream": value / world / n / 16000.0},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(fbytes), "d2h_bytes_per_step": int(pbytes), "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": int(launches),
             "clocks": clk,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "roofline": {"bound": "smem", "achieved": achieved, "peak": smem_peak, "unit": "GB/s", "frac": achieved / smem_peak,
                          "traffic": (tps * samples_launch if tps is not None else None), "traffic_source": tsrc,
-                         "peak_source": peak_src, "kernel": "lpcnet_sample_kernel_f32" if args.workload == "config2_float" else "lpcnet_sample_kernel", "kernel_ms_per_launch": kms, "kernel_share_of_step": kms * args.steps / (dev_s * 1e3),
+                         "peak_source": "measured in this run: conflict-free LDS.128 stream on all SMs (lpcnet_b200_measure_smem_peak, csrc/microbench.cu)",
+                         "peak_detail": smem, "smem_peak_gbs_nominal": smem_nominal,
+                         "kernel": {"config2_float": "lpcnet_sample_kernel_f32n" if n <= 4 * 148 else "lpcnet_sample_kernel_f32"}.get(args.workload, "lpcnet_sample_kernel"),
+                         "kernel_ms_per_launch": kms, "kernel_share_of_step": kms * args.steps / (dev_s * 1e3),
                          "algorithmic_bytes_per_sample": algo_total, "sparse_gemv_bytes_per_sample": algo_sparse,
+                         "sparse_gemv_achieved_gbs": sparse_achieved, "sparse_gemv_frac": sparse_achieved / smem_peak,
                          "level_serving_the_bytes": "shared memory (weights resident per SM) + L2 (embedding rows)",
                          "binding_unit": "L1/shared-memory data pipe (LSU wavefronts)", "binding_unit_pct_of_peak_ncu": l1pct,
-                         "smem_peak_gbs_nominal": smem_peak, "frac_of_smem_peak": achieved / smem_peak,
-                         "sparse_gemv_achieved_gbs": samples_launch * algo_sparse / (kms * 1e-3) / 1e9,
-                         "sparse_gemv_frac_of_smem_peak": samples_launch * algo_sparse / (kms * 1e-3) / 1e9 / smem_peak},
+                         "note": "one MMA operand fetch serves 16 streams, so algorithmic bytes/s can exceed the physical pipe rate; binding_unit_pct_of_peak_ncu is the physical utilisation",
+                         "hbm": {"algorithmic_bytes_per_sample": algo_hbm, "dram_bytes_per_sample_ncu": tps,
+                                 "achieved_gbs": (tps * samples_launch / (kms * 1e-3) / 1e9 if tps is not None else None),
+                                 "peak_gbs": hbm_peak, "peak_source": hbm_src,
+                                 "note": "DRAM traffic above the 2.5 B/sample algorithmic figure is the condA/condB/lpc hand-off between the frame-rate kernels and the per-sample kernel; <1 % of the HBM peak either way"}},
             "wall_s_timed_region": wall,
         }
         if gather_ms is not None:
             out["pcm_gather"] = {"ms": gather_ms, "bytes_per_rank": int(pbytes), "backend": "nccl"}
         if world == 1 and not args.no_cpu_baseline:
-            ncores = os.cpu_count() or 1
-            v, kind, cores, sample = cpu_reference_run(400, ncores)
-            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+            out["cpu_baseline"] = cpu_baseline_record(args.workload)
         print(json.dumps(out), flush=True)
 
     L.lpcnet_b200_device_free(d_feat)

@@ -41,7 +41,9 @@
 #include "devmath.cuh"
 
 #ifndef LPCNET_RCP_ARITH
-#define LPCNET_RCP_ARITH 0     // 1: GRU_A activations use the table-free RCPPS of devmath.cuh (exact, but measured 5 % slower: 8 more instructions per look-up outweigh the saved wavefronts)
+#define LPCNET_RCP_ARITH 0     // bit mask of the GRU_A gates (1: r, 2: z, 4: candidate) whose activations use the table-free RCPPS of devmath.cuh
+                               // instead of the shared-memory table (exact either way).  The table costs ~3.4 bank-conflicted wavefronts per
+                               // look-up on the LSU pipe, the arithmetic form 8 more issue slots: all three gates arithmetic (7) measured 5 % slower
 #endif
 #ifndef LPCNET_GATHER_NOALLOC
 #define LPCNET_GATHER_NOALLOC 0
@@ -284,10 +286,21 @@ __device__ __forceinline__ void activations(const ComputeCtx &C, float (&h)[GPW]
 {
     uint8_t *smem = C.smem;
     const int gid = C.gid, t = C.t, lane = C.lane, warp = C.warp;
-#if LPCNET_RCP_ARITH
-    const RcpArith rcp = RcpArith();
+    // per-gate choice of the RCPPS implementation (LPCNET_RCP_ARITH mask)
+#if LPCNET_RCP_ARITH & 1
+    const RcpArith rcp_r = RcpArith();
 #else
-    const RcpShared rcp = C.rcp;
+    const RcpShared rcp_r = C.rcp;
+#endif
+#if LPCNET_RCP_ARITH & 2
+    const RcpArith rcp_z = RcpArith();
+#else
+    const RcpShared rcp_z = C.rcp;
+#endif
+#if LPCNET_RCP_ARITH & 4
+    const RcpArith rcp_h = RcpArith();
+#else
+    const RcpShared rcp_h = C.rcp;
 #endif
     const int nxt = cur ^ 1;
     const uint32_t xs_cur = C.xs0 + cur * XS_BYTES, lc = C.gid8 | (H << 6);
@@ -298,7 +311,7 @@ __device__ __forceinline__ void activations(const ComputeCtx &C, float (&h)[GPW]
     uint8_t *tile_hb = smem + SM_TILES + (kh & 3) * TILE_BYTES;
     const float *tile_h = reinterpret_cast<const float *>(tile_hb) + gid * GIN_ROW;
     const uint32_t mb_full = smem_u32(smem + MB_FULL), mb_empty = smem_u32(smem + MB_EMPTY);
-    (void)t; (void)warp; (void)rcp; (void)nxt; (void)xs_cur; (void)lc; (void)xs_nxt; (void)tile_r; (void)tile_z; (void)tile_h; (void)mb_full; (void)mb_empty; (void)lane;
+    (void)t; (void)warp; (void)rcp_r; (void)rcp_z; (void)rcp_h; (void)nxt; (void)xs_cur; (void)lc; (void)xs_nxt; (void)tile_r; (void)tile_z; (void)tile_h; (void)mb_full; (void)mb_empty; (void)lane;
     // ---- reset gate r (nnet.c:431-435) with the gathered input term; keep rec_h * r (nnet.c:436-440) ----
     mbar_wait(mb_full + 8 * (kr & 3), (kr >> 2) & 1);
 #pragma unroll
@@ -324,8 +337,8 @@ __device__ __forceinline__ void activations(const ComputeCtx &C, float (&h)[GPW]
                 rational2(acc_finish2(a[0], a[1]), LPCNET_SIGMOID_COEF, num, den);
                 float n0, n1, d0, d1, rh0, rh1;
                 upk2(num, n0, n1); upk2(den, d0, d1);
-                const float r0 = fmaxf(0.f, fminf(1.f, __fmaf_rn(n0, rcp_emul(d0, rcp), 0.5f)));
-                const float r1 = fmaxf(0.f, fminf(1.f, __fmaf_rn(n1, rcp_emul(d1, rcp), 0.5f)));
+                const float r0 = fmaxf(0.f, fminf(1.f, __fmaf_rn(n0, rcp_emul(d0, rcp_r), 0.5f)));
+                const float r1 = fmaxf(0.f, fminf(1.f, __fmaf_rn(n1, rcp_emul(d1, rcp_r), 0.5f)));
                 upk2(acc_finish2(ah[0], ah[1]), rh0, rh1);
                 Sh[sl][2 * jj] = __float_as_int(__fmul_rn(rh0, r0));
                 Sh[sl][2 * jj + 1] = __float_as_int(__fmul_rn(rh1, r1));
@@ -334,7 +347,7 @@ __device__ __forceinline__ void activations(const ComputeCtx &C, float (&h)[GPW]
                 for (int i = 0; i < 2; i++) {
                     const float hv = h[sl][2 * jj + i];
                     const int acc = acc_init_t<FAST>(__fadd_rn(__fadd_rn(bri[i], __fmul_rn(dri[i], hv)), gin[i])) + Sg[sl][2 * jj + i];
-                    const float r = sigmoid_approx(acc_finish_t<FAST>(acc), rcp);
+                    const float r = sigmoid_approx(acc_finish_t<FAST>(acc), rcp_r);
                     const int acch = acc_init_t<FAST>(__fadd_rn(bhi[i], __fmul_rn(dhi[i], hv))) + Sh[sl][2 * jj + i];
                     Sh[sl][2 * jj + i] = __float_as_int(__fmul_rn(acc_finish_t<FAST>(acch), r));
                 }
@@ -372,13 +385,13 @@ __device__ __forceinline__ void activations(const ComputeCtx &C, float (&h)[GPW]
                 rational2(acc_finish2(a[0], a[1]), LPCNET_SIGMOID_COEF, num, den);
                 float n0, n1, d0, d1;
                 upk2(num, n0, n1); upk2(den, d0, d1);
-                Sg[sl][2 * jj] = __float_as_int(fmaxf(0.f, fminf(1.f, __fmaf_rn(n0, rcp_emul(d0, rcp), 0.5f))));
-                Sg[sl][2 * jj + 1] = __float_as_int(fmaxf(0.f, fminf(1.f, __fmaf_rn(n1, rcp_emul(d1, rcp), 0.5f))));
+                Sg[sl][2 * jj] = __float_as_int(fmaxf(0.f, fminf(1.f, __fmaf_rn(n0, rcp_emul(d0, rcp_z), 0.5f))));
+                Sg[sl][2 * jj + 1] = __float_as_int(fmaxf(0.f, fminf(1.f, __fmaf_rn(n1, rcp_emul(d1, rcp_z), 0.5f))));
             } else {
 #pragma unroll
                 for (int i = 0; i < 2; i++) {
                     const int acc = acc_init_t<FAST>(__fadd_rn(__fadd_rn(bzi[i], __fmul_rn(dzi[i], h[sl][2 * jj + i])), gin[i])) + Sg[sl][2 * jj + i];
-                    Sg[sl][2 * jj + i] = __float_as_int(sigmoid_approx(acc_finish_t<FAST>(acc), rcp));
+                    Sg[sl][2 * jj + i] = __float_as_int(sigmoid_approx(acc_finish_t<FAST>(acc), rcp_z));
                 }
             }
         }
@@ -398,7 +411,7 @@ __device__ __forceinline__ void activations(const ComputeCtx &C, float (&h)[GPW]
                 rational2(add2(pk2(__int_as_float(Sh[sl][2 * jj]), __int_as_float(Sh[sl][2 * jj + 1])), pk2(gin[0], gin[1])), LPCNET_TANH_COEF, num, den);
                 float d0, d1, t0, t1;
                 upk2(den, d0, d1);
-                upk2(mul2(num, pk2(rcp_emul(d0, rcp), rcp_emul(d1, rcp))), t0, t1);
+                upk2(mul2(num, pk2(rcp_emul(d0, rcp_h), rcp_emul(d1, rcp_h))), t0, t1);
                 const float hh[2] = {fmaxf(-1.f, fminf(1.f, t0)), fmaxf(-1.f, fminf(1.f, t1))};
                 float hn[2];
 #pragma unroll
@@ -414,7 +427,7 @@ __device__ __forceinline__ void activations(const ComputeCtx &C, float (&h)[GPW]
             } else {
 #pragma unroll
                 for (int i = 0; i < 2; i++) {
-                    const float hh = tanh_approx(__fadd_rn(__int_as_float(Sh[sl][2 * jj + i]), gin[i]), rcp);
+                    const float hh = tanh_approx(__fadd_rn(__int_as_float(Sh[sl][2 * jj + i]), gin[i]), rcp_h);
                     const float z = __int_as_float(Sg[sl][2 * jj + i]);
                     const float hn = __fadd_rn(__fmul_rn(z, h[sl][2 * jj + i]), __fmul_rn(__fsub_rn(1.f, z), hh));
                     h[sl][2 * jj + i] = hn;
