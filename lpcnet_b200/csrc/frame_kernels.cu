@@ -40,9 +40,25 @@ struct FrameNetArgs {
     const uint16_t *rcp16;
     float *conv1_state, *conv2_state;
     const float *features; long long stream_stride; int frame_stride;
-    int n, nframes, frame_count0;
+    int n, nframes;
+    int *frame_count;        // [n] per-stream frame counter (lpcnet.c:119), read at entry, advanced by nframes (saturating at 1000) at exit
+    int na;                  // GRU_A units: gru_a_dense_feature has 3*na outputs
+    int features_delay;      // FEATURES_DELAY of the model (conv2 warm-up zeroing, lpcnet.c:101)
     float *condA, *condB;
+    float *lpc_e2e;          // END2END models: [nframes][n][16] LPC from the network's reflection coefficients (lpcnet.c:107-108), else NULL
 };
+
+// rc2lpc (lpcnet.c:57-78): reflection coefficients -> direct-form LPC, the reference's exact (unusual) recursion
+__device__ __forceinline__ void rc2lpc_dev(float *lpc, const float *rc)
+{
+    float tmp[LPC_ORDER], ntmp[LPC_ORDER];
+    for (int i = 0; i < LPC_ORDER; i++) { tmp[i] = rc[i]; ntmp[i] = 0.f; }
+    for (int i = 0; i < LPC_ORDER; i++) {
+        for (int j = 0; j <= i - 1; j++) ntmp[j] = __fadd_rn(tmp[j], __fmul_rn(tmp[i], tmp[i - j - 1]));
+        for (int k = 0; k <= i - 1; k++) tmp[k] = ntmp[k];
+    }
+    for (int i = 0; i < LPC_ORDER; i++) lpc[i] = tmp[i];
+}
 
 __global__ void __launch_bounds__(FT) frame_net_kernel(const FrameNetArgs a)
 {
@@ -50,13 +66,14 @@ __global__ void __launch_bounds__(FT) frame_net_kernel(const FrameNetArgs a)
     __shared__ __align__(16) float x2[3 * COND][TS];        // conv2 input window
     __shared__ __align__(16) float c2[COND][TS], d1[COND][TS], cd[COND][TS];
     __shared__ int pitch_s[TS];
+    __shared__ int fc_s[TS];                                // frame_count of the block's streams
     const int tid = threadIdx.x;
     const int s0 = blockIdx.x * TS;
     auto sid = [&](int k) { return min(s0 + k, a.n - 1); };   // tail block: replicate the last stream, stores masked
 
     for (int e = tid; e < 2 * FRAME_IN * TS; e += FT) { int j = e / TS, k = e % TS; xin[j][k] = a.conv1_state[(size_t)sid(k) * 2 * FRAME_IN + j]; }
     for (int e = tid; e < 2 * COND * TS; e += FT) { int j = e / TS, k = e % TS; x2[j][k] = a.conv2_state[(size_t)sid(k) * 2 * COND + j]; }
-    int frame_count = a.frame_count0;
+    if (tid < TS) fc_s[tid] = a.frame_count[sid(tid)];
     __syncthreads();
 
     for (int f = 0; f < a.nframes; f++) {
@@ -85,7 +102,7 @@ __global__ void __launch_bounds__(FT) frame_net_kernel(const FrameNetArgs a)
             for (int k = 0; k < TS; k++) y[k] = b;
             layer_accum<3 * FRAME_IN>(y, a.conv1_w, COND, tid, xin);
 #pragma unroll
-            for (int k = 0; k < TS; k++) x2[2 * COND + tid][k] = frame_count < 1 ? 0.f : tanh_approx(y[k], a.rcp16);
+            for (int k = 0; k < TS; k++) x2[2 * COND + tid][k] = fc_s[k] < 1 ? 0.f : tanh_approx(y[k], a.rcp16);
         }
         __syncthreads();
         // conv1 window shift, mem <- tmp[nb_inputs:] (nnet.c:469): two passes through registers because source and
@@ -98,14 +115,14 @@ __global__ void __launch_bounds__(FT) frame_net_kernel(const FrameNetArgs a)
             c = 0;
             for (int e = tid; e < 2 * FRAME_IN * TS; e += FT, c++) xin[e / TS][e % TS] = tmpv[c];
         }
-        // ---- conv2 (zeroed while frame_count < FEATURES_DELAY=2, lpcnet.c:101) ----
+        // ---- conv2 (zeroed while frame_count < FEATURES_DELAY, lpcnet.c:101) ----
         {
             const float b = __ldg(&a.conv2_b[tid]);
 #pragma unroll
             for (int k = 0; k < TS; k++) y[k] = b;
             layer_accum<3 * COND>(y, a.conv2_w, COND, tid, x2);
 #pragma unroll
-            for (int k = 0; k < TS; k++) c2[tid][k] = frame_count < FEATURES_DELAY ? 0.f : tanh_approx(y[k], a.rcp16);
+            for (int k = 0; k < TS; k++) c2[tid][k] = fc_s[k] < a.features_delay ? 0.f : tanh_approx(y[k], a.rcp16);
         }
         __syncthreads();
         {
@@ -135,15 +152,24 @@ __global__ void __launch_bounds__(FT) frame_net_kernel(const FrameNetArgs a)
             for (int k = 0; k < TS; k++) cd[tid][k] = tanh_approx(y[k], a.rcp16);
         }
         __syncthreads();
-        // ---- gru_a_dense_feature (128 -> 1152, linear) and gru_b_dense_feature (128 -> 48, linear) ----
-        for (int o = 0; o < 3 * NA / FT; o++) {
+        // ---- END2END: the first 16 conditioning outputs are reflection coefficients (lpcnet.c:105,107-108) ----
+        if (a.lpc_e2e && tid < TS && s0 + tid < a.n) {
+            float rc[LPC_ORDER], lp[LPC_ORDER];
+            for (int i = 0; i < LPC_ORDER; i++) rc[i] = cd[i][tid];
+            rc2lpc_dev(lp, rc);
+            float *o = a.lpc_e2e + ((size_t)f * a.n + s0 + tid) * LPC_ORDER;
+            for (int i = 0; i < LPC_ORDER; i++) o[i] = lp[i];
+        }
+        // ---- gru_a_dense_feature (128 -> 3*na, linear) and gru_b_dense_feature (128 -> 48, linear) ----
+        const int na3 = 3 * a.na;
+        for (int o = 0; o < na3 / FT; o++) {
             const int i = o * FT + tid;
             const float b = __ldg(&a.gad_b[i]);
 #pragma unroll
             for (int k = 0; k < TS; k++) y[k] = b;
-            layer_accum<COND>(y, a.gad_w, 3 * NA, i, cd);
+            layer_accum<COND>(y, a.gad_w, na3, i, cd);
 #pragma unroll
-            for (int k = 0; k < TS; k++) if (s0 + k < a.n) a.condA[((size_t)f * a.n + s0 + k) * (3 * NA) + i] = y[k];
+            for (int k = 0; k < TS; k++) if (s0 + k < a.n) a.condA[((size_t)f * a.n + s0 + k) * na3 + i] = y[k];
         }
         if (tid < 3 * NB) {
             const float b = __ldg(&a.gbd_b[tid]);
@@ -153,9 +179,11 @@ __global__ void __launch_bounds__(FT) frame_net_kernel(const FrameNetArgs a)
 #pragma unroll
             for (int k = 0; k < TS; k++) if (s0 + k < a.n) a.condB[((size_t)f * a.n + s0 + k) * (3 * NB) + tid] = y[k];
         }
-        if (frame_count < 1000) frame_count++;
         __syncthreads();
+        if (tid < TS && fc_s[tid] < 1000) fc_s[tid]++;      // lpcnet.c:119 (visible to the next frame after its first barrier)
     }
+    __syncthreads();
+    if (tid < TS && s0 + tid < a.n) a.frame_count[s0 + tid] = fc_s[tid];
     for (int e = tid; e < 2 * FRAME_IN * TS; e += FT) { int j = e / TS, k = e % TS; if (s0 + k < a.n) a.conv1_state[(size_t)(s0 + k) * 2 * FRAME_IN + j] = xin[j][k]; }
     for (int e = tid; e < 2 * COND * TS; e += FT) { int j = e / TS, k = e % TS; if (s0 + k < a.n) a.conv2_state[(size_t)(s0 + k) * 2 * COND + j] = x2[j][k]; }
 }
@@ -318,14 +346,18 @@ __global__ void lpc_carry_out_kernel(float *carry, const float *lpc_raw, int n, 
     carry[(size_t)n * LPC_ORDER + i] = lpc_raw[(size_t)nframes * n * LPC_ORDER + i];   // the one before
 }
 
+// lpc_raw [nframes+2][n][16]: entry e holds the raw (unweighted) LPC of frame e-2 of this call (entries 0,1 = the carry of the
+// previous call), so a model with FEATURES_DELAY d reads entry f + 2 - d for frame f (lpcnet.c:109-115); END2END models get the
+// network's own LPC of frame f written to entry f + 2 (and are read with d = 0).
 void launch_frame_network(const DeviceModel &m, const FrameState &fs, const float *d_features, long long stream_stride,
-                          int frame_stride, int n, int nframes, int frame_count0, float *condA, float *condB,
-                          float *lpc_raw, cudaStream_t st)
+                          int frame_stride, int n, int nframes, float *condA, float *condB, float *lpc_raw, cudaStream_t st)
 {
     FrameNetArgs fa{m.embed_pitch, m.conv1_w, m.conv1_b, m.conv2_w, m.conv2_b, m.dense1_w, m.dense1_b, m.dense2_w, m.dense2_b,
                     m.gad_w, m.gad_b, m.gbd_w, m.gbd_b, m.rcp16, fs.conv1_state, fs.conv2_state, d_features, stream_stride,
-                    frame_stride, n, nframes, frame_count0, condA, condB};
+                    frame_stride, n, nframes, fs.frame_count, m.na, m.cfg.features_delay, condA, condB,
+                    m.cfg.end2end ? lpc_raw + (size_t)2 * n * LPC_ORDER : nullptr};
     frame_net_kernel<<<(n + TS - 1) / TS, FT, 0, st>>>(fa);
+    if (m.cfg.end2end) return;                                 // no cepstrum -> LPC path, no delay line (lpcnet.c:107-108)
     const int tpb = 128;
     lpc_carry_in_kernel<<<(n * LPC_ORDER + tpb - 1) / tpb, tpb, 0, st>>>(fs.lpc_carry, lpc_raw, n);
     LpcArgs la{d_features, stream_stride, frame_stride, n, nframes, m.dct, reinterpret_cast<const c32 *>(m.twiddles), m.bitrev, lpc_raw};

@@ -105,12 +105,42 @@ struct HostModel {               // everything model_load needs after parsing, b
     const float *gad_w, *gad_b, *gbd_w, *gbd_b, *emb_sig, *emb_pred, *emb_exc;
 };
 
-static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *blob, int len, float lpc_gamma)
+// Optional metadata record of blobs written by this library's exporter (lpcnet_b200_write_blob / tools/import_nnet_data.py):
+// float [4] = {LPC_GAMMA, FEATURES_DELAY, END2END, format version}.  The reference keeps these three in the generated
+// nnet_data.h (dump_lpcnet.py:306-329), i.e. outside the blob; its parser ignores arrays it does not look up, so the record
+// does not disturb lpcnet_load_model of the reference.
+static const char *kConfigRecord = "lpcnet_b200_config";
+
+static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *blob, int len, const ModelConfig *cfg_in)
 {
     memset(m, 0, sizeof(*m));
-    m->lpc_gamma = lpc_gamma;
     std::vector<std::pair<std::string, Arr>> A;
     if (!blob || len <= 0 || !parse_blob(blob, len, A)) { set_error("model: malformed DNNw blob"); return -1; }
+    // ---- per-model switches: explicit argument > metadata record > the reference's defaults (gamma 1 = no weighting would be
+    // wrong for most models, so callers without metadata must pass it: lpcnet_b200_batch_create has the argument) ----
+    m->cfg = ModelConfig{1.0f, MAX_FEATURES_DELAY, 0};
+    if (const Arr *c = find(A, kConfigRecord)) {
+        if (c->size >= 12) { const float *v = reinterpret_cast<const float *>(c->data); m->cfg = ModelConfig{v[0], (int)v[1], v[2] != 0.f}; }
+    }
+    if (cfg_in) {
+        if (cfg_in->lpc_gamma > 0.f) m->cfg.lpc_gamma = cfg_in->lpc_gamma;
+        if (cfg_in->features_delay >= 0) m->cfg.features_delay = cfg_in->features_delay;
+        if (cfg_in->end2end >= 0) m->cfg.end2end = cfg_in->end2end;
+    }
+    if (m->cfg.features_delay < 0 || m->cfg.features_delay > MAX_FEATURES_DELAY) { set_error("model: FEATURES_DELAY %d not in 0..%d", m->cfg.features_delay, MAX_FEATURES_DELAY); return -1; }
+    // ---- GRU_A size from the blob (training_tf2/train_lpcnet.py --grua-size); GRU_B / conditioning widths are fixed ----
+    {
+        const Arr *d = find(A, "sparse_gru_a_recurrent_weights_diag");
+        if (!d || d->size % 12) { set_error("model: array 'sparse_gru_a_recurrent_weights_diag' missing"); return -1; }
+        m->na = d->size / 12;
+        if (!na_supported(m->na)) {
+            set_error("model: GRU_A has %d units; per-sample kernels are built for 128, 256 and 384 (larger models do not fit one SM's shared memory with this mapping)", m->na);
+            return -1;
+        }
+    }
+    const int NA = m->na;
+    const Geom G = make_geom(NA);
+    const int NGRP = G.ngrp;
 
 #define NEED(var, name, count) const float *var = need_f(A, name, count); if (!var) return -1;
     NEED(embed_pitch, "embed_pitch_weights", 256 * PITCH_EMBED)
@@ -216,7 +246,7 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
             nB_pad += dirB_h[rg * kparts + k][1];
         }
     }
-    const ImageMap M = is_float ? MAP_F32 : MAP_INT8;
+    const ImageMap M = is_float ? map_f32(G) : map_int8(G);
     // int8 flavour: the dual_fc rows of the upper tree levels sit right in front of the variable arrays; keep as many (64, 32, 16,
     // 8) as the model's block lists leave room for
     int fcw_nodes = FCW_SMEM_NODES;
@@ -366,7 +396,7 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
         }
         if (!is_float) {
             memcpy(&img[M.fcw], hm.fc_rows.data(), (size_t)fcw_nodes * FCW_ROW * 4);
-            *reinterpret_cast<uint32_t *>(&img[IM_FCWN]) = (uint32_t)fcw_nodes;
+            *reinterpret_cast<uint32_t *>(&img[G.im_fcwn]) = (uint32_t)fcw_nodes;
         }
         else { memcpy(&img[M.fcb], fc_b, 512 * 4); memcpy(&img[M.fcf], fc_f, 512 * 4); }
     }
@@ -397,28 +427,28 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
     if (is_float) {
         SmemLayout &Ln = m->Ln;
         memset(&Ln, 0, sizeof(Ln));
-        uint32_t o = FN_IMAGE + FNI_VAR;
+        uint32_t o = G.fn_image + G.fni_var;
         auto takeN = [&](uint32_t bytes, uint32_t align) { o = align_up(o, align); uint32_t r = o; o += bytes; return r; };
         Ln.wA = takeN((uint32_t)(nblkA + 4) * 64, 128);          // (+4 blocks / +8 meta entries of slack: the pipelined chains read ahead)
         Ln.metaA = takeN((uint32_t)(nblkA + 8) * 2, 16);
         Ln.wB = takeN((uint32_t)(nblkB + 4) * 64, 128);
         Ln.metaB = takeN((uint32_t)(nblkB + 8) * 2, 16);
         Ln.total_bytes = align_up(o, 128);
-        Ln.sm_image = FN_IMAGE;
-        Ln.image_bytes = Ln.total_bytes - FN_IMAGE;
+        Ln.sm_image = G.fn_image;
+        Ln.image_bytes = Ln.total_bytes - G.fn_image;
         Ln.nblkA_padded = (uint32_t)nblkA; Ln.nblkB_padded = (uint32_t)nblkB;
         if (!sample_kernel_smem_ok(Ln.total_bytes)) { set_error("model: %u bytes of shared memory needed by the small-batch float kernel", Ln.total_bytes); return -1; }
         std::vector<uint8_t> &im = hm.img_n;
         im.assign(Ln.image_bytes, 0);
-        memcpy(&im[FNI_RCP], kRcpTable, sizeof(kRcpTable));
-        memcpy(&im[FNI_LOGIT], &img[M.logit], 256 * 4);
-        memcpy(&im[FNI_U2L], &img[M.u2l], 256 * 4);
-        memcpy(&im[FNI_FCW], hm.fc_rows.data(), (size_t)256 * FCW_ROW * 4);
+        memcpy(&im[G.fni_rcp], kRcpTable, sizeof(kRcpTable));
+        memcpy(&im[G.fni_logit], &img[M.logit], 256 * 4);
+        memcpy(&im[G.fni_u2l], &img[M.u2l], 256 * 4);
+        memcpy(&im[G.fni_fcw], hm.fc_rows.data(), (size_t)256 * FCW_ROW * 4);
         // lanes: groups sorted by the length of their longest (candidate-gate) list so that the four groups sharing a warp are alike
         std::vector<int> ord(NGRP);
         std::iota(ord.begin(), ord.end(), 0);
         std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return rowsA[2 * NGRP + a].size() > rowsA[2 * NGRP + b].size(); });
-        uint16_t *neur = reinterpret_cast<uint16_t *>(&im[FNI_NEUR]);
+        uint16_t *neur = reinterpret_cast<uint16_t *>(&im[G.fni_neur]);
         for (int l = 0; l < NA; l++) neur[l] = (uint16_t)(8 * ord[l / 8] + (l & 7));
         // blocks: [8 rows][4 cols] fp16 (the blob holds [4 cols][8 rows] fp32), lists in blob order (gate, group), idx order inside
         auto put_t = [](uint8_t *dst, const unsigned char *src) {
@@ -426,33 +456,33 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
             __half *h = reinterpret_cast<__half *>(dst);
             for (int r = 0; r < 8; r++) for (int c = 0; c < 4; c++) h[r * 4 + c] = __float2half_rn(f[c * 8 + r]);
         };
-        uint32_t *dA = reinterpret_cast<uint32_t *>(&im[FNI_DIRA]);
-        uint16_t *mA = reinterpret_cast<uint16_t *>(&im[Ln.metaA - FN_IMAGE]);
+        uint32_t *dA = reinterpret_cast<uint32_t *>(&im[G.fni_dira]);
+        uint16_t *mA = reinterpret_cast<uint16_t *>(&im[Ln.metaA - G.fn_image]);
         uint32_t bk = 0;
         for (int g = 0; g < NGRP; g++) for (int q = 0; q < 3; q++) {
             const auto &lst = rowsA[q * NGRP + g];
             dA[(g * 3 + q) * 2 + 0] = bk; dA[(g * 3 + q) * 2 + 1] = (uint32_t)lst.size();
-            for (size_t j = 0; j < lst.size(); j++) { put_t(&im[Ln.wA - FN_IMAGE + (size_t)(bk + j) * 64], lst[j].w); mA[bk + j] = (uint16_t)(lst[j].pos * 4); }
+            for (size_t j = 0; j < lst.size(); j++) { put_t(&im[Ln.wA - G.fn_image + (size_t)(bk + j) * 64], lst[j].w); mA[bk + j] = (uint16_t)(lst[j].pos * 4); }
             bk += (uint32_t)lst.size();
         }
-        float *pa = reinterpret_cast<float *>(&im[FNI_PARA]);
+        float *pa = reinterpret_cast<float *>(&im[G.fni_para]);
         for (int q = 0; q < 3; q++) for (int j = 0; j < NA; j++) {
             pa[(q * 2 + 0) * NA + j] = ga_bias[3 * NA + q * NA + j];            // recurrent bias (nnet.c:425-430)
             pa[(q * 2 + 1) * NA + j] = ga_diag[q * NA + j];
         }
-        uint32_t *dB = reinterpret_cast<uint32_t *>(&im[FNI_DIRB]);
-        uint16_t *mB = reinterpret_cast<uint16_t *>(&im[Ln.metaB - FN_IMAGE]);
+        uint32_t *dB = reinterpret_cast<uint32_t *>(&im[G.fni_dirb]);
+        uint16_t *mB = reinterpret_cast<uint16_t *>(&im[Ln.metaB - G.fn_image]);
         bk = 0;
         for (int rg = 0; rg < 6; rg++) {
             const auto &lst = rowsB[rg];
             dB[rg * 2 + 0] = bk; dB[rg * 2 + 1] = (uint32_t)lst.size();
-            for (size_t j = 0; j < lst.size(); j++) { put_t(&im[Ln.wB - FN_IMAGE + (size_t)(bk + j) * 64], lst[j].w); mB[bk + j] = (uint16_t)(lst[j].pos * 4); }
+            for (size_t j = 0; j < lst.size(); j++) { put_t(&im[Ln.wB - G.fn_image + (size_t)(bk + j) * 64], lst[j].w); mB[bk + j] = (uint16_t)(lst[j].pos * 4); }
             bk += (uint32_t)lst.size();
         }
         Ln.wBrecF = 1;
         for (int rg = 0; rg < 6; rg++) { if (rowsB[rg].size() != NA / 4) Ln.wBrecF = 0; else for (size_t j = 0; j < rowsB[rg].size(); j++) if (rowsB[rg][j].pos != (int)(4 * j)) Ln.wBrecF = 0; }
-        memcpy(&im[FNI_PARB], gb_bias, 6 * NB * 4);
-        memcpy(&im[FNI_WBREC], wBrec->data, 3 * NB * NB * 4);
+        memcpy(&im[G.fni_parb], gb_bias, 6 * NB * 4);
+        memcpy(&im[G.fni_wbrec], wBrec->data, 3 * NB * NB * 4);
     }
     hm.embed_pitch = embed_pitch; hm.conv1_w = conv1_w; hm.conv1_b = conv1_b; hm.conv2_w = conv2_w; hm.conv2_b = conv2_b;
     hm.dense1_w = dense1_w; hm.dense1_b = dense1_b; hm.dense2_w = dense2_w; hm.dense2_b = dense2_b;
@@ -471,32 +501,34 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
 }
 
 // Test hook (no CUDA needed): build the shared-memory image on the host and hand it out.
-int debug_build_image(const unsigned char *blob, int len, unsigned char *out, size_t cap, SmemLayout *L)
+int debug_build_image(const unsigned char *blob, int len, unsigned char *out, size_t cap, SmemLayout *L, Geom *g)
 {
     DeviceModel m; HostModel hm;
-    if (build_host_model(&m, hm, blob, len, 1.0f) != 0) return -1;
-    *L = m.L;
+    if (build_host_model(&m, hm, blob, len, nullptr) != 0) return -1;
+    *L = m.L; *g = make_geom(m.na);
     if (hm.img.size() > cap) { set_error("debug image: buffer too small"); return -1; }
     memcpy(out, hm.img.data(), hm.img.size());
     return (int)hm.img.size();
 }
 
 // Same for the second image of float models (neuron-per-lane kernel).
-int debug_build_image_n(const unsigned char *blob, int len, unsigned char *out, size_t cap, SmemLayout *L)
+int debug_build_image_n(const unsigned char *blob, int len, unsigned char *out, size_t cap, SmemLayout *L, Geom *g)
 {
     DeviceModel m; HostModel hm;
-    if (build_host_model(&m, hm, blob, len, 1.0f) != 0) return -1;
+    if (build_host_model(&m, hm, blob, len, nullptr) != 0) return -1;
     if (!m.is_float) { set_error("debug image: not a float blob"); return -1; }
-    *L = m.Ln;
+    *L = m.Ln; *g = make_geom(m.na);
     if (hm.img_n.size() > cap) { set_error("debug image: buffer too small"); return -1; }
     memcpy(out, hm.img_n.data(), hm.img_n.size());
     return (int)hm.img_n.size();
 }
 
-int model_load(DeviceModel *m, const unsigned char *blob, int len, float lpc_gamma)
+int model_load(DeviceModel *m, const unsigned char *blob, int len, const ModelConfig *cfg)
 {
     HostModel hm;
-    if (build_host_model(m, hm, blob, len, lpc_gamma) != 0) return -1;
+    if (build_host_model(m, hm, blob, len, cfg) != 0) return -1;
+    const int NA = m->na;
+    const float lpc_gamma = m->cfg.lpc_gamma;
     const std::vector<uint8_t> &img = hm.img;
     const float *embed_pitch = hm.embed_pitch, *conv1_w = hm.conv1_w, *conv1_b = hm.conv1_b, *conv2_w = hm.conv2_w, *conv2_b = hm.conv2_b;
     const float *dense1_w = hm.dense1_w, *dense1_b = hm.dense1_b, *dense2_w = hm.dense2_w, *dense2_b = hm.dense2_b;

@@ -37,6 +37,9 @@
 // among themselves with two named barriers.
 #include <cstdint>
 #include <cstdlib>
+#ifndef LPCNET_NA
+#define LPCNET_NA 384          // GRU_A units this translation unit is compiled for (lpcnet_b200/build.py compiles one per supported size)
+#endif
 #include "engine.h"
 #include "devmath.cuh"
 
@@ -62,6 +65,7 @@
 #endif
 
 namespace lpcnet_b200 {
+namespace LPCNET_KNS {
 
 namespace {
 
@@ -206,9 +210,10 @@ __device__ __forceinline__ int slot_stream(int cta_s0, int hh, int si, int spc, 
 
 // Producer warps: ONE gate's input term for the 16 streams of a half,
 //   G[si][k] = ((cond[s][k] + E_sig[a_s][k]) + E_pred[b_s][k]) + E_exc[c_s][k]        (nnet.c:484-491, left to right)
-// Producer p serves tile rows si = p, p+NWP, ...: per stream the four row pointers are formed once and the 384 columns
-// of the gate are covered by three 512-byte LDG.128 per row (4 L1 lines per request), i.e. 12 independent loads in
-// flight per lane, then 12 fp32 adds and three 512-byte conflict-free STS.128 into the [16][392] tile.
+// Producer p serves tile rows si = p, p+NWP, ...: per stream the four row pointers are formed once and the NA columns
+// of the gate are covered by NA/128 512-byte LDG.128 per row (4 L1 lines per request), i.e. 4*NA/128 (12 for the default
+// 384 units) independent loads in flight per lane, then as many fp32 adds and NA/128 512-byte conflict-free STS.128 into
+// the [16][NA + 8] tile.
 template <bool ONE>
 __device__ __forceinline__ void gather_half(float *__restrict__ G, const float *__restrict__ cond_f, int n, int cta_s0, int hh, int spc,
                                             const float *__restrict__ emb_sig, const float *__restrict__ emb_pred,
@@ -225,12 +230,13 @@ __device__ __forceinline__ void gather_half(float *__restrict__ G, const float *
         const float *e0 = emb_sig + idx_h[si] * (3 * NA) + col;
         const float *e1 = emb_pred + idx_h[HALF + si] * (3 * NA) + col;
         const float *e2 = emb_exc + idx_h[2 * HALF + si] * (3 * NA) + col;
-        float4 a[3], b[3], d[3], e[3];
+        constexpr int NCH = NA / 128;
+        float4 a[NCH], b[NCH], d[NCH], e[NCH];
 #pragma unroll
-        for (int j = 0; j < 3; j++) { a[j] = GLD(c + 128 * j); b[j] = GLD(e0 + 128 * j); d[j] = GLD(e1 + 128 * j); e[j] = GLD(e2 + 128 * j); }
+        for (int j = 0; j < NCH; j++) { a[j] = GLD(c + 128 * j); b[j] = GLD(e0 + 128 * j); d[j] = GLD(e1 + 128 * j); e[j] = GLD(e2 + 128 * j); }
         float *g = G + si * GIN_ROW + lane * 4;
 #pragma unroll
-        for (int j = 0; j < 3; j++) {
+        for (int j = 0; j < NCH; j++) {
             float4 r;
             r.x = __fadd_rn(__fadd_rn(__fadd_rn(a[j].x, b[j].x), d[j].x), e[j].x);
             r.y = __fadd_rn(__fadd_rn(__fadd_rn(a[j].y, b[j].y), d[j].y), e[j].y);
@@ -701,6 +707,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
         rng.z = P.rng[s]; rng.w = P.rng[(size_t)n + s]; rng.jsr = P.rng[2 * (size_t)n + s]; rng.jcong = P.rng[3 * (size_t)n + s];
         short *pcm_out = P.pcm + (size_t)s * P.pcm_stream_stride;
         float pred = 0.f;
+        const int preload = P.fast_cvt >> 8;                             // teacher-forced samples at the start of the call's first frame (lpcnet.c:256-259)
 
         // publish the conditioning indices of the half's next sample (lpcnet.c:251-254)
         auto publish = [&]() {
@@ -767,8 +774,14 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
                     const float tot = __fadd_rn(mine, other);            // channel 0 + channel 1 (commutative: both lanes get the same bits)
                     val = (val << 1) | (thr[b] < tot ? 1 : 0);
                 }
-                const int exc = val;
-                float pcm = __fadd_rn(pred, u2l[exc]);                   // lpcnet.c:260
+                int exc = val;
+                float pcm;
+                const bool forced = f == 0 && t_ < preload;
+                if (forced) {                                            // lpcnet.c:256-259: the network ran (state, RNG advanced) but the excitation
+                    const float o = (float)pcm_out[t_];                  // is derived from the signal the caller supplied in the output buffer
+                    pcm = __fsub_rn(o, __fmul_rn(0.85f, deemph));
+                    exc = lin2ulaw(__fsub_rn(pcm, pred));
+                } else pcm = __fadd_rn(pred, u2l[exc]);                  // lpcnet.c:260
 #pragma unroll
                 for (int j = LPC_ORDER - 1; j > 0; j--) ls[j] = ls[j - 1];
                 ls[0] = pcm;
@@ -777,7 +790,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
                 deemph = pcm;
                 if (pcm < -32767) pcm = -32767;
                 if (pcm > 32767) pcm = 32767;
-                if (live) pcm_out[(size_t)f * spf + t_] = (short)__double2int_rd(0.5 + (double)pcm);   // (int)floor(.5 + pcm)
+                if (live && !forced) pcm_out[(size_t)f * spf + t_] = (short)__double2int_rd(0.5 + (double)pcm);   // (int)floor(.5 + pcm); lpcnet.c:269
                 TRACE(P, (int)(k / 6), 21 + 4 * hh, lane);
                 if (last_t && !last) load_lpc(f + 1);
                 if (!last) publish();                                    // indices of the half's next sample
@@ -794,36 +807,18 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
     }
 }
 
-// Live streams per CTA: a batch smaller than 32 x SM count is spread over all SMs (one CTA per SM, fewer live slots each)
-// instead of filling a few SMs completely: the time of a CTA-step barely depends on how many of its slots are live.
-int streams_per_cta_for(int n_streams)
-{
-    // (spc <= 16 additionally selects the half-A-only schedule, launch_sample_kernel)
-    int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-    int spc = (n_streams + sms - 1) / sms;
-    if (const char *e = getenv("LPCNET_B200_STREAMS_PER_CTA")) spc = atoi(e);
-    return spc < 1 ? 1 : spc > STREAMS_PER_CTA ? STREAMS_PER_CTA : spc;
-}
-
-int sample_kernel_smem_ok(uint32_t bytes)
-{
-    return bytes <= 227u * 1024u;
-}
-
 cudaError_t launch_sample_kernel(const SampleParams &p, cudaStream_t st)
 {
     // per-device attribute; cheap enough to set on every launch (one launch covers >= 160 x n_streams samples)
-    const bool one = p.spc <= HALF && !getenv("LPCNET_B200_TWO_HALVES");
-    auto kern = p.fast_cvt ? (one ? lpcnet_sample_kernel<true, true> : lpcnet_sample_kernel<true, false>)
+    const bool one = p.one_half != 0;                             // (decided by the caller: spc <= 16, batch_api.cu)
+    auto kern = (p.fast_cvt & 1) ? (one ? lpcnet_sample_kernel<true, true> : lpcnet_sample_kernel<true, false>)
                            : (one ? lpcnet_sample_kernel<false, true> : lpcnet_sample_kernel<false, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     const int ctas = (p.n_streams + p.spc - 1) / p.spc;
-    SampleParams q = p;
-    q.one_half = one;
-    kern<<<ctas, SAMPLE_THREADS, q.L.total_bytes, st>>>(q);
+    kern<<<ctas, SAMPLE_THREADS, p.L.total_bytes, st>>>(p);
     return cudaGetLastError();
 }
 
+}  // namespace LPCNET_KNS
 }  // namespace lpcnet_b200

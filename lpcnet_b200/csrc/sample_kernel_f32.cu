@@ -14,10 +14,14 @@
 // fp32 [384][32].  The GRU_A input term is gathered per lane (no transposition tile: shared memory is full).
 #include <cstdint>
 #include <cuda_fp16.h>
+#ifndef LPCNET_NA
+#define LPCNET_NA 384          // GRU_A units this translation unit is compiled for
+#endif
 #include "engine.h"
 #include "devmath.cuh"
 
 namespace lpcnet_b200 {
+namespace LPCNET_KNS {
 
 namespace {
 
@@ -277,8 +281,14 @@ __global__ void __launch_bounds__(F_THREADS, 1) lpcnet_sample_kernel_f32(const _
                     sum1 = __fadd_rn(sum1, sum2);
                     val = (val << 1) | (thr[b] < sum1 ? 1 : 0);
                 }
-                const int exc = val;
-                float pcm = __fadd_rn(pred, u2l[exc]);
+                int exc = val;
+                float pcm;
+                const bool forced = f == 0 && t < (P.fast_cvt >> 8);      // `preload` teacher forcing (lpcnet.c:256-259), see SampleParams::fast_cvt
+                if (forced) {
+                    const float o = (float)pcm_out[t];
+                    pcm = __fsub_rn(o, __fmul_rn(0.85f, deemph));
+                    exc = lin2ulaw(__fsub_rn(pcm, pred));
+                } else pcm = __fadd_rn(pred, u2l[exc]);
 #pragma unroll
                 for (int j = LPC_ORDER - 1; j > 0; j--) ls[j] = ls[j - 1];
                 ls[0] = pcm;
@@ -287,7 +297,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) lpcnet_sample_kernel_f32(const _
                 deemph = pcm;
                 if (pcm < -32767) pcm = -32767;
                 if (pcm > 32767) pcm = 32767;
-                if (live) pcm_out[(size_t)f * spf + t] = (short)__double2int_rd(0.5 + (double)pcm);
+                if (live && !forced) pcm_out[(size_t)f * spf + t] = (short)__double2int_rd(0.5 + (double)pcm);
             }
         }
         if (live) {
@@ -308,4 +318,5 @@ cudaError_t launch_sample_kernel_f32(const SampleParams &p, cudaStream_t st)
     return cudaGetLastError();
 }
 
+}  // namespace LPCNET_KNS
 }  // namespace lpcnet_b200

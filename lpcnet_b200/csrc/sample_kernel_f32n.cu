@@ -13,10 +13,14 @@
 //   * one sampler warp, lane == stream (same code as the other float kernel).
 #include <cstdint>
 #include <cuda_fp16.h>
+#ifndef LPCNET_NA
+#define LPCNET_NA 384          // GRU_A units this translation unit is compiled for
+#endif
 #include "engine.h"
 #include "devmath.cuh"
 
 namespace lpcnet_b200 {
+namespace LPCNET_KNS {
 
 namespace {
 
@@ -296,8 +300,14 @@ __device__ __forceinline__ void run(const SampleParams &P, uint8_t *smem)
                     sum1 = __fadd_rn(sum1, sum2);
                     val = (val << 1) | (thr[b] < sum1 ? 1 : 0);
                 }
-                const int exc = val;
-                float pcm = __fadd_rn(pred, u2l[exc]);
+                int exc = val;
+                float pcm;
+                const bool forced = f == 0 && t < (P.fast_cvt >> 8);      // `preload` teacher forcing (lpcnet.c:256-259), see SampleParams::fast_cvt
+                if (forced) {
+                    const float o = (float)pcm_out[t];
+                    pcm = __fsub_rn(o, __fmul_rn(0.85f, deemph));
+                    exc = lin2ulaw(__fsub_rn(pcm, pred));
+                } else pcm = __fadd_rn(pred, u2l[exc]);
 #pragma unroll
                 for (int k = LPC_ORDER - 1; k > 0; k--) ls[k] = ls[k - 1];
                 ls[0] = pcm;
@@ -306,7 +316,7 @@ __device__ __forceinline__ void run(const SampleParams &P, uint8_t *smem)
                 deemph = pcm;
                 if (pcm < -32767) pcm = -32767;
                 if (pcm > 32767) pcm = 32767;
-                if (live) pcm_out[(size_t)f * spf + t] = (short)__double2int_rd(0.5 + (double)pcm);
+                if (live && !forced) pcm_out[(size_t)f * spf + t] = (short)__double2int_rd(0.5 + (double)pcm);
             }
         }
         if (live) {
@@ -338,4 +348,5 @@ cudaError_t launch_sample_kernel_f32n(const SampleParams &p, cudaStream_t st)
     return cudaGetLastError();
 }
 
+}  // namespace LPCNET_KNS
 }  // namespace lpcnet_b200
