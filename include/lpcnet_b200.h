@@ -30,6 +30,16 @@ extern "C" {
 #endif
 
 typedef struct LPCNetB200Batch LPCNetB200Batch;
+typedef struct LPCNetB200Snapshot LPCNetB200Snapshot;
+
+/* The three per-model switches the reference bakes into the generated nnet_data.h (training_tf2/dump_lpcnet.py:306-329)
+ * instead of the weight blob.  A negative / non-positive field means "take it from the blob's `lpcnet_b200_config`
+ * metadata record (written by lpcnet_b200_write_blob / tools/import_nnet_data.py) or, failing that, the reference default". */
+typedef struct LPCNetB200Config {
+    float lpc_gamma;        /* LPC_GAMMA: lpc_weighting factor (src/freq.c:299-308); default 1 (none) */
+    int features_delay;     /* FEATURES_DELAY 0..2: look-ahead frames (src/lpcnet.c:101,109-115,239); default 2 */
+    int end2end;            /* END2END: LPC from the network's reflection coefficients (src/lpcnet.c:57-78,107-108); default 0 */
+} LPCNetB200Config;
 
 /* Number of usable CUDA devices (0 => the engine cannot run; there is no CPU fallback). */
 LPCNET_EXPORT int lpcnet_b200_device_count(void);
@@ -45,9 +55,20 @@ LPCNET_EXPORT int lpcnet_b200_version(void);
  * "no weighting".  Returns NULL on error. */
 LPCNET_EXPORT LPCNetB200Batch *lpcnet_b200_batch_create(int n_streams, const unsigned char *blob, int blob_len,
                                                         float lpc_gamma, int device);
+/* Same with the per-model switches given explicitly (NULL: blob metadata / defaults).  The number of GRU_A units is read
+ * from the blob (128, 256 or 384: training_tf2/train_lpcnet.py --grua-size); GRU_B = 16 and cond = 128 are fixed. */
+LPCNET_EXPORT LPCNetB200Batch *lpcnet_b200_batch_create_ex(int n_streams, const unsigned char *blob, int blob_len,
+                                                           const LPCNetB200Config *cfg, int device);
 LPCNET_EXPORT void lpcnet_b200_batch_destroy(LPCNetB200Batch *b);
+/* GRU_A units and the switches in effect. */
+LPCNET_EXPORT int lpcnet_b200_batch_model_info(const LPCNetB200Batch *b, int *gru_a_units, LPCNetB200Config *cfg);
 /* lpcnet_reset() (reference src/lpcnet.c:174) applied to every stream. */
 LPCNET_EXPORT int lpcnet_b200_batch_reset(LPCNetB200Batch *b);
+/* lpcnet_reset() for the listed streams only: they start a new utterance (two silent frames, fresh RNG) while the other
+ * streams of the batch carry on.  Every stream has its own frame counter. */
+LPCNET_EXPORT int lpcnet_b200_batch_reset_streams(LPCNetB200Batch *b, const int *streams, int count);
+/* lpcnet_reset_signal() (reference src/lpcnet.c:226-233, used by the PLC): clears the sample-rate state only. */
+LPCNET_EXPORT int lpcnet_b200_batch_reset_signal(LPCNetB200Batch *b);
 LPCNET_EXPORT int lpcnet_b200_batch_streams(const LPCNetB200Batch *b);
 
 /* VQ codebooks for the decoder front-end (reference src/lpcnet_dec.c:129-143 reads ceps_codebook1..3 [1024][17]
@@ -64,6 +85,50 @@ LPCNET_EXPORT int lpcnet_b200_batch_synthesize(LPCNetB200Batch *b, const float *
 LPCNET_EXPORT int lpcnet_b200_batch_synthesize_device(LPCNetB200Batch *b, const float *d_features, int nframes,
                                                       int feature_stride, int samples_per_frame, short *d_pcm,
                                                       void *cuda_stream);
+
+/* == lpcnet_synthesize_impl(st, features, out, N, preload) (reference src/lpcnet.c:273-277; PLC entry point) ==
+ * The first `preload` samples of the call's FIRST frame are teacher-forced: the network runs (state and RNG advance) but the
+ * excitation is derived from the signal the caller supplies in pcm[s][0..preload) and those samples are not overwritten
+ * (src/lpcnet.c:256-259,269). */
+LPCNET_EXPORT int lpcnet_b200_batch_synthesize_ex(LPCNetB200Batch *b, const float *features, int nframes,
+                                                  int feature_stride, int samples_per_frame, short *pcm, int preload);
+LPCNET_EXPORT int lpcnet_b200_batch_synthesize_device_ex(LPCNetB200Batch *b, const float *d_features, int nframes,
+                                                         int feature_stride, int samples_per_frame, short *d_pcm,
+                                                         int preload, void *cuda_stream);
+/* == the other internal entry points the reference's PLC uses (src/lpcnet_private.h:125-133), batched ==
+ * run_frame_network (src/lpcnet.c:82-120) only: advances the 100 Hz state, keeps the last frame's conditioning */
+LPCNET_EXPORT int lpcnet_b200_batch_run_frame_network(LPCNetB200Batch *b, const float *features, int nframes, int feature_stride);
+/* lpcnet_synthesize_tail_impl (src/lpcnet.c:235-271): `samples` samples with the conditioning of the last frame-network run;
+ * pcm [n_streams][samples] */
+LPCNET_EXPORT int lpcnet_b200_batch_synthesize_tail(LPCNetB200Batch *b, int samples, short *pcm, int preload);
+/* run_frame_network_deferred / run_frame_network_flush (src/lpcnet.c:122-144): queue one feature frame per stream
+ * (features [n_streams][feature_stride], at most 4 queued, older ones drop out) / run the frame network over the queue */
+LPCNET_EXPORT int lpcnet_b200_batch_frame_network_deferred(LPCNetB200Batch *b, const float *features, int feature_stride);
+LPCNET_EXPORT int lpcnet_b200_batch_frame_network_flush(LPCNetB200Batch *b);
+
+/* == state by value ==  The reference's PLC copies `LPCNetState` structs to roll back speculative synthesis
+ * (src/lpcnet_plc.c:216-230).  One stream <-> opaque host blob of lpcnet_b200_batch_state_size() bytes (everything
+ * lpcnet_reset() clears: GRU states, signal history, conv/LPC delay lines, decoder memory, RNG, frame counter): */
+LPCNET_EXPORT int lpcnet_b200_batch_state_size(const LPCNetB200Batch *b);
+LPCNET_EXPORT int lpcnet_b200_batch_export_state(LPCNetB200Batch *b, int stream, void *buf);
+LPCNET_EXPORT int lpcnet_b200_batch_import_state(LPCNetB200Batch *b, int stream, const void *buf);
+/* ... and the whole batch, device to device: */
+LPCNET_EXPORT LPCNetB200Snapshot *lpcnet_b200_batch_snapshot_create(LPCNetB200Batch *b);
+LPCNET_EXPORT void lpcnet_b200_batch_snapshot_destroy(LPCNetB200Snapshot *s);
+LPCNET_EXPORT int lpcnet_b200_batch_snapshot_save(LPCNetB200Batch *b, LPCNetB200Snapshot *s);
+LPCNET_EXPORT int lpcnet_b200_batch_snapshot_restore(LPCNetB200Batch *b, const LPCNetB200Snapshot *s);
+
+/* == multi-GPU: PCM sink ==  Streams shard across GPUs with no data-path exchange; the only transfer is the
+ * gather of the PCM.  With a sink set, every synthesize/decode `_device` call also copies each finished chunk (<= 16 frames)
+ * of its PCM to  sink[(first_row + s) * pitch_samples + t]  on a copy stream (DMA engines over NVLink, no SM time) while the next
+ * chunk is being computed; the call's stream completes only after the last copy.  `sink` may live on another device of this
+ * process (peer access) or in another process (lpcnet_b200_ipc_export on the owner, lpcnet_b200_ipc_open here).
+ * sink == NULL removes it. */
+LPCNET_EXPORT int lpcnet_b200_batch_set_pcm_sink(LPCNetB200Batch *b, short *sink, long long pitch_samples, long long first_row);
+LPCNET_EXPORT int lpcnet_b200_ipc_export(void *d_ptr, unsigned char handle[64]);
+LPCNET_EXPORT void *lpcnet_b200_ipc_open(const unsigned char handle[64]);
+LPCNET_EXPORT int lpcnet_b200_ipc_close(void *p);
+LPCNET_EXPORT int lpcnet_b200_set_device(int device);
 
 /* == lpcnet_decode() per stream, `npackets` times ==
  * packets: [n_streams][npackets][8] bytes ; pcm: [n_streams][npackets*640] int16 */

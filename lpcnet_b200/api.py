@@ -25,6 +25,31 @@ def lib():
     L.lpcnet_b200_last_error.restype = ctypes.c_char_p
     L.lpcnet_b200_batch_create.restype = c_p
     L.lpcnet_b200_batch_create.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.c_float, ctypes.c_int]
+    L.lpcnet_b200_batch_create_ex.restype = c_p
+    L.lpcnet_b200_batch_create_ex.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_int, c_p, ctypes.c_int]
+    L.lpcnet_b200_batch_model_info.argtypes = [c_p, c_p, c_p]
+    L.lpcnet_b200_batch_reset_streams.argtypes = [c_p, c_p, ctypes.c_int]
+    L.lpcnet_b200_batch_reset_signal.argtypes = [c_p]
+    L.lpcnet_b200_batch_synthesize_ex.argtypes = [c_p, c_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_p, ctypes.c_int]
+    L.lpcnet_b200_batch_synthesize_device_ex.argtypes = [c_p, c_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_p, ctypes.c_int, c_p]
+    L.lpcnet_b200_batch_run_frame_network.argtypes = [c_p, c_p, ctypes.c_int, ctypes.c_int]
+    L.lpcnet_b200_batch_synthesize_tail.argtypes = [c_p, ctypes.c_int, c_p, ctypes.c_int]
+    L.lpcnet_b200_batch_frame_network_deferred.argtypes = [c_p, c_p, ctypes.c_int]
+    L.lpcnet_b200_batch_frame_network_flush.argtypes = [c_p]
+    L.lpcnet_b200_batch_state_size.argtypes = [c_p]
+    L.lpcnet_b200_batch_export_state.argtypes = [c_p, ctypes.c_int, c_p]
+    L.lpcnet_b200_batch_import_state.argtypes = [c_p, ctypes.c_int, c_p]
+    L.lpcnet_b200_batch_snapshot_create.restype = c_p
+    L.lpcnet_b200_batch_snapshot_create.argtypes = [c_p]
+    L.lpcnet_b200_batch_snapshot_destroy.argtypes = [c_p]
+    L.lpcnet_b200_batch_snapshot_save.argtypes = [c_p, c_p]
+    L.lpcnet_b200_batch_snapshot_restore.argtypes = [c_p, c_p]
+    L.lpcnet_b200_batch_set_pcm_sink.argtypes = [c_p, c_p, ctypes.c_longlong, ctypes.c_longlong]
+    L.lpcnet_b200_ipc_export.argtypes = [c_p, c_p]
+    L.lpcnet_b200_ipc_open.restype = c_p
+    L.lpcnet_b200_ipc_open.argtypes = [c_p]
+    L.lpcnet_b200_ipc_close.argtypes = [c_p]
+    L.lpcnet_b200_set_device.argtypes = [ctypes.c_int]
     L.lpcnet_b200_batch_destroy.argtypes = [c_p]
     L.lpcnet_b200_batch_reset.argtypes = [c_p]
     L.lpcnet_b200_batch_streams.argtypes = [c_p]
@@ -89,15 +114,30 @@ def measure_smem_peak(device=0):
             "lds32_gbs": out[4], "lds32_bytes_per_clk_sm": out[5], "sms": int(out[6])}
 
 
+class Config(ctypes.Structure):
+    """LPCNetB200Config (include/lpcnet_b200.h): LPC_GAMMA / FEATURES_DELAY / END2END of the model's generated nnet_data.h."""
+    _fields_ = [("lpc_gamma", ctypes.c_float), ("features_delay", ctypes.c_int), ("end2end", ctypes.c_int)]
+
+
 class Batch:
     """n independent synthesis streams stepped in lockstep on one GPU (include/lpcnet_b200.h)."""
 
-    def __init__(self, n_streams, blob, lpc_gamma=1.0, device=0, codebooks=None):
+    def __init__(self, n_streams, blob, lpc_gamma=1.0, device=0, codebooks=None, config=None):
+        """config: (lpc_gamma, features_delay, end2end) -> lpcnet_b200_batch_create_ex; None -> lpcnet_b200_batch_create(lpc_gamma)."""
         self._L = lib()
-        self._h = self._L.lpcnet_b200_batch_create(int(n_streams), blob, len(blob), float(lpc_gamma), int(device))
+        if config is not None:
+            c = Config(float(config[0]), int(config[1]), int(config[2]))
+            self._h = self._L.lpcnet_b200_batch_create_ex(int(n_streams), blob, len(blob), ctypes.byref(c), int(device))
+        else:
+            self._h = self._L.lpcnet_b200_batch_create(int(n_streams), blob, len(blob), float(lpc_gamma), int(device))
         if not self._h:
             raise LPCNetB200Error("lpcnet_b200_batch_create: " + _err())
         self.n = int(n_streams)
+        na = ctypes.c_int(0)
+        c = Config()
+        self._L.lpcnet_b200_batch_model_info(self._h, ctypes.byref(na), ctypes.byref(c))
+        self.na = int(na.value)
+        self.config = (float(c.lpc_gamma), int(c.features_delay), int(c.end2end))
         if codebooks is not None:
             cb = np.ascontiguousarray(codebooks, dtype=np.float32)
             if self._L.lpcnet_b200_batch_set_codebooks(self._h, cb.ctypes.data, cb.size) != 0:
@@ -114,15 +154,80 @@ class Batch:
         if self._L.lpcnet_b200_batch_reset(self._h) != 0:
             raise LPCNetB200Error(_err())
 
-    def synthesize(self, features, samples_per_frame=160):
-        """features [n][T][stride>=20] float32 (host) -> pcm [n][T*samples_per_frame] int16 (host)."""
+    def synthesize(self, features, samples_per_frame=160, preload=0, pcm_in=None):
+        """features [n][T][stride>=20] float32 (host) -> pcm [n][T*samples_per_frame] int16 (host).
+        preload > 0 (lpcnet_synthesize_impl's teacher forcing): pcm_in [n][>=preload] supplies the forced samples."""
         f = np.ascontiguousarray(features, dtype=np.float32)
         assert f.ndim == 3 and f.shape[0] == self.n
         T, stride = f.shape[1], f.shape[2]
-        pcm = np.empty((self.n, T * samples_per_frame), dtype=np.int16)
-        if self._L.lpcnet_b200_batch_synthesize(self._h, f.ctypes.data, T, stride, samples_per_frame, pcm.ctypes.data) != 0:
+        pcm = np.zeros((self.n, T * samples_per_frame), dtype=np.int16)
+        if preload:
+            pcm[:, :preload] = np.asarray(pcm_in)[:, :preload]
+        if self._L.lpcnet_b200_batch_synthesize_ex(self._h, f.ctypes.data, T, stride, samples_per_frame, pcm.ctypes.data, int(preload)) != 0:
             raise LPCNetB200Error("lpcnet_b200_batch_synthesize: " + _err())
         return pcm
+
+    def reset_streams(self, streams):
+        ids = np.ascontiguousarray(streams, dtype=np.int32)
+        if self._L.lpcnet_b200_batch_reset_streams(self._h, ids.ctypes.data, int(ids.size)) != 0:
+            raise LPCNetB200Error(_err())
+
+    def reset_signal(self):
+        if self._L.lpcnet_b200_batch_reset_signal(self._h) != 0:
+            raise LPCNetB200Error(_err())
+
+    def run_frame_network(self, features):
+        f = np.ascontiguousarray(features, dtype=np.float32)
+        if self._L.lpcnet_b200_batch_run_frame_network(self._h, f.ctypes.data, f.shape[1], f.shape[2]) != 0:
+            raise LPCNetB200Error(_err())
+
+    def synthesize_tail(self, samples, preload=0, pcm_in=None):
+        pcm = np.zeros((self.n, samples), dtype=np.int16)
+        if preload:
+            pcm[:, :preload] = np.asarray(pcm_in)[:, :preload]
+        if self._L.lpcnet_b200_batch_synthesize_tail(self._h, int(samples), pcm.ctypes.data, int(preload)) != 0:
+            raise LPCNetB200Error(_err())
+        return pcm
+
+    def frame_network_deferred(self, features):
+        """features [n][stride>=20]: one frame per stream queued (run_frame_network_deferred)."""
+        f = np.ascontiguousarray(features, dtype=np.float32)
+        if self._L.lpcnet_b200_batch_frame_network_deferred(self._h, f.ctypes.data, f.shape[1]) != 0:
+            raise LPCNetB200Error(_err())
+
+    def frame_network_flush(self):
+        if self._L.lpcnet_b200_batch_frame_network_flush(self._h) != 0:
+            raise LPCNetB200Error(_err())
+
+    def export_state(self, s):
+        buf = np.zeros(self._L.lpcnet_b200_batch_state_size(self._h) // 4, dtype=np.float32)
+        if self._L.lpcnet_b200_batch_export_state(self._h, int(s), buf.ctypes.data) != 0:
+            raise LPCNetB200Error(_err())
+        return buf
+
+    def import_state(self, s, buf):
+        b = np.ascontiguousarray(buf, dtype=np.float32)
+        assert b.size * 4 == self._L.lpcnet_b200_batch_state_size(self._h)
+        if self._L.lpcnet_b200_batch_import_state(self._h, int(s), b.ctypes.data) != 0:
+            raise LPCNetB200Error(_err())
+
+    def snapshot(self):
+        """Device-side copy of the whole batch state; returns a handle for restore()/free_snapshot()."""
+        h = self._L.lpcnet_b200_batch_snapshot_create(self._h)
+        if not h or self._L.lpcnet_b200_batch_snapshot_save(self._h, h) != 0:
+            raise LPCNetB200Error(_err())
+        return h
+
+    def restore(self, snap):
+        if self._L.lpcnet_b200_batch_snapshot_restore(self._h, snap) != 0:
+            raise LPCNetB200Error(_err())
+
+    def free_snapshot(self, snap):
+        self._L.lpcnet_b200_batch_snapshot_destroy(snap)
+
+    def set_pcm_sink(self, d_ptr, pitch_samples, first_row):
+        if self._L.lpcnet_b200_batch_set_pcm_sink(self._h, d_ptr, int(pitch_samples), int(first_row)) != 0:
+            raise LPCNetB200Error(_err())
 
     def synthesize_device(self, d_features_ptr, nframes, stride, d_pcm_ptr, samples_per_frame=160, cuda_stream=None):
         r = self._L.lpcnet_b200_batch_synthesize_device(self._h, d_features_ptr, nframes, stride, samples_per_frame, d_pcm_ptr, cuda_stream)
@@ -171,7 +276,7 @@ class Batch:
         return int(a.value), int(b.value)
 
     def get_state(self, s):
-        ga = np.zeros(384, np.float32); gb = np.zeros(16, np.float32); ls = np.zeros(16, np.float32)
+        ga = np.zeros(self.na, np.float32); gb = np.zeros(16, np.float32); ls = np.zeros(16, np.float32)
         misc = np.zeros(2, np.int32); rng = np.zeros(4, np.uint32)
         if self._L.lpcnet_b200_batch_get_state(self._h, int(s), ga.ctypes.data, gb.ctypes.data, ls.ctypes.data, misc.ctypes.data, rng.ctypes.data) != 0:
             raise LPCNetB200Error(_err())
@@ -180,7 +285,7 @@ class Batch:
     def debug_frame_network(self, features):
         f = np.ascontiguousarray(features, dtype=np.float32)
         T, stride = f.shape[1], f.shape[2]
-        ga = np.zeros((self.n, T, 1152), np.float32); gb = np.zeros((self.n, T, 48), np.float32); lpc = np.zeros((self.n, T, 16), np.float32)
+        ga = np.zeros((self.n, T, 3 * self.na), np.float32); gb = np.zeros((self.n, T, 48), np.float32); lpc = np.zeros((self.n, T, 16), np.float32)
         if self._L.lpcnet_b200_debug_frame_network(self._h, f.ctypes.data, T, stride, ga.ctypes.data, gb.ctypes.data, lpc.ctypes.data) != 0:
             raise LPCNetB200Error(_err())
         return ga, gb, lpc

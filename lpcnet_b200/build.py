@@ -7,7 +7,40 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "liblpcnet_b200.so")
-SOURCES = ["model.cu", "frame_kernels.cu", "sample_kernel.cu", "sample_kernel_f32.cu", "sample_kernel_f32n.cu", "batch_api.cu", "lpcnet_api.cu", "microbench.cu"]
+HOST_SOURCES = ["model.cu", "frame_kernels.cu", "batch_api.cu", "lpcnet_api.cu", "microbench.cu", "multi_api.cu", "blob_io.cu"]
+KERNEL_SOURCES = ["sample_kernel.cu", "sample_kernel_f32.cu", "sample_kernel_f32n.cu"]   # compiled once per GRU_A size (-DLPCNET_NA=<na>, engine.h)
+NA_SIZES = [128, 256, 384]
+HOST_SOURCES = [f for f in HOST_SOURCES if os.path.exists(os.path.join(CSRC, f))]
+
+
+def units():
+    """(source file, object name, extra -D flags) of every translation unit."""
+    u = [(s, s.replace(".cu", ".o"), []) for s in HOST_SOURCES]
+    for na in NA_SIZES:
+        u += [(s, s.replace(".cu", "_na%d.o" % na), ["-DLPCNET_NA=%d" % na]) for s in KERNEL_SOURCES]
+    return u
+
+
+def _compile_all(objdir, extra_defs, log):
+    """nvcc every unit (in parallel: the nine kernel units dominate the build time)."""
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(objdir, exist_ok=True)
+
+    def one(u):
+        src, obj, defs = u
+        o = os.path.join(objdir, obj)
+        cmd = [NVCC] + FLAGS + defs + ["-D%s" % d for d in extra_defs] + ["-c", os.path.join(CSRC, src), "-o", o]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return u, o, r
+    objs = []
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        for u, o, r in ex.map(one, units()):
+            log.append("==== %s %s\n%s" % (u[0], " ".join(u[2]), r.stderr))
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError("nvcc failed on %s %s" % (u[0], u[2]))
+            objs.append(o)
+    return objs
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-fmad=false",                    # never contract a*b+c: the pinned oracle build uses -ffp-contract=off
@@ -25,18 +58,11 @@ def needs_build():
 def build_variant(name, defines):
     """Tuning aid: build lpcnet_b200/variants/lib_<name>.so with extra -D flags (e.g. LPCNET_NWC=12)."""
     vdir = os.path.join(HERE, "variants")
-    os.makedirs(os.path.join(vdir, "obj_" + name), exist_ok=True)
-    objs = []
-    for s in SOURCES:
-        o = os.path.join(vdir, "obj_" + name, s.replace(".cu", ".o"))
-        cmd = [NVCC] + FLAGS + ["-D%s" % d for d in defines] + ["-c", os.path.join(CSRC, s), "-o", o]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            sys.stderr.write(r.stdout + r.stderr)
-            raise RuntimeError("nvcc failed on " + s)
-        if s == "sample_kernel.cu":
-            print(name, [l.strip() for l in r.stderr.splitlines() if "registers" in l or "spill" in l][-2:])
-        objs.append(o)
+    log = []
+    objs = _compile_all(os.path.join(vdir, "obj_" + name), defines, log)
+    for blk in log:
+        if blk.startswith("==== sample_kernel.cu -DLPCNET_NA=384"):
+            print(name, [l.strip() for l in blk.splitlines() if "registers" in l or "spill" in l][-2:])
     so = os.path.join(vdir, "lib_%s.so" % name)
     subprocess.check_call([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", so] + objs + ["-lcudart"])
     return so
@@ -45,18 +71,8 @@ def build_variant(name, defines):
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return SO
-    objs = []
-    os.makedirs(os.path.join(HERE, "_obj"), exist_ok=True)
     log = []
-    for s in SOURCES:
-        o = os.path.join(HERE, "_obj", s.replace(".cu", ".o"))
-        cmd = [NVCC] + FLAGS + ["-c", os.path.join(CSRC, s), "-o", o]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        log.append(r.stderr)
-        if r.returncode != 0:
-            sys.stderr.write(r.stdout + r.stderr)
-            raise RuntimeError("nvcc failed on " + s)
-        objs.append(o)
+    objs = _compile_all(os.path.join(HERE, "_obj"), [], log)
     r = subprocess.run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO] + objs + ["-lcudart"],
                        capture_output=True, text=True)
     if r.returncode != 0:

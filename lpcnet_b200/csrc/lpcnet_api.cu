@@ -28,7 +28,7 @@ std::mutex g_mu;
 std::vector<LPCNetB200Batch *> g_registry;
 std::vector<unsigned char> g_model;
 std::vector<float> g_codebooks;
-float g_gamma = 1.0f;
+float g_gamma = -1.0f;      // <= 0: not given -> the blob's metadata record, else 1 (lpcnet_b200_batch_create)
 bool g_env_checked = false, g_atexit = false;
 
 void drain() { std::lock_guard<std::mutex> l(g_mu); for (auto *b : g_registry) lpcnet_b200_batch_destroy(b); g_registry.clear(); }

@@ -51,18 +51,22 @@
 #define FRAME_SIZE 160
 #define WINDOW_SIZE 320
 #define FREQ_SIZE 161
-#define N_A 384
+#define N_A_MAX 384     /* largest GRU_A the port handles; the actual size comes from the blob (OModel.na) */
 #define N_B 16
 #define COND 128
 #define PITCH_EMBED 64
 #define FRAME_IN (NB_FEATURES + PITCH_EMBED)
-#define FEATURES_DELAY 2
+#define FEATURES_DELAY_MAX 2   /* FEATURES_DELAY is a per-model value 0..2 (OModel.features_delay), dump_lpcnet.py:323-329 */
+#define MAX_FEATURE_BUFFER_SIZE 4   /* lpcnet_private.h:26 */
 #define PREEMPH 0.85f
 
 typedef struct { float r, i; } cpx;
 
 typedef struct {
     int is_float;                 /* 0: oracle A (int8), 1: oracle B (float) */
+    int na;                       /* GRU_A units (from the blob) */
+    int features_delay;           /* FEATURES_DELAY of the generated nnet_data.h */
+    int end2end;                  /* END2END of the generated nnet_data.h */
     float lpc_gamma;
     /* frame network */
     const float *embed_pitch;     /* [256][64] */
@@ -97,12 +101,14 @@ typedef struct {
     /* resettable part — mirrors struct LPCNetState (src/lpcnet_private.h:28-48) */
     float conv1_state[FRAME_IN * 2];
     float conv2_state[COND * 2];
-    float gru_a_state[N_A];
+    float gru_a_state[N_A_MAX];
     float gru_b_state[N_B];
     int last_exc;
     float last_sig[LPC_ORDER];
-    float old_lpc[FEATURES_DELAY][LPC_ORDER];
-    float gru_a_condition[3 * N_A];
+    float feature_buffer[NB_FEATURES * MAX_FEATURE_BUFFER_SIZE];
+    int feature_buffer_fill;
+    float old_lpc[FEATURES_DELAY_MAX][LPC_ORDER];
+    float gru_a_condition[3 * N_A_MAX];
     float gru_b_condition[3 * N_B];
     int frame_count;
     float deemph_mem;
@@ -420,9 +426,22 @@ static void lpc_from_cepstrum(const OModel *m, float *lpc, const float *cepstrum
 }
 
 /* ------------------------------------------------------------------ frame network ------------------------------------------------------------------ */
+static void rc2lpc(float *lpc, const float *rc)                      /* lpcnet.c:57-78 */
+{
+    int i, j, k;
+    float tmp[LPC_ORDER], ntmp[LPC_ORDER] = {0.0};
+    memcpy(tmp, rc, sizeof(tmp));
+    for (i = 0; i < LPC_ORDER; i++) {
+        for (j = 0; j <= i - 1; j++) ntmp[j] = tmp[j] + tmp[i] * tmp[i - j - 1];
+        for (k = 0; k <= i - 1; k++) tmp[k] = ntmp[k];
+    }
+    for (i = 0; i < LPC_ORDER; i++) lpc[i] = tmp[i];
+}
+
 static void run_frame_network(OState *st, const float *features)     /* lpcnet.c:82-120 */
 {
     const OModel *m = st->m;
+    const int N_A = m->na, delay = m->features_delay;
     float in[FRAME_IN], conv1_out[COND], conv2_out[COND], dense1_out[COND], condition[COND];
     float *lpc = st->lpc;
     int pitch, i;
@@ -433,14 +452,17 @@ static void run_frame_network(OState *st, const float *features)     /* lpcnet.c
     conv1d(m, conv1_out, st->conv1_state, m->conv1_w, m->conv1_b, FRAME_IN, COND, in);
     if (st->frame_count < 1) memset(conv1_out, 0, sizeof(conv1_out));
     conv1d(m, conv2_out, st->conv2_state, m->conv2_w, m->conv2_b, COND, COND, conv1_out);
-    if (st->frame_count < FEATURES_DELAY) memset(conv2_out, 0, sizeof(conv2_out));
+    if (st->frame_count < delay) memset(conv2_out, 0, sizeof(conv2_out));
     dense(m, dense1_out, m->dense1_w, m->dense1_b, COND, COND, conv2_out, 1);
     dense(m, condition, m->dense2_w, m->dense2_b, COND, COND, dense1_out, 1);
     dense(m, st->gru_a_condition, m->gad_w, m->gad_b, COND, 3 * N_A, condition, 0);
     dense(m, st->gru_b_condition, m->gbd_w, m->gbd_b, COND, 3 * N_B, condition, 0);
-    memcpy(lpc, st->old_lpc[FEATURES_DELAY - 1], sizeof(float) * LPC_ORDER);
-    memmove(st->old_lpc[1], st->old_lpc[0], (FEATURES_DELAY - 1) * LPC_ORDER * sizeof(float));
-    lpc_from_cepstrum(m, st->old_lpc[0], features);
+    if (m->end2end) rc2lpc(lpc, condition);                        /* lpcnet.c:105,107-108 */
+    else if (delay > 0) {                                          /* lpcnet.c:109-112 */
+        memcpy(lpc, st->old_lpc[delay - 1], sizeof(float) * LPC_ORDER);
+        memmove(st->old_lpc[1], st->old_lpc[0], (delay - 1) * LPC_ORDER * sizeof(float));
+        lpc_from_cepstrum(m, st->old_lpc[0], features);
+    } else lpc_from_cepstrum(m, lpc, features);                    /* lpcnet.c:113-115 */
     {   /* lpc_weighting freq.c:299-308 */
         float gamma_i = m->lpc_gamma;
         for (i = 0; i < LPC_ORDER; i++) { lpc[i] *= gamma_i; gamma_i *= m->lpc_gamma; }
@@ -457,7 +479,7 @@ static void sparse_gemv(const OModel *m, float *out, const void *wv, int rows, i
 {
     int i, j, r, c;
     if (!m->is_float) {
-        const signed char *w = wv; unsigned char x[N_A];
+        const signed char *w = wv; unsigned char x[N_A_MAX];
         for (i = 0; i < cols; i++) x[i] = quant_u8(xin[i]);
         for (i = 0; i < rows; i += 8) {
             int nb = *idx++; int32_t acc[8];
@@ -487,7 +509,8 @@ static void sparse_gemv(const OModel *m, float *out, const void *wv, int rows, i
 static int run_sample_network(OState *st, int last_exc, int last_sig, int pred)     /* lpcnet.c:146-167 */
 {
     const OModel *m = st->m;
-    float gin[3 * N_A], recur[3 * N_A], zrh[3 * N_B], rec_b[3 * N_B];
+    const int N_A = m->na;
+    float gin[3 * N_A_MAX], recur[3 * N_A_MAX], zrh[3 * N_B], rec_b[3 * N_B];
     float *state = st->gru_a_state, *sb = st->gru_b_state;
     const float *bias;
     int i, k, b, j, val = 0;
@@ -545,10 +568,10 @@ static int run_sample_network(OState *st, int last_exc, int last_sig, int pred) 
     return val;
 }
 
-static void synthesize_tail(OState *st, short *output, int N)    /* lpcnet.c:235-271 (preload == 0) */
+static void synthesize_tail(OState *st, short *output, int N, int preload)    /* lpcnet_synthesize_tail_impl lpcnet.c:235-271 */
 {
     int i, j;
-    if (st->frame_count <= FEATURES_DELAY) { memset(output, 0, sizeof(short) * N); return; }
+    if (st->frame_count <= st->m->features_delay) { memset(output, 0, sizeof(short) * N); return; }
     for (i = 0; i < N; i++) {
         float pcm, pred = 0; int exc, last_sig_ulaw, pred_ulaw;
         for (j = 0; j < LPC_ORDER; j++) pred -= st->last_sig[j] * st->lpc[j];
@@ -556,7 +579,10 @@ static void synthesize_tail(OState *st, short *output, int N)    /* lpcnet.c:235
         pred_ulaw = lin2ulaw(pred);
         exc = run_sample_network(st, st->last_exc, last_sig_ulaw, pred_ulaw);
         if (st->trace_exc) st->trace_exc[i] = exc;
-        pcm = pred + st->m->ulaw2lin_tab[exc];
+        if (i < preload) {                                         /* lpcnet.c:256-259 */
+            exc = lin2ulaw(output[i] - PREEMPH * st->deemph_mem - pred);
+            pcm = output[i] - PREEMPH * st->deemph_mem;
+        } else pcm = pred + st->m->ulaw2lin_tab[exc];
         memmove(&st->last_sig[1], &st->last_sig[0], (LPC_ORDER - 1) * sizeof(float));
         st->last_sig[0] = pcm;
         st->last_exc = exc;
@@ -564,7 +590,7 @@ static void synthesize_tail(OState *st, short *output, int N)    /* lpcnet.c:235
         st->deemph_mem = pcm;
         if (pcm < -32767) pcm = -32767;
         if (pcm > 32767) pcm = 32767;
-        output[i] = (int)floor(.5 + pcm);
+        if (i >= preload) output[i] = (int)floor(.5 + pcm);
     }
 }
 
@@ -613,14 +639,18 @@ static void decode_packet(OState *st, float features[4][NB_TOTAL_FEATURES], cons
 }
 
 /* ------------------------------------------------------------------ public test API ------------------------------------------------------------------ */
-OModel *oracle_model_create(const unsigned char *blob_in, int len, const uint32_t *rcp_table, float lpc_gamma,
-                            const float *codebooks /* may be NULL */)
+/* features_delay / end2end: what the reference bakes into the generated nnet_data.h (FEATURES_DELAY, END2END) */
+OModel *oracle_model_create_ex(const unsigned char *blob_in, int len, const uint32_t *rcp_table, float lpc_gamma,
+                               int features_delay, int end2end, const float *codebooks /* may be NULL */)
 {
     OModel *m = calloc(1, sizeof(*m));
     unsigned char *d = malloc(len);
-    int tb_a = 0, tb_b = 0, sz = -1;
+    int tb_a = 0, tb_b = 0, sz = -1, N_A;
     memcpy(d, blob_in, len);
-    m->blob_copy = d; m->lpc_gamma = lpc_gamma;
+    m->blob_copy = d; m->lpc_gamma = lpc_gamma; m->features_delay = features_delay; m->end2end = end2end;
+    if (features_delay < 0 || features_delay > FEATURES_DELAY_MAX) goto fail;
+    if (!find_array(d, len, "sparse_gru_a_recurrent_weights_diag", &sz) || sz % 12 || sz / 12 > N_A_MAX) goto fail;
+    N_A = m->na = sz / 12; sz = -1;
     memcpy(m->rcp, rcp_table, sizeof(m->rcp));
     build_tables(m);
 #define F(field, name, count) if (!(m->field = need(d, len, name, (count) * 4))) { fprintf(stderr, "oracle: bad array %s\n", name); goto fail; }
@@ -654,6 +684,11 @@ OModel *oracle_model_create(const unsigned char *blob_in, int len, const uint32_
 fail:
     free(d); free(m); return NULL;
 }
+OModel *oracle_model_create(const unsigned char *blob_in, int len, const uint32_t *rcp_table, float lpc_gamma, const float *codebooks)
+{
+    return oracle_model_create_ex(blob_in, len, rcp_table, lpc_gamma, 2, 0, codebooks);
+}
+int oracle_model_na(const OModel *m) { return m->na; }
 void oracle_model_destroy(OModel *m) { if (m) { free(m->blob_copy); free(m->cb_copy); free(m); } }
 int oracle_model_is_float(const OModel *m) { return m->is_float; }
 
@@ -665,13 +700,56 @@ void oracle_reset(OState *st)                                   /* lpcnet_reset 
     st->last_exc = lin2ulaw(0.f);
     kiss99_srand(&st->rng, (const unsigned char *)"LPCNet", 6);
 }
+int oracle_state_size(void) { return (int)sizeof(OState); }
 OState *oracle_state_create(const OModel *m) { OState *st = calloc(1, sizeof(*st)); st->m = m; oracle_reset(st); return st; }
 void oracle_state_destroy(OState *st) { free(st); }
 
-void oracle_synthesize(OState *st, const float *features, short *output, int N)   /* lpcnet_synthesize lpcnet.c:273-281 */
+void oracle_synthesize_impl(OState *st, const float *features, short *output, int N, int preload)   /* lpcnet_synthesize_impl lpcnet.c:273-277 */
 {
     run_frame_network(st, features);
-    synthesize_tail(st, output, N);
+    synthesize_tail(st, output, N, preload);
+}
+void oracle_synthesize(OState *st, const float *features, short *output, int N)   /* lpcnet_synthesize lpcnet.c:279-281 */
+{
+    oracle_synthesize_impl(st, features, output, N, 0);
+}
+/* the other internal entry points the PLC uses (lpcnet_private.h:125-133) */
+void oracle_run_frame_network(OState *st, const float *features) { run_frame_network(st, features); }
+void oracle_synthesize_tail(OState *st, short *output, int N, int preload) { synthesize_tail(st, output, N, preload); }
+void oracle_frame_network_deferred(OState *st, const float *features)             /* run_frame_network_deferred lpcnet.c:122-132 */
+{
+    const int max_buffer_size = 3 + 3 - 2;
+    if (st->feature_buffer_fill == max_buffer_size) memmove(st->feature_buffer, &st->feature_buffer[NB_FEATURES], (max_buffer_size - 1) * NB_FEATURES * sizeof(float));
+    else st->feature_buffer_fill++;
+    memcpy(&st->feature_buffer[(st->feature_buffer_fill - 1) * NB_FEATURES], features, NB_FEATURES * sizeof(float));
+}
+void oracle_frame_network_flush(OState *st)                                       /* run_frame_network_flush lpcnet.c:134-144 */
+{
+    int i;
+    for (i = 0; i < st->feature_buffer_fill; i++) run_frame_network(st, &st->feature_buffer[i * NB_FEATURES]);
+    st->feature_buffer_fill = 0;
+}
+void oracle_reset_signal(OState *st)                                              /* lpcnet_reset_signal lpcnet.c:226-233 */
+{
+    st->deemph_mem = 0; st->last_exc = lin2ulaw(0.f);
+    memset(st->last_sig, 0, sizeof(st->last_sig)); memset(st->gru_a_state, 0, sizeof(st->gru_a_state)); memset(st->gru_b_state, 0, sizeof(st->gru_b_state));
+}
+/* The state in the layout of lpcnet_b200_batch_export_state (include/lpcnet_b200.h): floats hA[na] hB[16] last_sig[16] deemph
+ * conv1[168] conv2[256] old_lpc[0][16] old_lpc[1][16] vq_mem[18], then ints last_exc, frame_count, rng[4]. */
+int oracle_export_state(const OState *st, float *buf)
+{
+    const int na = st->m->na; int o = 0, iv[6];
+    memcpy(buf + o, st->gru_a_state, na * 4); o += na;
+    memcpy(buf + o, st->gru_b_state, N_B * 4); o += N_B;
+    memcpy(buf + o, st->last_sig, LPC_ORDER * 4); o += LPC_ORDER;
+    buf[o++] = st->deemph_mem;
+    memcpy(buf + o, st->conv1_state, sizeof(st->conv1_state)); o += 2 * FRAME_IN;
+    memcpy(buf + o, st->conv2_state, sizeof(st->conv2_state)); o += 2 * COND;
+    memcpy(buf + o, st->old_lpc, sizeof(st->old_lpc)); o += 2 * LPC_ORDER;
+    memcpy(buf + o, st->vq_mem, sizeof(st->vq_mem)); o += NB_BANDS;
+    iv[0] = st->last_exc; iv[1] = st->frame_count; memcpy(&iv[2], &st->rng, 16);
+    memcpy(buf + o, iv, sizeof(iv)); o += 6;
+    return o * 4;
 }
 void oracle_synthesize_trace(OState *st, const float *features, short *output, int N, int *exc)
 {
@@ -693,7 +771,7 @@ void oracle_decode_packet(OState *st, float *features /*[4][36]*/, const unsigne
 void oracle_frame_network(OState *st, const float *features, float *ga /*1152*/, float *gb /*48*/, float *lpc /*16*/)
 {
     run_frame_network(st, features);
-    memcpy(ga, st->gru_a_condition, sizeof(st->gru_a_condition));
+    memcpy(ga, st->gru_a_condition, sizeof(float) * 3 * st->m->na);
     memcpy(gb, st->gru_b_condition, sizeof(st->gru_b_condition));
     memcpy(lpc, st->lpc, sizeof(st->lpc));
 }
@@ -707,7 +785,7 @@ float oracle_sigmoid(const OModel *m, float x) { return sigmoid_a(m, x); }
 int oracle_lin2ulaw(float x) { return lin2ulaw(x); }
 void oracle_get_state(const OState *st, float *gru_a /*384*/, float *gru_b /*16*/, float *last_sig /*16*/, int *misc /*[last_exc, frame_count]*/, uint32_t *rng /*4*/)
 {
-    memcpy(gru_a, st->gru_a_state, sizeof(st->gru_a_state)); memcpy(gru_b, st->gru_b_state, sizeof(st->gru_b_state));
+    memcpy(gru_a, st->gru_a_state, sizeof(float) * st->m->na); memcpy(gru_b, st->gru_b_state, sizeof(st->gru_b_state));
     memcpy(last_sig, st->last_sig, sizeof(st->last_sig)); misc[0] = st->last_exc; misc[1] = st->frame_count;
     memcpy(rng, &st->rng, 16);
 }

@@ -86,6 +86,28 @@ int ref_frame_network(const unsigned char *blob, int len, const float *features,
     return 0;
 }
 
+/* ---- the internal entry points the reference's PLC uses (lpcnet_private.h:125-133) on an explicit state handle, so that the
+ * tests can drive the same call sequence on the reference, the oracle port and the engine ---- */
+void *ref_state_create(const unsigned char *blob, int len)
+{
+    LPCNetState *st = lpcnet_create();
+    if (lpcnet_load_model(st, blob, len) != 0) { lpcnet_destroy(st); return NULL; }
+    return st;
+}
+void ref_state_destroy(void *st) { lpcnet_destroy((LPCNetState *)st); }
+void ref_state_reset(void *st) { lpcnet_reset((LPCNetState *)st); }
+void ref_state_copy(void *dst, const void *src) { *(LPCNetState *)dst = *(const LPCNetState *)src; }   /* what lpcnet_plc.c:216-230 does */
+void ref_synthesize_impl(void *st, const float *features, short *out, int N, int preload) { lpcnet_synthesize_impl((LPCNetState *)st, features, out, N, preload); }
+void ref_run_frame_network(void *st, const float *features)
+{
+    LPCNetState *l = (LPCNetState *)st;
+    run_frame_network(l, l->gru_a_condition, l->gru_b_condition, l->lpc, features);
+}
+void ref_synthesize_tail(void *st, short *out, int N, int preload) { lpcnet_synthesize_tail_impl((LPCNetState *)st, out, N, preload); }
+void ref_frame_network_deferred(void *st, const float *features) { run_frame_network_deferred((LPCNetState *)st, features); }
+void ref_frame_network_flush(void *st) { run_frame_network_flush((LPCNetState *)st); }
+void ref_reset_signal(void *st) { lpcnet_reset_signal((LPCNetState *)st); }
+
 /* ---- many streams on a pool of host threads (golden generation at BASELINE sizes; work queue over streams) ---- */
 typedef struct {
     const unsigned char *blob; int len; const float *features; int stride; int nframes; short *pcm;
@@ -201,39 +223,4 @@ double ref_time_streams(const unsigned char *blob, int len, const float *feature
     pthread_barrier_destroy(&bar);
     free(th); free(jobs);
     return last - first;     /* negative on error */
-}
-
-/* ---- CPU baseline timing: `nthreads` independent streams, each synthesising the same nframes. ---- */
-typedef struct {
-    const unsigned char *blob; int len; const float *features; int stride; int nframes; short *pcm; int decode;
-    const unsigned char *packets;
-} job_t;
-
-static void *worker(void *arg)
-{
-    job_t *j = (job_t *)arg;
-    if (j->decode) ref_decode_stream(j->blob, j->len, j->packets, j->nframes, j->pcm);
-    else ref_synth_stream(j->blob, j->len, j->features, j->stride, j->nframes, j->pcm);
-    return NULL;
-}
-
-/* returns wall seconds; features: [nthreads][nframes][stride]; pcm: [nthreads][nframes*160] */
-double ref_time_synthesis(const unsigned char *blob, int len, const float *features, int stride, int nframes,
-                          int nthreads, short *pcm)
-{
-    struct timespec t0, t1;
-    pthread_t *th = malloc(sizeof(*th) * nthreads);
-    job_t *jobs = malloc(sizeof(*jobs) * nthreads);
-    int i;
-    clock_gettime(CLOCK_MONOTONIC, &t0);
-    for (i = 0; i < nthreads; i++) {
-        jobs[i].blob = blob; jobs[i].len = len; jobs[i].stride = stride; jobs[i].nframes = nframes; jobs[i].decode = 0;
-        jobs[i].features = features + (size_t)i * nframes * stride;
-        jobs[i].pcm = pcm + (size_t)i * nframes * LPCNET_FRAME_SIZE;
-        pthread_create(&th[i], NULL, worker, &jobs[i]);
-    }
-    for (i = 0; i < nthreads; i++) pthread_join(th[i], NULL);
-    clock_gettime(CLOCK_MONOTONIC, &t1);
-    free(th); free(jobs);
-    return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
 }

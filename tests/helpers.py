@@ -64,6 +64,17 @@ def oracle_lib():
     L = ctypes.CDLL(so)
     L.oracle_model_create.restype = c_p
     L.oracle_model_create.argtypes = [ctypes.c_char_p, ctypes.c_int, c_p, ctypes.c_float, c_p]
+    L.oracle_model_create_ex.restype = c_p
+    L.oracle_model_create_ex.argtypes = [ctypes.c_char_p, ctypes.c_int, c_p, ctypes.c_float, ctypes.c_int, ctypes.c_int, c_p]
+    L.oracle_synthesize_impl.argtypes = [c_p, c_p, c_p, ctypes.c_int, ctypes.c_int]
+    L.oracle_run_frame_network.argtypes = [c_p, c_p]
+    L.oracle_synthesize_tail.argtypes = [c_p, c_p, ctypes.c_int, ctypes.c_int]
+    L.oracle_frame_network_deferred.argtypes = [c_p, c_p]
+    L.oracle_frame_network_flush.argtypes = [c_p]
+    L.oracle_reset_signal.argtypes = [c_p]
+    L.oracle_export_state.argtypes = [c_p, c_p]
+    L.oracle_model_na.argtypes = [c_p]
+    L.oracle_state_size.argtypes = []
     L.oracle_state_create.restype = c_p
     L.oracle_state_create.argtypes = [c_p]
     L.oracle_state_destroy.argtypes = [c_p]
@@ -88,21 +99,23 @@ def oracle_lib():
 
 
 @functools.lru_cache(None)
-def oracle_model(kind="int8"):
+def oracle_model(kind="int8", tag=""):
+    """CPU-restatement model for a blob flavour (int8 / float / int8_clamp) of a model variant (tag, gen_model.VARIANTS)."""
     L = oracle_lib()
-    b = blob(kind)
-    m = L.oracle_model_create(b, len(b), rcp_table().ctypes.data, LPC_GAMMA, codebooks().ctypes.data)
+    b = blob(kind, tag)
+    gamma, delay, e2e = model_config(tag)
+    m = L.oracle_model_create_ex(b, len(b), rcp_table().ctypes.data, gamma, delay, int(e2e), codebooks().ctypes.data)
     assert m, "oracle failed to parse the blob"
     return m
 
 
-def oracle_synth(features, kind="int8", nthreads=8):
+def oracle_synth(features, kind="int8", nthreads=8, tag=""):
     """features [n][T][20] float32 -> pcm [n][T*160] int16 via the CPU restatement."""
     L = oracle_lib()
     f = np.ascontiguousarray(features, dtype=np.float32)
     n, T, stride = f.shape
     pcm = np.zeros((n, T * 160), dtype=np.int16)
-    L.oracle_synthesize_batch(oracle_model(kind), f.ctypes.data, stride, n, T, nthreads, pcm.ctypes.data)
+    L.oracle_synthesize_batch(oracle_model(kind, tag), f.ctypes.data, stride, n, T, nthreads, pcm.ctypes.data)
     return pcm
 
 
@@ -138,8 +151,14 @@ def ref_lib(build="A", tag=""):
     L.ref_ulaw2lin.argtypes = [ctypes.c_float]
     L.ref_lin2ulaw.argtypes = [ctypes.c_float]
     L.ref_activation.argtypes = [c_p, c_p, ctypes.c_int, ctypes.c_int]
-    L.ref_time_synthesis.restype = ctypes.c_double
-    L.ref_time_synthesis.argtypes = [ctypes.c_char_p, ctypes.c_int, c_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_p]
+    L.ref_state_create.restype = c_p
+    L.ref_state_create.argtypes = [ctypes.c_char_p, ctypes.c_int]
+    for fn, at in (("ref_state_destroy", [c_p]), ("ref_state_reset", [c_p]), ("ref_state_copy", [c_p, c_p]),
+                   ("ref_synthesize_impl", [c_p, c_p, c_p, ctypes.c_int, ctypes.c_int]), ("ref_run_frame_network", [c_p, c_p]),
+                   ("ref_synthesize_tail", [c_p, c_p, ctypes.c_int, ctypes.c_int]), ("ref_frame_network_deferred", [c_p, c_p]),
+                   ("ref_frame_network_flush", [c_p]), ("ref_reset_signal", [c_p])):
+        getattr(L, fn).argtypes = at
+        getattr(L, fn).restype = None
     return L
 
 

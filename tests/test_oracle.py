@@ -193,3 +193,41 @@ def test_oracle_port_clamp_fixture():
     pcm = np.zeros((4, 40 * 160), np.int16)
     L.oracle_synthesize_batch(m, f.ctypes.data, 20, 4, 40, 4, pcm.ctypes.data)
     np.testing.assert_array_equal(pcm, gold)
+
+
+VARIANT_TAGS = ["na256", "na128", "e2e", "delay0", "na256e2e"]
+
+
+@pytest.mark.parametrize("tag", VARIANT_TAGS)
+@pytest.mark.parametrize("build", ["A", "B"])
+def test_oracle_port_model_variants_match_reference_golden(tag, build):
+    """Other model shapes / switches (GRU_A 256 and 128 units, END2END, FEATURES_DELAY 0): the CPU restatement
+    against goldens of the reference compiled with that variant's generated nnet_data.h (tests/golden/variants.npz)."""
+    import os
+    from fixtures import make_feature_batch
+    gold = np.load(os.path.join(H.GOLDEN, "variants.npz"))["%s_%s" % (tag, build)]
+    f = make_feature_batch(range(2), 20)
+    kind = "float" if build == "B" else "int8"
+    np.testing.assert_array_equal(H.oracle_synth(f, kind, tag=tag), gold)
+    if H.have_ref(build, tag):                                   # build container: the compiled reference itself
+        np.testing.assert_array_equal(H.ref_synth(f, build, tag=tag), gold)
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("build,tag", [("A", ""), ("B", ""), ("A", "na256e2e"), ("A", "delay0")])
+def test_oracle_port_plc_entry_points_match_reference(build, tag):
+    """lpcnet_synthesize_impl(preload), run_frame_network + lpcnet_synthesize_tail_impl, deferred/flush, lpcnet_reset_signal and
+    state copies (what src/lpcnet_plc.c does around the hot path): the CPU restatement against the compiled reference."""
+    if not H.have_ref(build, tag):
+        pytest.skip("compiled reference not present")
+    import scenarios as S
+    from fixtures import make_features
+    T = 18
+    script = S.plc_like_script(T)
+    kind = "float" if build == "B" else "int8"
+    for stream in (0, 3):
+        f = make_features(stream, T)
+        want = S.run_single("ref", H.ref_lib(build, tag), S.RefState(build, tag), f, stream, script)
+        got = S.run_single("oracle", H.oracle_lib(), S.OracleState(kind, tag), f, stream, script)
+        np.testing.assert_array_equal(got, want)
+        assert np.abs(want).max() > 0
