@@ -129,6 +129,11 @@ LPCNET_EXPORT int lpcnet_b200_ipc_export(void *d_ptr, unsigned char handle[64]);
 LPCNET_EXPORT void *lpcnet_b200_ipc_open(const unsigned char handle[64]);
 LPCNET_EXPORT int lpcnet_b200_ipc_close(void *p);
 LPCNET_EXPORT int lpcnet_b200_set_device(int device);
+/* CUDA streams for the `cuda_stream` argument of the `_device` entry points (for callers without their own CUDA binding).
+ * The engine orders its state across streams itself: consecutive calls may use different streams. */
+LPCNET_EXPORT void *lpcnet_b200_stream_create(void);
+LPCNET_EXPORT void lpcnet_b200_stream_destroy(void *stream);
+LPCNET_EXPORT int lpcnet_b200_stream_sync(void *stream);
 
 /* == lpcnet_decode() per stream, `npackets` times ==
  * packets: [n_streams][npackets][8] bytes ; pcm: [n_streams][npackets*640] int16 */

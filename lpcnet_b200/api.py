@@ -50,6 +50,9 @@ def lib():
     L.lpcnet_b200_ipc_open.argtypes = [c_p]
     L.lpcnet_b200_ipc_close.argtypes = [c_p]
     L.lpcnet_b200_set_device.argtypes = [ctypes.c_int]
+    L.lpcnet_b200_stream_create.restype = c_p
+    L.lpcnet_b200_stream_destroy.argtypes = [c_p]
+    L.lpcnet_b200_stream_sync.argtypes = [c_p]
     L.lpcnet_b200_batch_destroy.argtypes = [c_p]
     L.lpcnet_b200_batch_reset.argtypes = [c_p]
     L.lpcnet_b200_batch_streams.argtypes = [c_p]

@@ -768,6 +768,15 @@ void lpcnet_b200_device_free(void *p) { if (p) cudaFree(p); }
 int lpcnet_b200_memcpy_h2d(void *dst, const void *src, size_t bytes) { CK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice)); return 0; }
 int lpcnet_b200_memcpy_d2h(void *dst, const void *src, size_t bytes) { CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost)); return 0; }
 int lpcnet_b200_set_device(int device) { CK(cudaSetDevice(device)); return 0; }
+// CUDA streams for callers without their own CUDA binding (the `cuda_stream` argument of the `_device` entry points)
+void *lpcnet_b200_stream_create(void)
+{
+    cudaStream_t s = nullptr;
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); return nullptr; }
+    return s;
+}
+void lpcnet_b200_stream_destroy(void *s) { if (s) cudaStreamDestroy((cudaStream_t)s); }
+int lpcnet_b200_stream_sync(void *s) { CK(cudaStreamSynchronize((cudaStream_t)s)); return 0; }
 
 int lpcnet_b200_batch_algorithmic_bytes(const LPCNetB200Batch *b, long *total, long *sparse_gemv)
 {

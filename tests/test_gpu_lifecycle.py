@@ -101,22 +101,18 @@ def test_per_stream_reset_and_frame_counters(eng):
 def test_caller_streams_are_ordered_against_the_engine_state(eng):
     """`_device` calls on two different caller-owned CUDA streams, interleaved with host-pointer calls and a state read: the
     engine orders its state across streams (event hand-over), so the result equals the single-stream run."""
-    import ctypes
     n, T = 33, 12
     f = make_feature_batch(range(600, 600 + n), T)
     L = eng.lib()
-    cudart = ctypes.CDLL("libcudart.so.12")
-    s1, s2 = ctypes.c_void_p(), ctypes.c_void_p()
-    assert cudart.cudaStreamCreateWithFlags(ctypes.byref(s1), 1) == 0 and cudart.cudaStreamCreateWithFlags(ctypes.byref(s2), 1) == 0
+    s1, s2 = L.lpcnet_b200_stream_create(), L.lpcnet_b200_stream_create()
+    assert s1 and s2
     want = H.oracle_synth(f, "int8")
     b = eng.Batch(n, H.blob("int8"), lpc_gamma=H.LPC_GAMMA)
     d_f = L.lpcnet_b200_device_alloc(f.nbytes)
     L.lpcnet_b200_memcpy_h2d(d_f, f.ctypes.data, f.nbytes)
     d_p = [L.lpcnet_b200_device_alloc(n * 3 * 160 * 2) for _ in range(3)]
-    fstride = T * 20
-    # frames 0-2 on stream 1, 3-5 on stream 2, 6-8 host call, 9-11 on stream 1 again; features stay [n][T][20] (stride T*20)
+    # frames 0-2 on stream 1, 3-5 on stream 2, 6-8 host-pointer call, 9-11 on stream 1 again
     def dev_call(t0, dp, st):
-        # d_features points at frame t0 of stream 0; the per-stream stride is the full T*20, so use the _ex entry with a sub-view
         fv = np.ascontiguousarray(f[:, t0:t0 + 3])
         ptr = L.lpcnet_b200_device_alloc(fv.nbytes); L.lpcnet_b200_memcpy_h2d(ptr, fv.ctypes.data, fv.nbytes)
         b.synthesize_device(ptr, 3, 20, dp, cuda_stream=st)
@@ -134,5 +130,4 @@ def test_caller_streams_are_ordered_against_the_engine_state(eng):
     for p in tmp + d_p + [d_f]:
         L.lpcnet_b200_device_free(p)
     b.close()
-    cudart.cudaStreamDestroy(s1); cudart.cudaStreamDestroy(s2)
-    assert fstride
+    L.lpcnet_b200_stream_destroy(s1); L.lpcnet_b200_stream_destroy(s2)
