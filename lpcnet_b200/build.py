@@ -59,7 +59,8 @@ def build_variant(name, defines):
     """Tuning aid: build lpcnet_b200/variants/lib_<name>.so with extra -D flags (e.g. LPCNET_NWC=12)."""
     vdir = os.path.join(HERE, "variants")
     log = []
-    objs = _compile_all(os.path.join(vdir, "obj_" + name), defines, log)
+    os.makedirs(vdir, exist_ok=True)
+    objs = _compile_all(os.path.join("/tmp", "lpcnet_b200_variant_obj_" + name), defines, log)     # objects outside the tree: the gpurun snapshot stays small
     for blk in log:
         if blk.startswith("==== sample_kernel.cu -DLPCNET_NA=384"):
             print(name, [l.strip() for l in blk.splitlines() if "registers" in l or "spill" in l][-2:])
