@@ -279,14 +279,29 @@ def main():
     else:
         feats = features_for(n, F, first_stream=n * rank)           # distinct per stream (and per rank)
     fbytes, pbytes = feats.nbytes, n * F * 160 * 2
+    L.lpcnet_b200_set_device(local)
     d_feat = L.lpcnet_b200_device_alloc(fbytes)
-    if dist is not None:                                      # under torchrun the PCM buffer is a torch tensor so NCCL can gather it
-        import torch
-        pcm_t = torch.empty((n, F * 160), dtype=torch.int16, device="cuda")
-        d_pcm = pcm_t.data_ptr()
-    else:
-        d_pcm = L.lpcnet_b200_device_alloc(pbytes)
+    d_pcm = L.lpcnet_b200_device_alloc(pbytes)
     assert d_feat and d_pcm
+    # N > 1: the one exchange of the path, the PCM gather to rank 0, is part of EVERY step: rank 0 owns the job's PCM
+    # buffer [world*n][F*160]; the other ranks open it through CUDA IPC and set it as their batch's PCM sink, so each finished
+    # chunk is pushed there by the rank's copy engine over NVLink inside the call (csrc/batch_api.cu forward_to_sink).  torch
+    # only carries the 64-byte handle and the barriers; no framework tensor is on the data path.
+    d_gather, gather_opened = None, None
+    if dist is not None:
+        handle = [None]
+        if rank == 0:
+            d_gather = L.lpcnet_b200_device_alloc(pbytes * world)
+            assert d_gather
+            hb = (ctypes.c_ubyte * 64)()
+            assert L.lpcnet_b200_ipc_export(d_gather, hb) == 0, L.lpcnet_b200_last_error()
+            handle = [bytes(hb)]
+        dist.broadcast_object_list(handle, src=0)
+        if rank != 0:
+            gather_opened = L.lpcnet_b200_ipc_open(handle[0])
+            assert gather_opened, L.lpcnet_b200_last_error()
+            d_gather = gather_opened
+        batch.set_pcm_sink(d_gather, F * 160, n * rank)
     L.lpcnet_b200_memcpy_h2d(d_feat, feats.ctypes.data, fbytes)
     # pinned host buffers for the e2e leg
     h_feat_p = L.lpcnet_b200_host_alloc(fbytes)
@@ -350,17 +365,19 @@ def main():
         t = torch.tensor([dev_s, e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_s, e2e_s = float(t[0]), float(t[1])
-        # the one real exchange of the path: gather the PCM shards to rank 0 over NCCL (timed separately, device events)
-        from lpcnet_b200.sharding import gather_pcm
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        gather_pcm(pcm_t, n * world, dist, dst=0)                # untimed: first collective sets up the NCCL channels
-        dist.barrier(); torch.cuda.synchronize()
-        e0.record()
-        full = gather_pcm(pcm_t, n * world, dist, dst=0)
-        e1.record(); torch.cuda.synchronize()
-        gather_ms = e0.elapsed_time(e1)
+        # the gather ran inside every timed step; check what arrived: every rank's shard of the last step must sit in rank 0's
+        # buffer bit for bit (digest of the rank's local PCM vs digest of its rows in the gathered buffer)
+        import hashlib
+        loc = np.ctypeslib.as_array(ctypes.cast(h_pcm_p, ctypes.POINTER(ctypes.c_int16)), shape=(n, F * 160))   # PCM of the last (e2e) step, as returned to the host
+        digs = [None] * world
+        dist.all_gather_object(digs, hashlib.sha256(loc.tobytes()).hexdigest())
+        gather_ok = None
         if rank == 0:
-            assert full.shape == (n * world, F * 160)
+            full = np.empty((world * n, F * 160), np.int16)
+            L.lpcnet_b200_memcpy_d2h(full.ctypes.data, d_gather, pbytes * world)
+            gather_ok = all(hashlib.sha256(full[r * n:(r + 1) * n].tobytes()).hexdigest() == digs[r] for r in range(world))
+            assert gather_ok, "PCM gather: rank 0's buffer does not hold every rank's shard"
+        gather_ms = 0.0
     else:
         gather_ms = None
 
@@ -386,7 +403,7 @@ def main():
             "config": {"workload": {"config3_int8": "config3_int8: %d streams/GPU x %d frames x 160 samples per step, int8 block-sparse GRU_A, bit-exact vs reference build A",
                                     "config2_float": "config2_float: %d streams/GPU x %d frames x 160 samples per step, float GRU arithmetic with fp16-stored weights, bit-exact vs reference build B",
                                     "config5_decode": "config5_decode: %d streams/GPU x %d frames (8-byte packets -> lpcnet_decode), int8, synthetic VQ codebooks"}[args.workload] % (n, F),
-                       "streams_per_gpu": n, "frames_per_step": F, "samples_per_step": samples_step, "parallelism": "streams sharded across GPUs (dp%d), no data-path collective" % world,
+                       "streams_per_gpu": n, "frames_per_step": F, "samples_per_step": samples_step, "parallelism": "streams sharded across GPUs (dp%d), no collective inside the sample loop%s" % (world, "; PCM of every step gathered to rank 0 inside the timed region" if world > 1 else ""),
                        "l2": "256 MiB memset between timed steps (outside the event bracket)", "inputs": "distinct features/packets per stream (seed 1000+s / 2000+s), every stream starts from the reference RNG seed", "x_realtime_per_stream": value / world / n / 16000.0},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(fbytes), "d2h_bytes_per_step": int(pbytes), "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": int(launches),
@@ -409,14 +426,22 @@ def main():
             "wall_s_timed_region": wall,
         }
         if gather_ms is not None:
-            out["pcm_gather"] = {"ms": gather_ms, "bytes_per_rank": int(pbytes), "backend": "nccl"}
+            out["pcm_gather"] = {"in_timed_region": True, "verified": bool(gather_ok), "bytes_per_rank_per_step": int(pbytes), "gathered_bytes_per_step": int(pbytes * world),
+                                 "transport": "per-chunk cudaMemcpy2DAsync from each rank's copy engine into rank 0's buffer (CUDA IPC peer mapping, NVLink), "
+                                              "enqueued by the C-ABI call itself (lpcnet_b200_batch_set_pcm_sink); value and e2e both include it"}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_record(args.workload)
         print(json.dumps(out), flush=True)
 
+    if dist is not None:
+        batch.set_pcm_sink(None, 0, 0)
+        dist.barrier()                                        # nobody still writes into rank 0's buffer
+        if gather_opened:
+            L.lpcnet_b200_ipc_close(gather_opened)
+        elif d_gather:
+            L.lpcnet_b200_device_free(d_gather)
     L.lpcnet_b200_device_free(d_feat)
-    if dist is None:
-        L.lpcnet_b200_device_free(d_pcm)
+    L.lpcnet_b200_device_free(d_pcm)
     L.lpcnet_b200_host_free(h_feat_p); L.lpcnet_b200_host_free(h_pcm_p)
     batch.close()
     if dist is not None:

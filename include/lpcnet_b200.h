@@ -41,6 +41,32 @@ typedef struct LPCNetB200Config {
     int end2end;            /* END2END: LPC from the network's reflection coefficients (src/lpcnet.c:57-78,107-108); default 0 */
 } LPCNetB200Config;
 
+/* One named array of a model blob: the reference's WeightArray (src/nnet.h:43-48).  type: 0 float, 1 int, 2 qweight (int8);
+ * size in bytes. */
+typedef struct LPCNetB200Array {
+    const char *name;
+    int type;
+    int size;
+    const void *data;
+} LPCNetB200Array;
+
+/* == model blob I/O (host only, no CUDA) ==
+ * lpcnet_b200_write_blob: serialise arrays to the "DNNw" weight-blob format exactly like the reference's write_weights()
+ * (src/write_lpcnet_weights.c:47-67: 64-byte WeightHead, payload zero-padded to a multiple of 64 bytes).  With cfg != NULL the
+ * three switches the reference leaves in nnet_data.h travel as one extra record `lpcnet_b200_config` (float[4]: LPC_GAMMA,
+ * FEATURES_DELAY, END2END, format version) which the reference's own loader ignores.  out == NULL: returns the size needed.
+ * Returns the number of bytes written, < 0 on error. */
+LPCNET_EXPORT long long lpcnet_b200_write_blob(const LPCNetB200Array *arrays, int count, const LPCNetB200Config *cfg,
+                                               unsigned char *out, size_t cap);
+LPCNET_EXPORT int lpcnet_b200_write_blob_file(const char *path, const LPCNetB200Array *arrays, int count, const LPCNetB200Config *cfg);
+/* parse_weights() (src/parse_lpcnet_weights.c:37-76): lists the records of a blob (entries point into `blob`).  Returns the
+ * number of records (may exceed cap; only cap are filled), < 0 if the blob is malformed. */
+LPCNET_EXPORT int lpcnet_b200_parse_blob(const unsigned char *blob, int len, LPCNetB200Array *arrays, int cap);
+/* The blob's `lpcnet_b200_config` record: 1 = found (cfg filled), 0 = the blob has none, < 0 malformed blob. */
+LPCNET_EXPORT int lpcnet_b200_blob_config(const unsigned char *blob, int len, LPCNetB200Config *cfg);
+/* Whole-file read (weights_blob.bin, .f32 feature files, packet files): out == NULL returns the size. */
+LPCNET_EXPORT long long lpcnet_b200_read_file(const char *path, unsigned char *out, size_t cap);
+
 /* Number of usable CUDA devices (0 => the engine cannot run; there is no CPU fallback). */
 LPCNET_EXPORT int lpcnet_b200_device_count(void);
 /* Last error message of the calling thread ("" if none). */
@@ -129,6 +155,39 @@ LPCNET_EXPORT int lpcnet_b200_ipc_export(void *d_ptr, unsigned char handle[64]);
 LPCNET_EXPORT void *lpcnet_b200_ipc_open(const unsigned char handle[64]);
 LPCNET_EXPORT int lpcnet_b200_ipc_close(void *p);
 LPCNET_EXPORT int lpcnet_b200_set_device(int device);
+
+/* == multi-GPU in ONE process ==  `n_streams` independent streams cut into contiguous index ranges over `n_devices` CUDA devices
+ * (devices[k] = CUDA ordinal of shard k; NULL = 0..n_devices-1), weights replicated, one LPCNetB200Batch per device.  Every call
+ * enqueues all shards (each on its device's own stream) and then waits: the devices run concurrently and nothing is exchanged
+ * inside the sample loop.  Host-out calls let every device copy its shard to the caller's buffer over its own PCIe link;
+ * `_gather` calls collect the PCM in the memory of devices[0] instead ([n_streams][T] int16, e.g. from lpcnet_b200_device_alloc_on):
+ * each finished chunk travels by peer DMA over NVLink while the next chunk is computed (the PCM sink above).
+ * Use pinned host buffers (lpcnet_b200_host_alloc) so that the copies of different devices overlap. */
+typedef struct LPCNetB200Multi LPCNetB200Multi;
+LPCNET_EXPORT LPCNetB200Multi *lpcnet_b200_multi_create(int n_streams, const unsigned char *blob, int blob_len, const LPCNetB200Config *cfg,
+                                                        const int *devices, int n_devices);
+LPCNET_EXPORT void lpcnet_b200_multi_destroy(LPCNetB200Multi *m);
+LPCNET_EXPORT int lpcnet_b200_multi_streams(const LPCNetB200Multi *m);
+LPCNET_EXPORT int lpcnet_b200_multi_devices(const LPCNetB200Multi *m);
+/* 1 if every device can write devices[0]'s memory directly (NVLink peer access); 0: gathers are staged by the driver */
+LPCNET_EXPORT int lpcnet_b200_multi_peer_access(const LPCNetB200Multi *m);
+/* shard k: its CUDA device and stream range [first, first + count) */
+LPCNET_EXPORT int lpcnet_b200_multi_shard(const LPCNetB200Multi *m, int k, int *device, int *first, int *count);
+/* the shard's batch, for the per-stream lifecycle calls (reset_streams, export/import_state, snapshots) with LOCAL stream ids */
+LPCNET_EXPORT LPCNetB200Batch *lpcnet_b200_multi_batch(LPCNetB200Multi *m, int k);
+LPCNET_EXPORT int lpcnet_b200_multi_reset(LPCNetB200Multi *m);
+LPCNET_EXPORT int lpcnet_b200_multi_set_codebooks(LPCNetB200Multi *m, const float *cb, size_t n_floats);
+/* same arguments as lpcnet_b200_batch_synthesize / _decode with n = all streams */
+LPCNET_EXPORT int lpcnet_b200_multi_synthesize(LPCNetB200Multi *m, const float *features, int nframes, int feature_stride,
+                                               int samples_per_frame, short *pcm);
+LPCNET_EXPORT int lpcnet_b200_multi_decode(LPCNetB200Multi *m, const unsigned char *packets, int npackets, short *pcm);
+/* host in, PCM gathered on devices[0]: d_pcm [n_streams][nframes*samples_per_frame] (resp. [n_streams][npackets*640]) */
+LPCNET_EXPORT int lpcnet_b200_multi_synthesize_gather(LPCNetB200Multi *m, const float *features, int nframes, int feature_stride,
+                                                      int samples_per_frame, short *d_pcm);
+LPCNET_EXPORT int lpcnet_b200_multi_decode_gather(LPCNetB200Multi *m, const unsigned char *packets, int npackets, short *d_pcm);
+/* contiguous range of shard k when n items are cut into `parts` (sizes differ by at most one; earlier shards take the remainder) */
+LPCNET_EXPORT int lpcnet_b200_shard_range(int n, int k, int parts, int *first, int *count);
+LPCNET_EXPORT void *lpcnet_b200_device_alloc_on(int device, size_t bytes);
 /* CUDA streams for the `cuda_stream` argument of the `_device` entry points (for callers without their own CUDA binding).
  * The engine orders its state across streams itself: consecutive calls may use different streams. */
 LPCNET_EXPORT void *lpcnet_b200_stream_create(void);

@@ -84,6 +84,33 @@ def lib():
     L.lpcnet_b200_host_alloc.argtypes = [ctypes.c_size_t]
     L.lpcnet_b200_host_free.argtypes = [c_p]
     L.lpcnet_b200_measure_smem_peak.argtypes = [ctypes.c_int, c_p]
+    # model blob I/O (csrc/blob_io.cu)
+    L.lpcnet_b200_write_blob.restype = ctypes.c_longlong
+    L.lpcnet_b200_write_blob.argtypes = [c_p, ctypes.c_int, c_p, c_p, ctypes.c_size_t]
+    L.lpcnet_b200_write_blob_file.argtypes = [ctypes.c_char_p, c_p, ctypes.c_int, c_p]
+    L.lpcnet_b200_parse_blob.argtypes = [ctypes.c_char_p, ctypes.c_int, c_p, ctypes.c_int]
+    L.lpcnet_b200_blob_config.argtypes = [ctypes.c_char_p, ctypes.c_int, c_p]
+    L.lpcnet_b200_read_file.restype = ctypes.c_longlong
+    L.lpcnet_b200_read_file.argtypes = [ctypes.c_char_p, c_p, ctypes.c_size_t]
+    # multi-GPU in one process (csrc/multi_api.cu)
+    L.lpcnet_b200_multi_create.restype = c_p
+    L.lpcnet_b200_multi_create.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_int, c_p, c_p, ctypes.c_int]
+    L.lpcnet_b200_multi_destroy.argtypes = [c_p]
+    L.lpcnet_b200_multi_streams.argtypes = [c_p]
+    L.lpcnet_b200_multi_devices.argtypes = [c_p]
+    L.lpcnet_b200_multi_peer_access.argtypes = [c_p]
+    L.lpcnet_b200_multi_shard.argtypes = [c_p, ctypes.c_int, c_p, c_p, c_p]
+    L.lpcnet_b200_multi_batch.restype = c_p
+    L.lpcnet_b200_multi_batch.argtypes = [c_p, ctypes.c_int]
+    L.lpcnet_b200_multi_reset.argtypes = [c_p]
+    L.lpcnet_b200_multi_set_codebooks.argtypes = [c_p, c_p, ctypes.c_size_t]
+    L.lpcnet_b200_multi_synthesize.argtypes = [c_p, c_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_p]
+    L.lpcnet_b200_multi_decode.argtypes = [c_p, c_p, ctypes.c_int, c_p]
+    L.lpcnet_b200_multi_synthesize_gather.argtypes = [c_p, c_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_p]
+    L.lpcnet_b200_multi_decode_gather.argtypes = [c_p, c_p, ctypes.c_int, c_p]
+    L.lpcnet_b200_shard_range.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, c_p, c_p]
+    L.lpcnet_b200_device_alloc_on.restype = c_p
+    L.lpcnet_b200_device_alloc_on.argtypes = [ctypes.c_int, ctypes.c_size_t]
     # reference API (include/lpcnet.h)
     L.lpcnet_create.restype = c_p
     L.lpcnet_destroy.argtypes = [c_p]
@@ -120,6 +147,140 @@ def measure_smem_peak(device=0):
 class Config(ctypes.Structure):
     """LPCNetB200Config (include/lpcnet_b200.h): LPC_GAMMA / FEATURES_DELAY / END2END of the model's generated nnet_data.h."""
     _fields_ = [("lpc_gamma", ctypes.c_float), ("features_delay", ctypes.c_int), ("end2end", ctypes.c_int)]
+
+
+class Array(ctypes.Structure):
+    """LPCNetB200Array (include/lpcnet_b200.h) = the reference's WeightArray (src/nnet.h:43-48)."""
+    _fields_ = [("name", ctypes.c_char_p), ("type", ctypes.c_int), ("size", ctypes.c_int), ("data", ctypes.c_void_p)]
+
+
+def parse_blob(blob):
+    """[(name, type, bytes)] of a DNNw blob (lpcnet_b200_parse_blob)."""
+    L = lib()
+    n = L.lpcnet_b200_parse_blob(blob, len(blob), None, 0)
+    if n < 0:
+        raise LPCNetB200Error("parse_blob: " + _err())
+    recs = (Array * n)()
+    L.lpcnet_b200_parse_blob(blob, len(blob), recs, n)
+    return [(r.name.decode(), int(r.type), ctypes.string_at(r.data, r.size)) for r in recs]
+
+
+def write_blob(arrays, config=None):
+    """arrays: [(name, type, bytes-like)] -> DNNw blob bytes (lpcnet_b200_write_blob); config = (gamma, delay, end2end) or None."""
+    L = lib()
+    n = len(arrays)
+    recs = (Array * n)()
+    keep = []
+    for i, (name, typ, data) in enumerate(arrays):
+        raw = bytes(data)
+        buf = ctypes.create_string_buffer(raw, len(raw))
+        nm = name.encode()
+        keep += [buf, nm]
+        recs[i].name = nm; recs[i].type = int(typ); recs[i].size = len(raw); recs[i].data = ctypes.addressof(buf)
+    c = Config(float(config[0]), int(config[1]), int(config[2])) if config is not None else None
+    cp = ctypes.byref(c) if c is not None else None
+    need = L.lpcnet_b200_write_blob(recs, n, cp, None, 0)
+    if need < 0:
+        raise LPCNetB200Error("write_blob: " + _err())
+    out = (ctypes.c_ubyte * need)()
+    if L.lpcnet_b200_write_blob(recs, n, cp, out, need) != need:
+        raise LPCNetB200Error("write_blob: " + _err())
+    return bytes(out)
+
+
+def blob_config(blob):
+    """(gamma, delay, end2end) of the blob's lpcnet_b200_config record, or None."""
+    c = Config()
+    r = lib().lpcnet_b200_blob_config(blob, len(blob), ctypes.byref(c))
+    if r < 0:
+        raise LPCNetB200Error("blob_config: " + _err())
+    return (float(c.lpc_gamma), int(c.features_delay), int(c.end2end)) if r else None
+
+
+def shard_range(n, k, parts):
+    a, b = ctypes.c_int(0), ctypes.c_int(0)
+    if lib().lpcnet_b200_shard_range(int(n), int(k), int(parts), ctypes.byref(a), ctypes.byref(b)) != 0:
+        raise LPCNetB200Error(_err())
+    return int(a.value), int(a.value + b.value)
+
+
+class Multi:
+    """n independent streams sharded over several GPUs of ONE process (lpcnet_b200_multi_*, csrc/multi_api.cu)."""
+
+    def __init__(self, n_streams, blob, devices, config=None, codebooks=None):
+        self._L = lib()
+        devs = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+        c = Config(float(config[0]), int(config[1]), int(config[2])) if config is not None else None
+        self._h = self._L.lpcnet_b200_multi_create(int(n_streams), blob, len(blob), ctypes.byref(c) if c is not None else None, devs, len(devices))
+        if not self._h:
+            raise LPCNetB200Error("lpcnet_b200_multi_create: " + _err())
+        self.n = int(n_streams)
+        self.devices = list(devices)
+        if codebooks is not None:
+            cb = np.ascontiguousarray(codebooks, dtype=np.float32)
+            if self._L.lpcnet_b200_multi_set_codebooks(self._h, cb.ctypes.data, cb.size) != 0:
+                raise LPCNetB200Error(_err())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.lpcnet_b200_multi_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def shard(self, k):
+        d, a, c = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+        if self._L.lpcnet_b200_multi_shard(self._h, int(k), ctypes.byref(d), ctypes.byref(a), ctypes.byref(c)) != 0:
+            raise LPCNetB200Error(_err())
+        return int(d.value), int(a.value), int(c.value)
+
+    def peer_access(self):
+        return bool(self._L.lpcnet_b200_multi_peer_access(self._h))
+
+    def reset(self):
+        if self._L.lpcnet_b200_multi_reset(self._h) != 0:
+            raise LPCNetB200Error(_err())
+
+    def synthesize(self, features, samples_per_frame=160, gather=False):
+        """features [n][T][stride] -> pcm [n][T*spf]; gather=True collects the PCM on devices[0] first (NVLink peer DMA) and reads it back from there."""
+        f = np.ascontiguousarray(features, dtype=np.float32)
+        assert f.ndim == 3 and f.shape[0] == self.n
+        T, stride = f.shape[1], f.shape[2]
+        pcm = np.zeros((self.n, T * samples_per_frame), dtype=np.int16)
+        if not gather:
+            if self._L.lpcnet_b200_multi_synthesize(self._h, f.ctypes.data, T, stride, samples_per_frame, pcm.ctypes.data) != 0:
+                raise LPCNetB200Error("lpcnet_b200_multi_synthesize: " + _err())
+            return pcm
+        d = self._L.lpcnet_b200_device_alloc_on(self.devices[0], pcm.nbytes)
+        if not d:
+            raise LPCNetB200Error(_err())
+        try:
+            if self._L.lpcnet_b200_multi_synthesize_gather(self._h, f.ctypes.data, T, stride, samples_per_frame, d) != 0:
+                raise LPCNetB200Error("lpcnet_b200_multi_synthesize_gather: " + _err())
+            self._L.lpcnet_b200_set_device(self.devices[0])
+            if self._L.lpcnet_b200_memcpy_d2h(pcm.ctypes.data, d, pcm.nbytes) != 0:
+                raise LPCNetB200Error(_err())
+        finally:
+            self._L.lpcnet_b200_device_free(d)
+        return pcm
+
+    def decode(self, packets, gather=False):
+        p = np.ascontiguousarray(packets, dtype=np.uint8)
+        assert p.ndim == 3 and p.shape[0] == self.n and p.shape[2] == 8
+        pcm = np.zeros((self.n, p.shape[1] * 640), dtype=np.int16)
+        if not gather:
+            if self._L.lpcnet_b200_multi_decode(self._h, p.ctypes.data, p.shape[1], pcm.ctypes.data) != 0:
+                raise LPCNetB200Error("lpcnet_b200_multi_decode: " + _err())
+            return pcm
+        d = self._L.lpcnet_b200_device_alloc_on(self.devices[0], pcm.nbytes)
+        try:
+            if self._L.lpcnet_b200_multi_decode_gather(self._h, p.ctypes.data, p.shape[1], d) != 0:
+                raise LPCNetB200Error("lpcnet_b200_multi_decode_gather: " + _err())
+            self._L.lpcnet_b200_set_device(self.devices[0])
+            self._L.lpcnet_b200_memcpy_d2h(pcm.ctypes.data, d, pcm.nbytes)
+        finally:
+            self._L.lpcnet_b200_device_free(d)
+        return pcm
 
 
 class Batch:

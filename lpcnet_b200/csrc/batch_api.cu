@@ -471,7 +471,7 @@ static int forward_to_sink(LPCNetB200Batch *b, const short *d_pcm, long long pcm
     CK(cudaStreamWaitEvent(b->sink_stream, b->sink_ev, 0));
     CK(cudaMemcpy2DAsync(b->sink + b->sink_row0 * b->sink_pitch + (size_t)c0 * spf, b->sink_pitch * sizeof(short),
                          d_pcm + (size_t)c0 * spf, pcm_stride * sizeof(short), (size_t)nf * spf * sizeof(short), b->n,
-                         cudaMemcpyDeviceToDevice, b->sink_stream));
+                         cudaMemcpyDefault, b->sink_stream));       // (the sink may live on another device: UVA infers the route)
     return 0;
 }
 
