@@ -20,7 +20,7 @@ using namespace lpcnet_b200;
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_error("%s failed: %s", #call, cudaGetErrorString(e_)); return -1; } } while (0)
 
-static const int CHUNK = 16;        // frames of conditioning buffered per sample-kernel launch
+static const int CHUNK = FRAME_CHUNK;   // frames of conditioning buffered per sample-kernel launch
 static const int DEFER_MAX = 4;     // MAX_FEATURE_BUFFER_SIZE (lpcnet_private.h:26): conv1.kernel_size + conv2.kernel_size - 2
 
 // the sample-rate part of the per-stream state (resettable part of struct LPCNetState), structure of arrays
@@ -315,6 +315,7 @@ LPCNetB200Batch *lpcnet_b200_batch_create_ex(int n_streams, const unsigned char 
     al((void **)&b->fs.conv1_state, sizeof(float) * 2 * FRAME_IN * n); al((void **)&b->fs.conv2_state, sizeof(float) * 2 * COND * n);
     al((void **)&b->fs.lpc_carry, sizeof(float) * 2 * LPC_ORDER * n); al((void **)&b->fs.vq_mem, sizeof(float) * NB_BANDS * n);
     al((void **)&b->fs.frame_count, sizeof(int) * n);
+    al((void **)&b->fs.work, sizeof(float) * frame_work_floats(n));
     al((void **)&b->condA, sizeof(float) * (size_t)CHUNK * n * 3 * na); al((void **)&b->condB, sizeof(float) * (size_t)CHUNK * n * 3 * NB);
     al((void **)&b->lpc_raw, sizeof(float) * (size_t)(CHUNK + 2) * n * LPC_ORDER);
     if (ok && cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) ok = false;
@@ -352,7 +353,7 @@ void lpcnet_b200_batch_destroy(LPCNetB200Batch *b)
     if (b->sink_ev) cudaEventDestroy(b->sink_ev);
     if (b->sink_done) cudaEventDestroy(b->sink_done);
     free_sample_state(&b->ss); free_sample_state(&b->shadow);
-    void *ptrs[] = {b->fs.conv1_state, b->fs.conv2_state, b->fs.lpc_carry, b->fs.vq_mem, b->fs.frame_count, b->condA, b->condB, b->lpc_raw,
+    void *ptrs[] = {b->fs.conv1_state, b->fs.conv2_state, b->fs.lpc_carry, b->fs.vq_mem, b->fs.frame_count, b->fs.work, b->condA, b->condB, b->lpc_raw,
                     b->d_features, b->d_pcm, b->d_packets, b->d_state, b->d_nsil};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (b->kev) { for (cudaEvent_t e : *b->kev) cudaEventDestroy(e); delete b->kev; }
@@ -493,7 +494,7 @@ static int synth_device(LPCNetB200Batch *b, const float *d_feat, long long strea
     for (int c0 = 0; c0 < nframes; c0 += CHUNK) {
         const int nf = nframes - c0 < CHUNK ? nframes - c0 : CHUNK;
         launch_frame_network(b->model, b->fs, d_feat + (size_t)c0 * frame_stride, stream_stride, frame_stride, n, nf, b->condA, b->condB, b->lpc_raw, st);
-        launches += b->model.cfg.end2end ? 1 : 4;
+        launches += frame_network_launches(b->model);
         b->cond_last = nf - 1;
         const int r = sample_frames(b, 0, nf, spf, d_pcm + (size_t)c0 * spf, pcm_stride, c0 == 0 ? preload : 0, st);
         if (r < 0) return -1;

@@ -27,6 +27,7 @@ constexpr int FRAME_SIZE = 160;
 constexpr int MAX_FEATURES_DELAY = 2;             // FEATURES_DELAY of the reference (dump_lpcnet.py:323-329) is a per-model value 0..2
 constexpr int WINDOW_SIZE = 320;
 constexpr int FREQ_SIZE = 161;
+constexpr int FRAME_CHUNK = 16;                   // frames of conditioning evaluated (and buffered) per per-sample kernel launch
 constexpr int NA_SUPPORTED[] = {128, 256, 384};   // GRU_A sizes with a compiled per-sample kernel (multiples of 128: 16 neuron groups per compute-warp slot)
 constexpr int NA_MAX = 384;
 
@@ -361,11 +362,14 @@ struct FrameState {           // per-batch persistent state of the 100 Hz path
     float *lpc_carry;         // [2][n][16] raw LPC of the two previous frames
     float *vq_mem;            // [n][18] decoder memory
     int *frame_count;         // [n] frames seen since the stream's last reset, saturating at 1000 (lpcnet.c:119)
+    float *work;              // scratch of the layer-by-layer conditioning network (frame_work_floats(n) floats; not part of the state)
 };
 
 // lpc_raw [nframes+2][n][16]: entry e = raw LPC of frame e-2 of the call (entries 0,1 = carry); frame f reads entry f + 2 - delay
 void launch_frame_network(const DeviceModel &m, const FrameState &fs, const float *d_features, long long stream_stride,
                           int frame_stride, int n, int nframes, float *condA, float *condB, float *lpc_raw, cudaStream_t st);
+int frame_network_launches(const DeviceModel &m);           // engine kernels one launch_frame_network call launches
+size_t frame_work_floats(size_t n);
 void launch_decode_packets(const DeviceModel &m, const FrameState &fs, const uint8_t *d_packets, int n, int npackets,
                            float *d_features /* [n][4*npackets][20] */, cudaStream_t st);
 // one set of launchers per compiled GRU_A size

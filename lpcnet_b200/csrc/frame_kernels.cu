@@ -17,35 +17,123 @@
 
 namespace lpcnet_b200 {
 
-constexpr int TS = 8;                  // streams per block (register tile over streams: one weight load feeds 8 FMAs)
-constexpr int FT = 128;                // threads per block == COND
+// The conditioning network is evaluated LAYER BY LAYER over all (stream, frame) columns of a chunk as plain fp32 GEMMs:
+// nothing in it is sequential across frames except the 3-frame convolution windows, and those are just overlapping reads of a
+// per-stream row buffer that starts with the two carried frames (conv state).  One generic kernel, frame_gemm_kernel:
+//   Y[col][i] = act(bias[i] + sum_{j<M} W[j*N+i] * X[col][j]),   j ascending, one fmaf per term, accumulator starts at the bias
+// = the per-row FMA chain of sgemv_accum16 (vec_avx.h:618-643) for every output, so the result does not depend on the tiling.
+// Block tile 128 outputs x 32 columns x 16 k, 128 threads, thread tile 8 x 4 (32 FFMA per 3 LDS.128); W and X tiles are
+// double-buffered through shared memory (register-staged prefetch of the next k-tile while the current one is multiplied).
+// Small blocks on purpose: a layer has only ~1300 tiles at 4096 streams x 10 frames, 6 blocks per SM keep the SMs evenly loaded.
+constexpr int GT_N = 128, GT_C = 32, GT_K = 16, GT_XPAD = 36, GT_THREADS = 128;
 
-// one dense/conv layer for TS streams: out[i][k] = act(b[i] + sum_j W[j*N+i]*x[j][k]); thread i = threadIdx.x + o*FT
-template <int M>
-__device__ __forceinline__ void layer_accum(float y[TS], const float *__restrict__ W, int N, int i, const float (*x)[TS])
+struct GemmArgs {
+    const float *W, *bias; int M, N;       // W[j*N + i] (reference layout of dense / conv weights: dump_lpcnet.py:194-200,229-245)
+    const float *X; int xS, xF;            // column (s, f) reads its M inputs at X + ((size_t)s*xS + f)*xF  (conv: overlapping windows, xF < M)
+    float *Y; long long ys, yf, y0;        // output i of column (s, f) goes to Y + s*ys + f*yf + y0 + i
+    int F, ncols;                          // frames per stream in this call, ncols = n*F
+    const int *fc; int zthr;               // output zeroed while frame_count[s] + f < zthr (warm-up, lpcnet.c:99,101); fc == NULL: never
+    const uint16_t *rcp16;
+};
+
+template <bool TANH>
+__global__ void __launch_bounds__(GT_THREADS) frame_gemm_kernel(const GemmArgs a)
 {
-#pragma unroll 4
-    for (int j = 0; j < M; j++) {
-        const float w = __ldg(&W[(size_t)j * N + i]);
-        const float4 a = *reinterpret_cast<const float4 *>(&x[j][0]);
-        const float4 b = *reinterpret_cast<const float4 *>(&x[j][4]);
-        y[0] = __fmaf_rn(w, a.x, y[0]); y[1] = __fmaf_rn(w, a.y, y[1]); y[2] = __fmaf_rn(w, a.z, y[2]); y[3] = __fmaf_rn(w, a.w, y[3]);
-        y[4] = __fmaf_rn(w, b.x, y[4]); y[5] = __fmaf_rn(w, b.y, y[5]); y[6] = __fmaf_rn(w, b.z, y[6]); y[7] = __fmaf_rn(w, b.w, y[7]);
+    __shared__ __align__(16) float Ws[2][GT_K][GT_N];
+    __shared__ __align__(16) float Xs[2][GT_K][GT_XPAD];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int c0 = blockIdx.x * GT_C, i0 = blockIdx.y * GT_N;
+    // ---- loader roles: X tile = 32 columns x 16 k (thread: column tid/4, 4 consecutive k), W tile = 16 k x 128 outputs (thread: 4 rows, one float4) ----
+    const int xc = c0 + (tid >> 2), kq = tid & 3;
+    const bool xvalid = xc < a.ncols;
+    const int xs_ = xvalid ? xc / a.F : 0, xf_ = xvalid ? xc - (xc / a.F) * a.F : 0;
+    const float *xp = a.X + ((size_t)xs_ * a.xS + xf_) * a.xF + 4 * kq;
+    const int wq = tid & 31, wr = tid >> 5;
+    const bool wvalid = i0 + 4 * wq < a.N;
+    const float *wp = a.W + i0 + 4 * wq;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 wreg[4], xreg;
+    auto gload = [&](int k0) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) { const int k = k0 + wr + 4 * e; wreg[e] = (wvalid && k < a.M) ? ldg4(wp + (size_t)k * a.N) : zero4; }
+        xreg = (xvalid && k0 + 4 * kq < a.M) ? ldg4(xp + k0) : zero4;
+    };
+    auto sstore = [&](int b) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) *reinterpret_cast<float4 *>(&Ws[b][wr + 4 * e][4 * wq]) = wreg[e];
+        const int c = tid >> 2;
+        Xs[b][4 * kq + 0][c] = xreg.x; Xs[b][4 * kq + 1][c] = xreg.y; Xs[b][4 * kq + 2][c] = xreg.z; Xs[b][4 * kq + 3][c] = xreg.w;
+    };
+    // ---- compute roles: warp (wn, wc) owns 64 outputs x 16 columns; lane (ln, lc) outputs nA..nA+3, nA+32..nA+35, columns cc..cc+3 ----
+    const int wn = warp & 1, wc = warp >> 1, ln = lane & 7, lc = lane >> 3;
+    const int nA = wn * 64 + ln * 4, cc = wc * 16 + lc * 4;
+    float acc[8][4];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const int i = i0 + nA + (r & 3) + (r >> 2) * 32;
+        const float b = i < a.N ? __ldg(&a.bias[i]) : 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[r][c] = b;
+    }
+    const int nk = (a.M + GT_K - 1) / GT_K;
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    for (int kt = 0; kt < nk; kt++) {
+        const int b = kt & 1;
+        if (kt + 1 < nk) gload((kt + 1) * GT_K);
+        const int klen = min(GT_K, a.M - kt * GT_K);          // the last tile of a 252-input layer is short: no zero-padded terms are added
+        auto step = [&](int kk) {
+            const float4 wa = *reinterpret_cast<const float4 *>(&Ws[b][kk][nA]);
+            const float4 wb = *reinterpret_cast<const float4 *>(&Ws[b][kk][nA + 32]);
+            const float4 x = *reinterpret_cast<const float4 *>(&Xs[b][kk][cc]);
+            const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w}, xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) acc[r][c] = __fmaf_rn(w[r], xv[c], acc[r][c]);
+        };
+        if (klen == GT_K) {
+#pragma unroll
+            for (int kk = 0; kk < GT_K; kk++) step(kk);
+        } else {
+            for (int kk = 0; kk < klen; kk++) step(kk);
+        }
+        if (kt + 1 < nk) sstore(b ^ 1);
+        __syncthreads();
+    }
+    // ---- epilogue: activation, warm-up zeroing, store ----
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const int col = c0 + cc + c;
+        if (col >= a.ncols) continue;
+        const int s = col / a.F, f = col - s * a.F;
+        const bool zero = a.fc && __ldg(&a.fc[s]) + f < a.zthr;
+        float *yp = a.Y + (size_t)s * a.ys + (size_t)f * a.yf + a.y0 + i0 + nA;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            if (i0 + nA + 32 * h >= a.N) continue;
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                float y = acc[4 * h + e][c];
+                if (TANH) y = tanh_approx(y, a.rcp16);
+                v[e] = zero ? 0.f : y;
+            }
+            *reinterpret_cast<float4 *>(yp + 32 * h) = make_float4(v[0], v[1], v[2], v[3]);
+        }
     }
 }
 
-struct FrameNetArgs {
-    const float *embed_pitch, *conv1_w, *conv1_b, *conv2_w, *conv2_b, *dense1_w, *dense1_b, *dense2_w, *dense2_b;
-    const float *gad_w, *gad_b, *gbd_w, *gbd_b;
-    const uint16_t *rcp16;
+struct FrameIoArgs {
+    const float *embed_pitch;
     float *conv1_state, *conv2_state;
     const float *features; long long stream_stride; int frame_stride;
-    int n, nframes;
-    int *frame_count;        // [n] per-stream frame counter (lpcnet.c:119), read at entry, advanced by nframes (saturating at 1000) at exit
-    int na;                  // GRU_A units: gru_a_dense_feature has 3*na outputs
-    int features_delay;      // FEATURES_DELAY of the model (conv2 warm-up zeroing, lpcnet.c:101)
-    float *condA, *condB;
-    float *lpc_e2e;          // END2END models: [nframes][n][16] LPC from the network's reflection coefficients (lpcnet.c:107-108), else NULL
+    int n, F;
+    int *frame_count;
+    float *E1, *E2;          // row buffers [n][F+2][84] / [n][F+2][128]: rows 0,1 = the carried frames (conv state), row 2+f = frame f
+    const float *CD;         // [n][F][128] conditioning vectors (END2END: the first 16 are reflection coefficients)
+    float *lpc_e2e;          // [F][n][16] or NULL
 };
 
 // rc2lpc (lpcnet.c:57-78): reflection coefficients -> direct-form LPC, the reference's exact (unusual) recursion
@@ -60,193 +148,96 @@ __device__ __forceinline__ void rc2lpc_dev(float *lpc, const float *rc)
     for (int i = 0; i < LPC_ORDER; i++) lpc[i] = tmp[i];
 }
 
-__global__ void __launch_bounds__(FT) frame_net_kernel(const FrameNetArgs a)
+// input assembly (lpcnet.c:93-96): one block per stream fills its rows of E1 (features | pitch embedding) and the carried rows of E1 / E2
+__global__ void __launch_bounds__(128) frame_assemble_kernel(const FrameIoArgs a)
 {
-    __shared__ __align__(16) float xin[3 * FRAME_IN][TS];   // conv1 input window: [2 old frames | current]
-    __shared__ __align__(16) float x2[3 * COND][TS];        // conv2 input window
-    __shared__ __align__(16) float c2[COND][TS], d1[COND][TS], cd[COND][TS];
-    __shared__ int pitch_s[TS];
-    __shared__ int fc_s[TS];                                // frame_count of the block's streams
-    const int tid = threadIdx.x;
-    const int s0 = blockIdx.x * TS;
-    auto sid = [&](int k) { return min(s0 + k, a.n - 1); };   // tail block: replicate the last stream, stores masked
-
-    for (int e = tid; e < 2 * FRAME_IN * TS; e += FT) { int j = e / TS, k = e % TS; xin[j][k] = a.conv1_state[(size_t)sid(k) * 2 * FRAME_IN + j]; }
-    for (int e = tid; e < 2 * COND * TS; e += FT) { int j = e / TS, k = e % TS; x2[j][k] = a.conv2_state[(size_t)sid(k) * 2 * COND + j]; }
-    if (tid < TS) fc_s[tid] = a.frame_count[sid(tid)];
-    __syncthreads();
-
-    for (int f = 0; f < a.nframes; f++) {
-        // ---- input assembly (lpcnet.c:93-96) ----
-        if (tid < TS) {
-            const float *ft = a.features + (size_t)sid(tid) * a.stream_stride + (size_t)f * a.frame_stride;
+    const int s = blockIdx.x, tid = threadIdx.x;
+    float *e1 = a.E1 + (size_t)s * (a.F + 2) * FRAME_IN, *e2 = a.E2 + (size_t)s * (a.F + 2) * COND;
+    for (int e = tid; e < 2 * FRAME_IN; e += blockDim.x) e1[e] = a.conv1_state[(size_t)s * 2 * FRAME_IN + e];
+    for (int e = tid; e < 2 * COND; e += blockDim.x) e2[e] = a.conv2_state[(size_t)s * 2 * COND + e];
+    for (int e = tid; e < a.F * FRAME_IN; e += blockDim.x) {
+        const int f = e / FRAME_IN, j = e - f * FRAME_IN;
+        const float *ft = a.features + (size_t)s * a.stream_stride + (size_t)f * a.frame_stride;
+        float v;
+        if (j < NB_FEAT) v = ft[j];
+        else {
             // pitch = (int)floor(.1 + 50*features[NB_BANDS]+100): 50*f is a float product, the sums are double
             int p = (int)floor((.1 + (double)__fmul_rn(50.f, ft[NB_BANDS])) + 100.0);
-            pitch_s[tid] = min(255, max(33, p));
+            p = min(255, max(33, p));
+            v = __ldg(&a.embed_pitch[p * PITCH_EMBED + (j - NB_FEAT)]);
         }
-        for (int e = tid; e < NB_FEAT * TS; e += FT) {
-            int j = e / TS, k = e % TS;
-            xin[2 * FRAME_IN + j][k] = a.features[(size_t)sid(k) * a.stream_stride + (size_t)f * a.frame_stride + j];
-        }
-        __syncthreads();
-        for (int e = tid; e < PITCH_EMBED * TS; e += FT) {
-            int j = e / TS, k = e % TS;
-            xin[2 * FRAME_IN + NB_FEAT + j][k] = __ldg(&a.embed_pitch[pitch_s[k] * PITCH_EMBED + j]);
-        }
-        __syncthreads();
-        float y[TS];
-        // ---- conv1 (nnet.c:452-470; zeroed while frame_count < FEATURE_CONV1_DELAY=1, lpcnet.c:99) ----
-        {
-            const float b = __ldg(&a.conv1_b[tid]);
-#pragma unroll
-            for (int k = 0; k < TS; k++) y[k] = b;
-            layer_accum<3 * FRAME_IN>(y, a.conv1_w, COND, tid, xin);
-#pragma unroll
-            for (int k = 0; k < TS; k++) x2[2 * COND + tid][k] = fc_s[k] < 1 ? 0.f : tanh_approx(y[k], a.rcp16);
-        }
-        __syncthreads();
-        // conv1 window shift, mem <- tmp[nb_inputs:] (nnet.c:469): two passes through registers because source and
-        // destination rows overlap
-        {
-            float tmpv[(2 * FRAME_IN * TS + FT - 1) / FT];
-            int c = 0;
-            for (int e = tid; e < 2 * FRAME_IN * TS; e += FT, c++) tmpv[c] = xin[FRAME_IN + e / TS][e % TS];
-            __syncthreads();
-            c = 0;
-            for (int e = tid; e < 2 * FRAME_IN * TS; e += FT, c++) xin[e / TS][e % TS] = tmpv[c];
-        }
-        // ---- conv2 (zeroed while frame_count < FEATURES_DELAY, lpcnet.c:101) ----
-        {
-            const float b = __ldg(&a.conv2_b[tid]);
-#pragma unroll
-            for (int k = 0; k < TS; k++) y[k] = b;
-            layer_accum<3 * COND>(y, a.conv2_w, COND, tid, x2);
-#pragma unroll
-            for (int k = 0; k < TS; k++) c2[tid][k] = fc_s[k] < a.features_delay ? 0.f : tanh_approx(y[k], a.rcp16);
-        }
-        __syncthreads();
-        {
-            float tmpv[(2 * COND * TS + FT - 1) / FT];
-            int c = 0;
-            for (int e = tid; e < 2 * COND * TS; e += FT, c++) tmpv[c] = x2[COND + e / TS][e % TS];
-            __syncthreads();
-            c = 0;
-            for (int e = tid; e < 2 * COND * TS; e += FT, c++) x2[e / TS][e % TS] = tmpv[c];
-        }
-        // ---- dense1, dense2 (tanh) ----
-        {
-            const float b = __ldg(&a.dense1_b[tid]);
-#pragma unroll
-            for (int k = 0; k < TS; k++) y[k] = b;
-            layer_accum<COND>(y, a.dense1_w, COND, tid, c2);
-#pragma unroll
-            for (int k = 0; k < TS; k++) d1[tid][k] = tanh_approx(y[k], a.rcp16);
-        }
-        __syncthreads();
-        {
-            const float b = __ldg(&a.dense2_b[tid]);
-#pragma unroll
-            for (int k = 0; k < TS; k++) y[k] = b;
-            layer_accum<COND>(y, a.dense2_w, COND, tid, d1);
-#pragma unroll
-            for (int k = 0; k < TS; k++) cd[tid][k] = tanh_approx(y[k], a.rcp16);
-        }
-        __syncthreads();
-        // ---- END2END: the first 16 conditioning outputs are reflection coefficients (lpcnet.c:105,107-108) ----
-        if (a.lpc_e2e && tid < TS && s0 + tid < a.n) {
-            float rc[LPC_ORDER], lp[LPC_ORDER];
-            for (int i = 0; i < LPC_ORDER; i++) rc[i] = cd[i][tid];
-            rc2lpc_dev(lp, rc);
-            float *o = a.lpc_e2e + ((size_t)f * a.n + s0 + tid) * LPC_ORDER;
-            for (int i = 0; i < LPC_ORDER; i++) o[i] = lp[i];
-        }
-        // ---- gru_a_dense_feature (128 -> 3*na, linear) and gru_b_dense_feature (128 -> 48, linear) ----
-        const int na3 = 3 * a.na;
-        for (int o = 0; o < na3 / FT; o++) {
-            const int i = o * FT + tid;
-            const float b = __ldg(&a.gad_b[i]);
-#pragma unroll
-            for (int k = 0; k < TS; k++) y[k] = b;
-            layer_accum<COND>(y, a.gad_w, na3, i, cd);
-#pragma unroll
-            for (int k = 0; k < TS; k++) if (s0 + k < a.n) a.condA[((size_t)f * a.n + s0 + k) * na3 + i] = y[k];
-        }
-        if (tid < 3 * NB) {
-            const float b = __ldg(&a.gbd_b[tid]);
-#pragma unroll
-            for (int k = 0; k < TS; k++) y[k] = b;
-            layer_accum<COND>(y, a.gbd_w, 3 * NB, tid, cd);
-#pragma unroll
-            for (int k = 0; k < TS; k++) if (s0 + k < a.n) a.condB[((size_t)f * a.n + s0 + k) * (3 * NB) + tid] = y[k];
-        }
-        __syncthreads();
-        if (tid < TS && fc_s[tid] < 1000) fc_s[tid]++;      // lpcnet.c:119 (visible to the next frame after its first barrier)
+        e1[(size_t)(2 + f) * FRAME_IN + j] = v;
     }
-    __syncthreads();
-    if (tid < TS && s0 + tid < a.n) a.frame_count[s0 + tid] = fc_s[tid];
-    for (int e = tid; e < 2 * FRAME_IN * TS; e += FT) { int j = e / TS, k = e % TS; if (s0 + k < a.n) a.conv1_state[(size_t)(s0 + k) * 2 * FRAME_IN + j] = xin[j][k]; }
-    for (int e = tid; e < 2 * COND * TS; e += FT) { int j = e / TS, k = e % TS; if (s0 + k < a.n) a.conv2_state[(size_t)(s0 + k) * 2 * COND + j] = x2[j][k]; }
+}
+
+// after the layers: new conv states = the last two rows (mem <- tmp[nb_inputs:], nnet.c:469), frame counters (lpcnet.c:119),
+// END2END LPC (lpcnet.c:105,107-108)
+__global__ void __launch_bounds__(128) frame_finish_kernel(const FrameIoArgs a)
+{
+    const int s = blockIdx.x, tid = threadIdx.x;
+    const float *e1 = a.E1 + ((size_t)s * (a.F + 2) + a.F) * FRAME_IN, *e2 = a.E2 + ((size_t)s * (a.F + 2) + a.F) * COND;
+    for (int e = tid; e < 2 * FRAME_IN; e += blockDim.x) a.conv1_state[(size_t)s * 2 * FRAME_IN + e] = e1[e];
+    for (int e = tid; e < 2 * COND; e += blockDim.x) a.conv2_state[(size_t)s * 2 * COND + e] = e2[e];
+    if (tid == 0) a.frame_count[s] = min(1000, a.frame_count[s] + a.F);
+    if (a.lpc_e2e && tid < a.F) {
+        float lp[LPC_ORDER];
+        rc2lpc_dev(lp, a.CD + ((size_t)s * a.F + tid) * COND);
+        float *o = a.lpc_e2e + ((size_t)tid * a.n + s) * LPC_ORDER;
+        for (int i = 0; i < LPC_ORDER; i++) o[i] = lp[i];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// cepstrum -> LPC, one thread per (frame, stream).  The 320-point complex FFT follows the reference's mixed-radix
-// schedule (factors 5,4,4,4: lpcnet_tables.c:200) butterfly for butterfly so that the 17 autocorrelation lags — and
-// hence the LPCs, the prediction and every u-law index derived from it — are bit-identical.
+// cepstrum -> LPC, one WARP per (frame, stream).  The 320-point complex FFT follows the reference's mixed-radix schedule
+// (factors 5,4,4,4: lpcnet_tables.c:200) butterfly for butterfly, so that the 17 autocorrelation lags — and hence the LPCs,
+// the prediction and every u-law index derived from it — are bit-identical; the 80 (64) butterflies of a stage are independent
+// and are dealt to the lanes, the data lives in shared memory.  IDCT rows and the spectral interpolation are spread over the
+// lanes the same way (each output is still one sequential chain); the Levinson recursion is serial and runs on lane 0.
 struct c32 { float r, i; };
 #define CMUL(m_, a_, b_) do { (m_).r = (a_).r * (b_).r - (a_).i * (b_).i; (m_).i = (a_).r * (b_).i + (a_).i * (b_).r; } while (0)
 #define CADD(r_, a_, b_) do { (r_).r = (a_).r + (b_).r; (r_).i = (a_).i + (b_).i; } while (0)
 #define CSUB(r_, a_, b_) do { (r_).r = (a_).r - (b_).r; (r_).i = (a_).i - (b_).i; } while (0)
 
-__device__ void radix4(c32 *Fout, int fstride, const c32 *__restrict__ tw, int m, int N, int mm)   // kiss_fft.c:101-170
+// kiss_fft.c:101-170 (kf_bfly4), one butterfly; m == 1: the twiddle-free first stage
+__device__ __forceinline__ void bfly4_first(c32 *Fout)
 {
-    if (m == 1) {
-        for (int i = 0; i < N; i++) {
-            c32 s0, s1;
-            CSUB(s0, Fout[0], Fout[2]); CADD(Fout[0], Fout[0], Fout[2]);
-            CADD(s1, Fout[1], Fout[3]); CSUB(Fout[2], Fout[0], s1); CADD(Fout[0], Fout[0], s1);
-            CSUB(s1, Fout[1], Fout[3]);
-            Fout[1].r = s0.r + s1.i; Fout[1].i = s0.i - s1.r;
-            Fout[3].r = s0.r - s1.i; Fout[3].i = s0.i + s1.r;
-            Fout += 4;
-        }
-    } else {
-        c32 *beg = Fout; const int m2 = 2 * m, m3 = 3 * m;
-        for (int i = 0; i < N; i++) {
-            Fout = beg + i * mm;
-            for (int j = 0; j < m; j++) {
-                c32 s0, s1, s2, s3, s4, s5;
-                const c32 t1 = tw[j * fstride], t2 = tw[j * fstride * 2], t3 = tw[j * fstride * 3];
-                CMUL(s0, Fout[m], t1); CMUL(s1, Fout[m2], t2); CMUL(s2, Fout[m3], t3);
-                CSUB(s5, Fout[0], s1); CADD(Fout[0], Fout[0], s1);
-                CADD(s3, s0, s2); CSUB(s4, s0, s2);
-                CSUB(Fout[m2], Fout[0], s3);
-                CADD(Fout[0], Fout[0], s3);
-                Fout[m].r = s5.r + s4.i; Fout[m].i = s5.i - s4.r;
-                Fout[m3].r = s5.r - s4.i; Fout[m3].i = s5.i + s4.r;
-                ++Fout;
-            }
-        }
-    }
+    c32 s0, s1;
+    CSUB(s0, Fout[0], Fout[2]); CADD(Fout[0], Fout[0], Fout[2]);
+    CADD(s1, Fout[1], Fout[3]); CSUB(Fout[2], Fout[0], s1); CADD(Fout[0], Fout[0], s1);
+    CSUB(s1, Fout[1], Fout[3]);
+    Fout[1].r = s0.r + s1.i; Fout[1].i = s0.i - s1.r;
+    Fout[3].r = s0.r - s1.i; Fout[3].i = s0.i + s1.r;
 }
-__device__ void radix5_last(c32 *F0, const c32 *__restrict__ tw)     // kiss_fft.c:232-311 with m=64, N=1, fstride=1
+__device__ __forceinline__ void bfly4(c32 *Fout, int m, const c32 t1, const c32 t2, const c32 t3)
+{
+    const int m2 = 2 * m, m3 = 3 * m;
+    c32 s0, s1, s2, s3, s4, s5;
+    CMUL(s0, Fout[m], t1); CMUL(s1, Fout[m2], t2); CMUL(s2, Fout[m3], t3);
+    CSUB(s5, Fout[0], s1); CADD(Fout[0], Fout[0], s1);
+    CADD(s3, s0, s2); CSUB(s4, s0, s2);
+    CSUB(Fout[m2], Fout[0], s3);
+    CADD(Fout[0], Fout[0], s3);
+    Fout[m].r = s5.r + s4.i; Fout[m].i = s5.i - s4.r;
+    Fout[m3].r = s5.r - s4.i; Fout[m3].i = s5.i + s4.r;
+}
+// kiss_fft.c:232-311 (kf_bfly5) with m = 64, N = 1, fstride = 1: butterfly u
+__device__ __forceinline__ void bfly5_last(c32 *F0, int u, const c32 *__restrict__ tw)
 {
     const int m = 64;
     const c32 ya = tw[m], yb = tw[2 * m];
+    F0 += u;
     c32 *F1 = F0 + m, *F2 = F0 + 2 * m, *F3 = F0 + 3 * m, *F4 = F0 + 4 * m;
-    for (int u = 0; u < m; ++u) {
-        c32 s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11, s12;
-        s0 = *F0;
-        CMUL(s1, *F1, tw[u]); CMUL(s2, *F2, tw[2 * u]); CMUL(s3, *F3, tw[3 * u]); CMUL(s4, *F4, tw[4 * u]);
-        CADD(s7, s1, s4); CSUB(s10, s1, s4); CADD(s8, s2, s3); CSUB(s9, s2, s3);
-        F0->r = F0->r + (s7.r + s8.r); F0->i = F0->i + (s7.i + s8.i);
-        s5.r = s0.r + (s7.r * ya.r + s8.r * yb.r); s5.i = s0.i + (s7.i * ya.r + s8.i * yb.r);
-        s6.r = s10.i * ya.i + s9.i * yb.i; s6.i = -(s10.r * ya.i + s9.r * yb.i);
-        CSUB(*F1, s5, s6); CADD(*F4, s5, s6);
-        s11.r = s0.r + (s7.r * yb.r + s8.r * ya.r); s11.i = s0.i + (s7.i * yb.r + s8.i * ya.r);
-        s12.r = s9.i * ya.i - s10.i * yb.i; s12.i = s10.r * yb.i - s9.r * ya.i;
-        CADD(*F2, s11, s12); CSUB(*F3, s11, s12);
-        ++F0; ++F1; ++F2; ++F3; ++F4;
-    }
+    c32 s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11, s12;
+    s0 = *F0;
+    CMUL(s1, *F1, tw[u]); CMUL(s2, *F2, tw[2 * u]); CMUL(s3, *F3, tw[3 * u]); CMUL(s4, *F4, tw[4 * u]);
+    CADD(s7, s1, s4); CSUB(s10, s1, s4); CADD(s8, s2, s3); CSUB(s9, s2, s3);
+    F0->r = F0->r + (s7.r + s8.r); F0->i = F0->i + (s7.i + s8.i);
+    s5.r = s0.r + (s7.r * ya.r + s8.r * yb.r); s5.i = s0.i + (s7.i * ya.r + s8.i * yb.r);
+    s6.r = s10.i * ya.i + s9.i * yb.i; s6.i = -(s10.r * ya.i + s9.r * yb.i);
+    CSUB(*F1, s5, s6); CADD(*F4, s5, s6);
+    s11.r = s0.r + (s7.r * yb.r + s8.r * ya.r); s11.i = s0.i + (s7.i * yb.r + s8.i * ya.r);
+    s12.r = s9.i * ya.i - s10.i * yb.i; s12.i = s10.r * yb.i - s9.r * ya.i;
+    CADD(*F2, s11, s12); CSUB(*F3, s11, s12);
 }
 
 struct LpcArgs {
@@ -255,66 +246,77 @@ struct LpcArgs {
     float *lpc_raw;       // [nframes+2][n][16]; this kernel fills entries 2..nframes+1
 };
 
-__global__ void __launch_bounds__(64) lpc_kernel(const LpcArgs a)
+constexpr int LPC_WARPS = 4;
+__constant__ short c_eband5ms[NB_BANDS] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 14, 16, 20, 24, 28, 34, 40};               // freq.c:45-48
+__constant__ float c_compensation[NB_BANDS] = {0.8f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 0.666667f, 0.5f, 0.5f, 0.5f,
+                                               0.333333f, 0.25f, 0.25f, 0.2f, 0.166667f, 0.173913f};                  // freq.c:50-52
+
+__global__ void __launch_bounds__(LPC_WARPS * 32) lpc_kernel(const LpcArgs a)
 {
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (long long)a.n * a.nframes) return;
+    __shared__ c32 ysh[LPC_WARPS][WINDOW_SIZE];
+    __shared__ float exsh[LPC_WARPS][NB_BANDS + 2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long gid = (long long)blockIdx.x * LPC_WARPS + warp;
+    if (gid >= (long long)a.n * a.nframes) return;               // (whole warps leave; only __syncwarp below)
     const int f = (int)(gid / a.n), s = (int)(gid % a.n);
     const float *cep = a.features + (size_t)s * a.stream_stride + (size_t)f * a.frame_stride;
-    const short eband5ms[NB_BANDS] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 14, 16, 20, 24, 28, 34, 40};               // freq.c:45-48
-    const float compensation[NB_BANDS] = {0.8f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 0.666667f, 0.5f, 0.5f, 0.5f,
-                                          0.333333f, 0.25f, 0.25f, 0.2f, 0.166667f, 0.173913f};                  // freq.c:50-52
-    float tmp[NB_BANDS], Ex[NB_BANDS];
-    for (int i = 0; i < NB_BANDS; i++) tmp[i] = cep[i];
-    tmp[0] += 4;
-    const double idct_scale = sqrt(2. / NB_BANDS);
-    for (int i = 0; i < NB_BANDS; i++) {                          // idct freq.c:230-240
+    c32 *y = ysh[warp];
+    float *Ex = exsh[warp];
+    // idct (freq.c:230-240) + 10^x * compensation (freq.c:318): band i on lane i
+    if (lane < NB_BANDS) {
         float sum = 0;
-        for (int j = 0; j < NB_BANDS; j++) sum += tmp[j] * __ldg(&a.dct[i * NB_BANDS + j]);
-        Ex[i] = (float)((double)sum * idct_scale);
+        for (int j = 0; j < NB_BANDS; j++) { const float t = j == 0 ? cep[0] + 4 : cep[j]; sum += t * __ldg(&a.dct[lane * NB_BANDS + j]); }
+        const double idct_scale = sqrt(2. / NB_BANDS);
+        const float e = (float)((double)sum * idct_scale);
+        Ex[lane] = (float)(pow(10.0, (double)e) * (double)c_compensation[lane]);
     }
-    for (int i = 0; i < NB_BANDS; i++) Ex[i] = (float)(pow(10.0, (double)Ex[i]) * (double)compensation[i]);   // freq.c:318
+    __syncwarp();
     // interp_band_gain (freq.c:202-215) + Hermitian extension (freq.c:256-266) + scale & digit-reverse (kiss_fft.c:575-584)
-    c32 y[WINDOW_SIZE];
-    {
-        float Xr[FREQ_SIZE];
-        for (int i = 0; i < FREQ_SIZE; i++) Xr[i] = 0;
-        for (int i = 0; i < NB_BANDS - 1; i++) {
-            int band_size = (eband5ms[i + 1] - eband5ms[i]) * 4;
-            for (int j = 0; j < band_size; j++) {
-                float frac = __fdiv_rn((float)j, (float)band_size);
-                Xr[(eband5ms[i] * 4) + j] = (1 - frac) * Ex[i] + frac * Ex[i + 1];
-            }
+    const float scale = 1.f / WINDOW_SIZE;
+    for (int i = lane; i < WINDOW_SIZE; i += 32) {
+        const int k = i < FREQ_SIZE ? i : WINDOW_SIZE - i;          // bin whose gain this sample carries
+        float xr = 0.f;                                             // bin 160 stays 0 (freq.c:285)
+        if (k < FREQ_SIZE - 1) {
+            int b = 0;
+            while (b < NB_BANDS - 2 && k >= c_eband5ms[b + 1] * 4) b++;
+            const int band_size = (c_eband5ms[b + 1] - c_eband5ms[b]) * 4, j = k - c_eband5ms[b] * 4;
+            const float frac = __fdiv_rn((float)j, (float)band_size);
+            xr = (1 - frac) * Ex[b] + frac * Ex[b + 1];
         }
-        Xr[FREQ_SIZE - 1] = 0;
-        const float scale = 1.f / WINDOW_SIZE;
-        for (int i = 0; i < WINDOW_SIZE; i++) {
-            float xr = i < FREQ_SIZE ? Xr[i] : Xr[WINDOW_SIZE - i];
-            float xi = i < FREQ_SIZE ? 0.f : -0.f;
-            int o = a.bitrev[i];
-            y[o].r = scale * xr; y[o].i = scale * xi;
-        }
+        const float xi = i < FREQ_SIZE ? 0.f : -0.f;
+        const int o = a.bitrev[i];
+        y[o].r = scale * xr; y[o].i = scale * xi;
     }
-    radix4(y, 80, a.tw, 1, 80, 4);
-    radix4(y, 20, a.tw, 4, 20, 16);
-    radix4(y, 5, a.tw, 16, 5, 64);
-    radix5_last(y, a.tw);
+    __syncwarp();
+    for (int i = lane; i < 80; i += 32) bfly4_first(y + 4 * i);                               // m = 1,  N = 80
+    __syncwarp();
+    for (int b = lane; b < 80; b += 32) { const int i = b >> 2, j = b & 3; bfly4(y + i * 16 + j, 4, a.tw[j * 20], a.tw[j * 40], a.tw[j * 60]); }      // m = 4,  N = 20, fstride 20
+    __syncwarp();
+    for (int b = lane; b < 80; b += 32) { const int i = b >> 4, j = b & 15; bfly4(y + i * 64 + j, 16, a.tw[j * 5], a.tw[j * 10], a.tw[j * 15]); }     // m = 16, N = 5,  fstride 5
+    __syncwarp();
+    for (int u = lane; u < 64; u += 32) bfly5_last(y, u, a.tw);
+    __syncwarp();
+    if (lane != 0) return;
     float ac[LPC_ORDER + 1];
     ac[0] = WINDOW_SIZE * y[0].r;
     for (int i = 1; i < LPC_ORDER + 1; i++) ac[i] = WINDOW_SIZE * y[WINDOW_SIZE - i].r;
     ac[0] = (float)((double)ac[0] + ((double)ac[0] * 1e-4 + 320 / 12 / 38.));       // freq.c:292
     for (int i = 1; i < LPC_ORDER + 1; i++) ac[i] = (float)((double)ac[i] * (1 - 6e-5 * i * i));   // freq.c:294
     float lpc[LPC_ORDER];
+#pragma unroll
     for (int i = 0; i < LPC_ORDER; i++) lpc[i] = 0;
     {                                                             // lpcn_lpc freq.c:86-127 (float build)
         float error = ac[0];
         if (ac[0] != 0) {
+#pragma unroll
             for (int i = 0; i < LPC_ORDER; i++) {
                 float rr = 0;
+#pragma unroll
                 for (int j = 0; j < i; j++) rr += lpc[j] * ac[i - j];
                 rr += ac[i + 1];
                 float r = __fdiv_rn(-rr, error);
                 lpc[i] = r;
+#pragma unroll
                 for (int j = 0; j < (i + 1) >> 1; j++) {
                     float t1 = lpc[j], t2 = lpc[i - 1 - j];
                     lpc[j] = t1 + r * t2;
@@ -326,6 +328,7 @@ __global__ void __launch_bounds__(64) lpc_kernel(const LpcArgs a)
         }
     }
     float *out = a.lpc_raw + ((size_t)(f + 2) * a.n + s) * LPC_ORDER;
+#pragma unroll
     for (int i = 0; i < LPC_ORDER; i++) out[i] = lpc[i];
 }
 
@@ -352,19 +355,40 @@ __global__ void lpc_carry_out_kernel(float *carry, const float *lpc_raw, int n, 
 void launch_frame_network(const DeviceModel &m, const FrameState &fs, const float *d_features, long long stream_stride,
                           int frame_stride, int n, int nframes, float *condA, float *condB, float *lpc_raw, cudaStream_t st)
 {
-    FrameNetArgs fa{m.embed_pitch, m.conv1_w, m.conv1_b, m.conv2_w, m.conv2_b, m.dense1_w, m.dense1_b, m.dense2_w, m.dense2_b,
-                    m.gad_w, m.gad_b, m.gbd_w, m.gbd_b, m.rcp16, fs.conv1_state, fs.conv2_state, d_features, stream_stride,
-                    frame_stride, n, nframes, fs.frame_count, m.na, m.cfg.features_delay, condA, condB,
-                    m.cfg.end2end ? lpc_raw + (size_t)2 * n * LPC_ORDER : nullptr};
-    frame_net_kernel<<<(n + TS - 1) / TS, FT, 0, st>>>(fa);
+    const int F = nframes, na3 = 3 * m.na;
+    // scratch rows of this chunk (FrameState::work, sized for FRAME_CHUNK frames): E1 [n][F+2][84], E2 [n][F+2][128], P, Q [n][F][128]
+    float *E1 = fs.work, *E2 = E1 + (size_t)n * (FRAME_CHUNK + 2) * FRAME_IN, *P = E2 + (size_t)n * (FRAME_CHUNK + 2) * COND, *Q = P + (size_t)n * FRAME_CHUNK * COND;
+    FrameIoArgs io{m.embed_pitch, fs.conv1_state, fs.conv2_state, d_features, stream_stride, frame_stride, n, F, fs.frame_count, E1, E2, P,
+                   m.cfg.end2end ? lpc_raw + (size_t)2 * n * LPC_ORDER : nullptr};
+    frame_assemble_kernel<<<n, 128, 0, st>>>(io);
+    const int ncols = n * F;
+    auto gemm = [&](bool tanh_act, const float *W, const float *bias, int M, int N, const float *X, int xS, int xF,
+                    float *Y, long long ys, long long yf, long long y0, const int *fc, int zthr) {
+        GemmArgs g{W, bias, M, N, X, xS, xF, Y, ys, yf, y0, F, ncols, fc, zthr, m.rcp16};
+        dim3 grid((ncols + GT_C - 1) / GT_C, (N + GT_N - 1) / GT_N);
+        if (tanh_act) frame_gemm_kernel<true><<<grid, GT_THREADS, 0, st>>>(g);
+        else frame_gemm_kernel<false><<<grid, GT_THREADS, 0, st>>>(g);
+    };
+    // conv1 (nnet.c:452-470; zeroed while frame_count < FEATURE_CONV1_DELAY = 1, lpcnet.c:99): window = rows f..f+2 of E1 -> row 2+f of E2
+    gemm(true, m.conv1_w, m.conv1_b, 3 * FRAME_IN, COND, E1, F + 2, FRAME_IN, E2, (long long)(F + 2) * COND, COND, 2 * COND, fs.frame_count, 1);
+    // conv2 (zeroed while frame_count < FEATURES_DELAY, lpcnet.c:101)
+    gemm(true, m.conv2_w, m.conv2_b, 3 * COND, COND, E2, F + 2, COND, P, (long long)F * COND, COND, 0, fs.frame_count, m.cfg.features_delay);
+    gemm(true, m.dense1_w, m.dense1_b, COND, COND, P, F, COND, Q, (long long)F * COND, COND, 0, nullptr, 0);
+    gemm(true, m.dense2_w, m.dense2_b, COND, COND, Q, F, COND, P, (long long)F * COND, COND, 0, nullptr, 0);
+    // gru_a_dense_feature (128 -> 3*na, linear) and gru_b_dense_feature (128 -> 48, linear): outputs frame-major [f][n][.]
+    gemm(false, m.gad_w, m.gad_b, COND, na3, P, F, COND, condA, na3, (long long)n * na3, 0, nullptr, 0);
+    gemm(false, m.gbd_w, m.gbd_b, COND, 3 * NB, P, F, COND, condB, 3 * NB, (long long)n * 3 * NB, 0, nullptr, 0);
+    frame_finish_kernel<<<n, 128, 0, st>>>(io);
     if (m.cfg.end2end) return;                                 // no cepstrum -> LPC path, no delay line (lpcnet.c:107-108)
     const int tpb = 128;
     lpc_carry_in_kernel<<<(n * LPC_ORDER + tpb - 1) / tpb, tpb, 0, st>>>(fs.lpc_carry, lpc_raw, n);
     LpcArgs la{d_features, stream_stride, frame_stride, n, nframes, m.dct, reinterpret_cast<const c32 *>(m.twiddles), m.bitrev, lpc_raw};
     long long tot = (long long)n * nframes;
-    lpc_kernel<<<(unsigned)((tot + 63) / 64), 64, 0, st>>>(la);
+    lpc_kernel<<<(unsigned)((tot + LPC_WARPS - 1) / LPC_WARPS), LPC_WARPS * 32, 0, st>>>(la);
     lpc_carry_out_kernel<<<(n * LPC_ORDER + tpb - 1) / tpb, tpb, 0, st>>>(fs.lpc_carry, lpc_raw, n, nframes);
 }
+int frame_network_launches(const DeviceModel &m) { return m.cfg.end2end ? 8 : 11; }
+size_t frame_work_floats(size_t n) { return n * ((size_t)(FRAME_CHUNK + 2) * (FRAME_IN + COND) + 2 * (size_t)FRAME_CHUNK * COND); }
 
 // ------------------------------------------------------------------------------------------------------------------
 // decode_packet (lpcnet_dec.c:81-155): 64-bit packet -> 4 feature frames; one thread per stream, packets in order
