@@ -1,11 +1,11 @@
 /* lpcnet.h — public C API of the B200-native LPCNet synthesis engine.
  *
- * Drop-in for the synthesis / decoder / model-loading subset of xiph/LPCNet's public header
- * (reference: include/lpcnet.h).  Every prototype below has the same name, argument list, return type and
- * meaning as the reference declaration cited next to it, so `src/lpcnet_demo.c -synthesis/-decode` and any
- * embedding application re-link against liblpcnet_b200.so unchanged.  Encoder, feature-extraction and PLC
- * entry points of the reference header (include/lpcnet.h:103-155,191-212) are NOT part of the accelerated
- * path and are not exported.
+ * Drop-in for the synthesis / decoder / encoder / feature-extraction / model-loading part of xiph/LPCNet's public
+ * header (reference: include/lpcnet.h).  Every prototype below has the same name, argument list, return type and
+ * meaning as the reference declaration cited next to it, so `src/lpcnet_demo.c -features/-encode/-synthesis/-decode`
+ * and any embedding application re-link against liblpcnet_b200.so unchanged.  The PLC entry points of the reference
+ * header (include/lpcnet.h:191-212) are not exported: they need the PLC model (plc_data), which is outside the path; what
+ * the PLC calls on the synthesis side (preload, tail, deferred frame network, state copies) is in lpcnet_b200.h.
  *
  * All state lives on the GPU.  The opaque structs below only hold a handle; `*_get_size()` is the size of that
  * handle.  There is no CPU fallback: if no CUDA device is usable `*_create` returns NULL, `*_init` returns -1
@@ -35,6 +35,20 @@ extern "C" {
 
 typedef struct LPCNetState LPCNetState;
 typedef struct LPCNetDecState LPCNetDecState;
+typedef struct LPCNetEncState LPCNetEncState;
+
+/* ---- encoder / feature extraction (PCM -> 1.6 kb/s packets, PCM -> feature frames) ---- */
+LPCNET_EXPORT int lpcnet_encoder_get_size(void);                         /* ref :103 */
+LPCNET_EXPORT int lpcnet_encoder_init(LPCNetEncState *st);               /* ref :112 returns 0 */
+LPCNET_EXPORT LPCNetEncState *lpcnet_encoder_create(void);               /* ref :117 */
+LPCNET_EXPORT void lpcnet_encoder_destroy(LPCNetEncState *st);           /* ref :122 */
+/* pcm: LPCNET_PACKET_SAMPLES shorts in, buf: LPCNET_COMPRESSED_SIZE bytes out; returns 0 */
+LPCNET_EXPORT int lpcnet_encode(LPCNetEncState *st, const short *pcm, unsigned char *buf);   /* ref :130 */
+/* 640 samples -> four unquantised feature vectors */
+LPCNET_EXPORT int lpcnet_compute_features(LPCNetEncState *st, const short *pcm, float features[4][NB_TOTAL_FEATURES]);   /* ref :138 */
+/* LPCNET_FRAME_SIZE samples -> one feature vector (what `lpcnet_demo -features` writes per frame) */
+LPCNET_EXPORT int lpcnet_compute_single_frame_features(LPCNetEncState *st, const short *pcm, float features[NB_TOTAL_FEATURES]);        /* ref :146 */
+LPCNET_EXPORT int lpcnet_compute_single_frame_features_float(LPCNetEncState *st, const float *pcm, float features[NB_TOTAL_FEATURES]);  /* ref :155 */
 
 /* ---- decoder (1.6 kb/s packets -> PCM) ---- */
 LPCNET_EXPORT int lpcnet_decoder_get_size(void);                         /* ref :67  */

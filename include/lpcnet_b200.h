@@ -200,6 +200,30 @@ LPCNET_EXPORT int lpcnet_b200_batch_decode(LPCNetB200Batch *b, const unsigned ch
 LPCNET_EXPORT int lpcnet_b200_batch_decode_device(LPCNetB200Batch *b, const unsigned char *d_packets, int npackets,
                                                   short *d_pcm, void *cuda_stream);
 
+/* == the analysis side, batched: feature extraction and the 1.6 kb/s encoder ==
+ * n independent LPCNetEncState streams (reference src/lpcnet_private.h:55-75) on one device, all starting from
+ * lpcnet_encoder_create() (zeroed state, src/lpcnet_enc.c:471-482).  Results equal the reference's per-stream calls. */
+typedef struct LPCNetB200EncBatch LPCNetB200EncBatch;
+LPCNET_EXPORT LPCNetB200EncBatch *lpcnet_b200_enc_create(int n_streams, int device);
+LPCNET_EXPORT void lpcnet_b200_enc_destroy(LPCNetB200EncBatch *e);
+LPCNET_EXPORT int lpcnet_b200_enc_reset(LPCNetB200EncBatch *e);                      /* lpcnet_encoder_init() for every stream */
+LPCNET_EXPORT int lpcnet_b200_enc_streams(const LPCNetB200EncBatch *e);
+/* the VQ codebooks lpcnet_encode searches (same four arrays, same order as lpcnet_b200_batch_set_codebooks) */
+LPCNET_EXPORT int lpcnet_b200_enc_set_codebooks(LPCNetB200EncBatch *e, const float *cb, size_t n_floats);
+/* == lpcnet_compute_single_frame_features() per stream and frame (src/lpcnet_enc.c:919; `lpcnet_demo -features`) ==
+ * pcm [n_streams][nframes*160] int16 (or float: lpcnet_compute_single_frame_features_float) -> features [n_streams][nframes][36]
+ * (18 cepstral coefficients, pitch, pitch correlation, 16 LPC: the `.f32` feature-file row the synthesis side reads) */
+LPCNET_EXPORT int lpcnet_b200_enc_compute_features(LPCNetB200EncBatch *e, const short *pcm, int nframes, float *features);
+LPCNET_EXPORT int lpcnet_b200_enc_compute_features_float(LPCNetB200EncBatch *e, const float *pcm, int nframes, float *features);
+LPCNET_EXPORT int lpcnet_b200_enc_compute_features_device(LPCNetB200EncBatch *e, const short *d_pcm, int nframes, float *d_features, void *cuda_stream);
+/* == lpcnet_encode() per stream and 640-sample packet (src/lpcnet_enc.c:882) ==  pcm [n][npackets*640] -> packets [n][npackets][8] */
+LPCNET_EXPORT int lpcnet_b200_enc_encode(LPCNetB200EncBatch *e, const short *pcm, int npackets, unsigned char *packets);
+LPCNET_EXPORT int lpcnet_b200_enc_encode_device(LPCNetB200EncBatch *e, const short *d_pcm, int npackets, unsigned char *d_packets, void *cuda_stream);
+/* == lpcnet_compute_features() (src/lpcnet_enc.c:896): unquantised 4-frame analysis ==  pcm [n][npackets*640] -> features [n][npackets*4][36] */
+LPCNET_EXPORT int lpcnet_b200_enc_compute_features4(LPCNetB200EncBatch *e, const short *pcm, int npackets, float *features);
+/* Test hook (host only): the analysis window and DCT table as the engine builds them (src/dump_lpcnet_tables.c:83-96): hw[160], dct[324] */
+LPCNET_EXPORT void lpcnet_b200_enc_tables(float *half_window, float *dct);
+
 /* ---- introspection used by the tests and the benchmark ---- */
 /* Device time (ms, CUDA events on the engine's stream) the per-sample kernel took in the last synthesize/decode
  * call, summed over its launches; *launches receives how many engine kernels that call launched in total. */

@@ -111,6 +111,21 @@ def lib():
     L.lpcnet_b200_shard_range.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, c_p, c_p]
     L.lpcnet_b200_device_alloc_on.restype = c_p
     L.lpcnet_b200_device_alloc_on.argtypes = [ctypes.c_int, ctypes.c_size_t]
+    # analysis side (csrc/enc_kernels.cu)
+    L.lpcnet_b200_enc_create.restype = c_p
+    L.lpcnet_b200_enc_create.argtypes = [ctypes.c_int, ctypes.c_int]
+    L.lpcnet_b200_enc_destroy.argtypes = [c_p]
+    L.lpcnet_b200_enc_reset.argtypes = [c_p]
+    L.lpcnet_b200_enc_streams.argtypes = [c_p]
+    L.lpcnet_b200_enc_set_codebooks.argtypes = [c_p, c_p, ctypes.c_size_t]
+    L.lpcnet_b200_enc_compute_features.argtypes = [c_p, c_p, ctypes.c_int, c_p]
+    L.lpcnet_b200_enc_compute_features_float.argtypes = [c_p, c_p, ctypes.c_int, c_p]
+    L.lpcnet_b200_enc_compute_features_device.argtypes = [c_p, c_p, ctypes.c_int, c_p, c_p]
+    L.lpcnet_b200_enc_encode.argtypes = [c_p, c_p, ctypes.c_int, c_p]
+    L.lpcnet_b200_enc_encode_device.argtypes = [c_p, c_p, ctypes.c_int, c_p, c_p]
+    L.lpcnet_b200_enc_compute_features4.argtypes = [c_p, c_p, ctypes.c_int, c_p]
+    L.lpcnet_b200_enc_tables.restype = None
+    L.lpcnet_b200_enc_tables.argtypes = [c_p, c_p]
     # reference API (include/lpcnet.h)
     L.lpcnet_create.restype = c_p
     L.lpcnet_destroy.argtypes = [c_p]
@@ -281,6 +296,67 @@ class Multi:
         finally:
             self._L.lpcnet_b200_device_free(d)
         return pcm
+
+
+class EncBatch:
+    """n independent analysis streams on one GPU (lpcnet_b200_enc_*, csrc/enc_kernels.cu): feature extraction and the encoder."""
+
+    def __init__(self, n_streams, device=0, codebooks=None):
+        self._L = lib()
+        self._h = self._L.lpcnet_b200_enc_create(int(n_streams), int(device))
+        if not self._h:
+            raise LPCNetB200Error("lpcnet_b200_enc_create: " + _err())
+        self.n = int(n_streams)
+        if codebooks is not None:
+            cb = np.ascontiguousarray(codebooks, dtype=np.float32)
+            if self._L.lpcnet_b200_enc_set_codebooks(self._h, cb.ctypes.data, cb.size) != 0:
+                raise LPCNetB200Error(_err())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.lpcnet_b200_enc_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reset(self):
+        if self._L.lpcnet_b200_enc_reset(self._h) != 0:
+            raise LPCNetB200Error(_err())
+
+    def compute_features(self, pcm):
+        """pcm [n][T*160] int16 (or float32: the _float entry point) -> features [n][T][36]."""
+        p = np.ascontiguousarray(pcm)
+        assert p.ndim == 2 and p.shape[0] == self.n and p.shape[1] % 160 == 0
+        T = p.shape[1] // 160
+        out = np.zeros((self.n, T, 36), np.float32)
+        if p.dtype == np.float32:
+            r = self._L.lpcnet_b200_enc_compute_features_float(self._h, p.ctypes.data, T, out.ctypes.data)
+        else:
+            p = np.ascontiguousarray(p, dtype=np.int16)
+            r = self._L.lpcnet_b200_enc_compute_features(self._h, p.ctypes.data, T, out.ctypes.data)
+        if r != 0:
+            raise LPCNetB200Error("lpcnet_b200_enc_compute_features: " + _err())
+        return out
+
+    def encode(self, pcm):
+        """pcm [n][P*640] int16 -> packets [n][P][8] uint8."""
+        p = np.ascontiguousarray(pcm, dtype=np.int16)
+        assert p.ndim == 2 and p.shape[0] == self.n and p.shape[1] % 640 == 0
+        P = p.shape[1] // 640
+        out = np.zeros((self.n, P, 8), np.uint8)
+        if self._L.lpcnet_b200_enc_encode(self._h, p.ctypes.data, P, out.ctypes.data) != 0:
+            raise LPCNetB200Error("lpcnet_b200_enc_encode: " + _err())
+        return out
+
+    def compute_features4(self, pcm):
+        """pcm [n][P*640] int16 -> features [n][P*4][36] (lpcnet_compute_features: superframe analysis without quantisation)."""
+        p = np.ascontiguousarray(pcm, dtype=np.int16)
+        assert p.ndim == 2 and p.shape[0] == self.n and p.shape[1] % 640 == 0
+        P = p.shape[1] // 640
+        out = np.zeros((self.n, P * 4, 36), np.float32)
+        if self._L.lpcnet_b200_enc_compute_features4(self._h, p.ctypes.data, P, out.ctypes.data) != 0:
+            raise LPCNetB200Error("lpcnet_b200_enc_compute_features4: " + _err())
+        return out
 
 
 class Batch:

@@ -21,17 +21,25 @@ using lpcnet_b200::set_error;
 
 struct LPCNetState { uint32_t magic; uint32_t flags; LPCNetB200Batch *batch; };
 struct LPCNetDecState { LPCNetState lpcnet_state; };   // same first-member layout as src/lpcnet_private.h:50-53
+struct LPCNetEncState { uint32_t magic; uint32_t flags; LPCNetB200EncBatch *enc; };
 
 namespace {
 const uint32_t MAGIC = 0x4C50424Eu;   // "LPBN"
 std::mutex g_mu;
 std::vector<LPCNetB200Batch *> g_registry;
+std::vector<LPCNetB200EncBatch *> g_enc_registry;
 std::vector<unsigned char> g_model;
 std::vector<float> g_codebooks;
 float g_gamma = -1.0f;      // <= 0: not given -> the blob's metadata record, else 1 (lpcnet_b200_batch_create)
 bool g_env_checked = false, g_atexit = false;
 
-void drain() { std::lock_guard<std::mutex> l(g_mu); for (auto *b : g_registry) lpcnet_b200_batch_destroy(b); g_registry.clear(); }
+void drain()
+{
+    std::lock_guard<std::mutex> l(g_mu);
+    for (auto *b : g_registry) lpcnet_b200_batch_destroy(b);
+    for (auto *e : g_enc_registry) lpcnet_b200_enc_destroy(e);
+    g_registry.clear(); g_enc_registry.clear();
+}
 
 bool read_file(const char *path, std::vector<unsigned char> &out)
 {
@@ -198,6 +206,72 @@ int lpcnet_decode(LPCNetDecState *st, const unsigned char *buf, short *pcm)
     }
     if (lpcnet_b200_batch_decode(st->lpcnet_state.batch, buf, 1, pcm) != 0) { memset(pcm, 0, sizeof(short) * LPCNET_PACKET_SAMPLES); return -1; }
     return 0;
+}
+
+
+// ---- encoder / feature extraction: a batch of ONE analysis stream behind the reference's LPCNetEncState API (lpcnet_enc.c:466-486,882-933) ----
+static void enc_release(LPCNetEncState *st)
+{
+    if (st->magic == MAGIC && st->enc) {
+        bool mine = false;
+        { std::lock_guard<std::mutex> l(g_mu); for (size_t i = 0; i < g_enc_registry.size(); i++) if (g_enc_registry[i] == st->enc) { g_enc_registry.erase(g_enc_registry.begin() + i); mine = true; break; } }
+        if (mine) lpcnet_b200_enc_destroy(st->enc);
+    }
+    st->enc = nullptr;
+}
+int lpcnet_encoder_get_size(void) { return (int)sizeof(LPCNetEncState); }
+int lpcnet_encoder_init(LPCNetEncState *st)
+{
+    if (!st) return -1;
+    enc_release(st);
+    st->magic = MAGIC; st->flags = 0; st->enc = nullptr;
+    LPCNetB200EncBatch *e = lpcnet_b200_enc_create(1, device_id());
+    if (!e) return -1;
+    std::lock_guard<std::mutex> l(g_mu);
+    check_env();
+    if (!g_codebooks.empty()) lpcnet_b200_enc_set_codebooks(e, g_codebooks.data(), g_codebooks.size());
+    g_enc_registry.push_back(e);
+    if (!g_atexit) { atexit(drain); g_atexit = true; }
+    st->enc = e;
+    return 0;
+}
+LPCNetEncState *lpcnet_encoder_create(void)
+{
+    LPCNetEncState *st = (LPCNetEncState *)calloc(1, sizeof(LPCNetEncState));
+    if (!st) return nullptr;
+    if (lpcnet_encoder_init(st) != 0) { free(st); return nullptr; }
+    return st;
+}
+void lpcnet_encoder_destroy(LPCNetEncState *st)
+{
+    if (!st) return;
+    enc_release(st);
+    free(st);
+}
+static LPCNetB200EncBatch *enc_of(LPCNetEncState *st, const char *who)
+{
+    if (!st || st->magic != MAGIC || !st->enc) { set_error("%s: encoder state not initialised", who); return nullptr; }
+    return st->enc;
+}
+int lpcnet_encode(LPCNetEncState *st, const short *pcm, unsigned char *buf)
+{
+    LPCNetB200EncBatch *e = enc_of(st, "lpcnet_encode");
+    return e && lpcnet_b200_enc_encode(e, pcm, 1, buf) == 0 ? 0 : -1;
+}
+int lpcnet_compute_features(LPCNetEncState *st, const short *pcm, float features[4][NB_TOTAL_FEATURES])
+{
+    LPCNetB200EncBatch *e = enc_of(st, "lpcnet_compute_features");
+    return e && lpcnet_b200_enc_compute_features4(e, pcm, 1, &features[0][0]) == 0 ? 0 : -1;
+}
+int lpcnet_compute_single_frame_features(LPCNetEncState *st, const short *pcm, float features[NB_TOTAL_FEATURES])
+{
+    LPCNetB200EncBatch *e = enc_of(st, "lpcnet_compute_single_frame_features");
+    return e && lpcnet_b200_enc_compute_features(e, pcm, 1, features) == 0 ? 0 : -1;
+}
+int lpcnet_compute_single_frame_features_float(LPCNetEncState *st, const float *pcm, float features[NB_TOTAL_FEATURES])
+{
+    LPCNetB200EncBatch *e = enc_of(st, "lpcnet_compute_single_frame_features_float");
+    return e && lpcnet_b200_enc_compute_features_float(e, pcm, 1, features) == 0 ? 0 : -1;
 }
 
 }  // extern "C"

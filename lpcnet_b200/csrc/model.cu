@@ -523,6 +523,30 @@ int debug_build_image_n(const unsigned char *blob, int len, unsigned char *out, 
     return (int)hm.img_n.size();
 }
 
+// DCT / FFT tables exactly as src/dump_lpcnet_tables.c:53,87-93 and kiss_fft.c:406-421 build them (host libm); shared with the
+// analysis side (enc_kernels.cu)
+void build_fft_tables(std::vector<float> &dct, std::vector<float> &tw, std::vector<int16_t> &br)
+{
+    static const int factors[8] = {5, 64, 4, 16, 4, 4, 4, 1};
+    dct.assign(NB_BANDS * NB_BANDS, 0.f); tw.assign(2 * WINDOW_SIZE, 0.f); br.assign(WINDOW_SIZE, 0);
+    for (int i = 0; i < NB_BANDS; i++) for (int j = 0; j < NB_BANDS; j++) {
+        dct[i * NB_BANDS + j] = cos((i + .5) * j * M_PI / NB_BANDS);
+        if (j == 0) dct[i * NB_BANDS + j] *= sqrt(.5);
+    }
+    for (int i = 0; i < WINDOW_SIZE; i++) {
+        const double pi = 3.14159265358979323846264338327;
+        double phase = (-2 * pi / WINDOW_SIZE) * i;
+        tw[2 * i] = (float)cos(phase); tw[2 * i + 1] = (float)sin(phase);
+    }
+    // digit-reversal permutation of the 5x4x4x4 decomposition (compute_bitrev_table, kiss_fft.c:314-345)
+    struct Rec { static void go(int Fout, int16_t *f, int fstride, const int *fac) {
+        int p = fac[0], mm = fac[1];
+        if (mm == 1) { for (int j = 0; j < p; j++) { *f = (int16_t)(Fout + j); f += fstride; } }
+        else { for (int j = 0; j < p; j++) { go(Fout, f, fstride * p, fac + 2); f += fstride; Fout += mm; } }
+    } };
+    Rec::go(0, br.data(), 1, factors);
+}
+
 int model_load(DeviceModel *m, const unsigned char *blob, int len, const ModelConfig *cfg)
 {
     HostModel hm;
@@ -550,26 +574,9 @@ int model_load(DeviceModel *m, const unsigned char *blob, int len, const ModelCo
     UP(gbd_w, gbd_w, COND * 3 * NB) UP(gbd_b, gbd_b, 3 * NB)
     UP(rcp16, kRcpTable, 2048)
     {
-        // DCT / FFT tables exactly as src/dump_lpcnet_tables.c:53,87-93 and kiss_fft.c:406-421 build them (host libm)
-        static const int factors[8] = {5, 64, 4, 16, 4, 4, 4, 1};
-        std::vector<float> dct(NB_BANDS * NB_BANDS), tw(2 * WINDOW_SIZE);
-        std::vector<int16_t> br(WINDOW_SIZE);
-        for (int i = 0; i < NB_BANDS; i++) for (int j = 0; j < NB_BANDS; j++) {
-            dct[i * NB_BANDS + j] = cos((i + .5) * j * M_PI / NB_BANDS);
-            if (j == 0) dct[i * NB_BANDS + j] *= sqrt(.5);
-        }
-        for (int i = 0; i < WINDOW_SIZE; i++) {
-            const double pi = 3.14159265358979323846264338327;
-            double phase = (-2 * pi / WINDOW_SIZE) * i;
-            tw[2 * i] = (float)cos(phase); tw[2 * i + 1] = (float)sin(phase);
-        }
-        // digit-reversal permutation of the 5x4x4x4 decomposition (compute_bitrev_table, kiss_fft.c:314-345)
-        struct Rec { static void go(int Fout, int16_t *f, int fstride, const int *fac) {
-            int p = fac[0], mm = fac[1];
-            if (mm == 1) { for (int j = 0; j < p; j++) { *f = (int16_t)(Fout + j); f += fstride; } }
-            else { for (int j = 0; j < p; j++) { go(Fout, f, fstride * p, fac + 2); f += fstride; Fout += mm; } }
-        } };
-        Rec::go(0, br.data(), 1, factors);
+        std::vector<float> dct, tw;
+        std::vector<int16_t> br;
+        build_fft_tables(dct, tw, br);
         UP(dct, dct.data(), dct.size()) UP(twiddles, tw.data(), tw.size()) UP(bitrev, br.data(), br.size())
         float gp[LPC_ORDER]; float gi = lpc_gamma;
         for (int i = 0; i < LPC_ORDER; i++) { gp[i] = gi; gi *= lpc_gamma; }   // freq.c:299-308

@@ -1,14 +1,11 @@
 /* TEST INFRASTRUCTURE.  The reference CLI (src/lpcnet_demo.c) also references the encoder and PLC entry points,
- * which are outside the accelerated path.  These stubs let the UNTOUCHED demo source link against
- * liblpcnet_b200.so so that its -synthesis and -decode modes exercise the drop-in API; the other modes abort. */
+ * The encoder side is served by liblpcnet_b200.so itself; only the PLC (needs the PLC model) and two internal helpers the
+ * demo's `-addlpc` mode calls are outside it.  These stubs let the UNTOUCHED demo source link against liblpcnet_b200.so so
+ * that its -features, -encode, -synthesis and -decode modes exercise the drop-in API; the PLC / addlpc modes abort. */
 #include <stdio.h>
 #include <stdlib.h>
 #include "lpcnet.h"
-static void na(const char *f) { fprintf(stderr, "%s: not part of the B200 synthesis engine\n", f); exit(2); }
-LPCNetEncState *lpcnet_encoder_create(void) { na("lpcnet_encoder_create"); return 0; }
-void lpcnet_encoder_destroy(LPCNetEncState *st) { (void)st; }
-int lpcnet_encode(LPCNetEncState *st, const short *pcm, unsigned char *buf) { (void)st; (void)pcm; (void)buf; na("lpcnet_encode"); return -1; }
-int lpcnet_compute_single_frame_features(LPCNetEncState *st, const short *pcm, float features[NB_TOTAL_FEATURES]) { (void)st; (void)pcm; (void)features; na("lpcnet_compute_single_frame_features"); return -1; }
+static void na(const char *f) { fprintf(stderr, "%s: not part of the B200 engine\n", f); exit(2); }
 LPCNetPLCState *lpcnet_plc_create(int options) { (void)options; na("lpcnet_plc_create"); return 0; }
 void lpcnet_plc_destroy(LPCNetPLCState *st) { (void)st; }
 int lpcnet_plc_update(LPCNetPLCState *st, short *pcm) { (void)st; (void)pcm; na("lpcnet_plc_update"); return -1; }

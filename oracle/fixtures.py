@@ -36,3 +36,34 @@ def make_packets(stream, npackets):
     """[npackets][8] uint8 uniform random codec packets (src/lpcnet_dec.c:81 consumes 64 bits each)."""
     rng = np.random.default_rng(2000 + int(stream))
     return rng.integers(0, 256, size=(npackets, 8), dtype=np.uint8)
+
+
+def make_pcm(stream, nframes):
+    """[nframes*160] int16 speech-like test signal for the analysis side: harmonic source with vibrato
+    (f0 80..300 Hz), a couple of formant-ish resonances, amplitude modulation with silent gaps, plus noise; seed 3000+s."""
+    rng = np.random.default_rng(3000 + int(stream))
+    n = nframes * 160
+    t = np.arange(n) / 16000.0
+    f0 = rng.uniform(80, 300) * (1 + 0.05 * np.sin(2 * np.pi * rng.uniform(3, 7) * t + rng.uniform(0, 6.28)))
+    f0 *= np.exp(0.15 * np.cumsum(rng.normal(0, 0.002, n)))
+    ph = 2 * np.pi * np.cumsum(f0) / 16000.0
+    src = sum(np.sin(k * ph + rng.uniform(0, 6.28)) / k for k in range(1, 24))
+    # two resonances (direct-form recursion on the excitation)
+    y = src + 0.3 * rng.normal(0, 1, n)
+    for fc, bw in ((rng.uniform(400, 900), 120.0), (rng.uniform(1400, 2600), 200.0)):
+        r = np.exp(-np.pi * bw / 16000.0)
+        a1, a2 = 2 * r * np.cos(2 * np.pi * fc / 16000.0), -r * r
+        out = np.zeros(n)
+        y1 = y2 = 0.0
+        for i in range(n):
+            v = y[i] + a1 * y1 + a2 * y2
+            out[i] = v
+            y2, y1 = y1, v
+        y = y + 0.5 * out
+    env = np.clip(0.55 + 0.6 * np.sin(2 * np.pi * rng.uniform(0.7, 2.5) * t + rng.uniform(0, 6.28)), 0, 1) ** 2   # gaps of near-silence
+    y = y / (np.abs(y).max() + 1e-9) * rng.uniform(3000, 15000) * env + rng.normal(0, 12, n)
+    return np.clip(np.rint(y), -32767, 32767).astype(np.int16)
+
+
+def make_pcm_batch(streams, nframes):
+    return np.stack([make_pcm(s, nframes) for s in streams])

@@ -108,6 +108,57 @@ void ref_frame_network_deferred(void *st, const float *features) { run_frame_net
 void ref_frame_network_flush(void *st) { run_frame_network_flush((LPCNetState *)st); }
 void ref_reset_signal(void *st) { lpcnet_reset_signal((LPCNetState *)st); }
 
+/* ---- encoder / feature extraction: the reference's own entry points on one stream with a fresh state ---- */
+/* lpcnet_compute_single_frame_features (lpcnet_enc.c:919) per 160-sample frame: pcm [nframes*160] -> features [nframes][36] */
+int ref_features_stream(const short *pcm, int nframes, float *features)
+{
+    int i;
+    LPCNetEncState *st = lpcnet_encoder_create();
+    for (i = 0; i < nframes; i++) lpcnet_compute_single_frame_features(st, pcm + (size_t)i * LPCNET_FRAME_SIZE, features + (size_t)i * NB_TOTAL_FEATURES);
+    lpcnet_encoder_destroy(st);
+    return 0;
+}
+int ref_features_stream_float(const float *pcm, int nframes, float *features)
+{
+    int i;
+    LPCNetEncState *st = lpcnet_encoder_create();
+    for (i = 0; i < nframes; i++) lpcnet_compute_single_frame_features_float(st, pcm + (size_t)i * LPCNET_FRAME_SIZE, features + (size_t)i * NB_TOTAL_FEATURES);
+    lpcnet_encoder_destroy(st);
+    return 0;
+}
+/* lpcnet_encode (lpcnet_enc.c:882) per 640-sample packet: pcm [npackets*640] -> packets [npackets][8] */
+int ref_encode_stream(const short *pcm, int npackets, unsigned char *packets)
+{
+    int i;
+    LPCNetEncState *st = lpcnet_encoder_create();
+    for (i = 0; i < npackets; i++) lpcnet_encode(st, pcm + (size_t)i * LPCNET_PACKET_SAMPLES, packets + (size_t)i * LPCNET_COMPRESSED_SIZE);
+    lpcnet_encoder_destroy(st);
+    return 0;
+}
+/* lpcnet_compute_features (lpcnet_enc.c:896): unquantised 4-frame analysis, pcm [npackets*640] -> features [npackets*4][36] */
+int ref_features4_stream(const short *pcm, int npackets, float *features)
+{
+    int i;
+    LPCNetEncState *st = lpcnet_encoder_create();
+    for (i = 0; i < npackets; i++) lpcnet_compute_features(st, pcm + (size_t)i * LPCNET_PACKET_SAMPLES, (float (*)[NB_TOTAL_FEATURES])(features + (size_t)i * 4 * NB_TOTAL_FEATURES));
+    lpcnet_encoder_destroy(st);
+    return 0;
+}
+/* a mixed call sequence on ONE state: encode, then single-frame analysis (pcount stays where lpcnet_encode left it) */
+int ref_encode_then_features(const short *pcm, int npackets, unsigned char *packets, int nframes, float *features)
+{
+    int i;
+    LPCNetEncState *st = lpcnet_encoder_create();
+    for (i = 0; i < npackets; i++) lpcnet_encode(st, pcm + (size_t)i * LPCNET_PACKET_SAMPLES, packets + (size_t)i * LPCNET_COMPRESSED_SIZE);
+    pcm += (size_t)npackets * LPCNET_PACKET_SAMPLES;
+    for (i = 0; i < nframes; i++) lpcnet_compute_single_frame_features(st, pcm + (size_t)i * LPCNET_FRAME_SIZE, features + (size_t)i * NB_TOTAL_FEATURES);
+    lpcnet_encoder_destroy(st);
+    return 0;
+}
+extern const float half_window[];
+extern const float dct_table[];
+void ref_enc_tables(float *hw /*[160]*/, float *dct /*[324]*/) { memcpy(hw, half_window, sizeof(float) * OVERLAP_SIZE); memcpy(dct, dct_table, sizeof(float) * NB_BANDS * NB_BANDS); }
+
 /* ---- many streams on a pool of host threads (golden generation at BASELINE sizes; work queue over streams) ---- */
 typedef struct {
     const unsigned char *blob; int len; const float *features; int stride; int nframes; short *pcm;

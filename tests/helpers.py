@@ -153,6 +153,12 @@ def ref_lib(build="A", tag=""):
     L.ref_activation.argtypes = [c_p, c_p, ctypes.c_int, ctypes.c_int]
     L.ref_state_create.restype = c_p
     L.ref_state_create.argtypes = [ctypes.c_char_p, ctypes.c_int]
+    for fn in ("ref_features_stream", "ref_features_stream_float", "ref_encode_stream", "ref_features4_stream"):
+        if hasattr(L, fn):
+            getattr(L, fn).argtypes = [c_p, ctypes.c_int, c_p]
+    if hasattr(L, "ref_encode_then_features"):
+        L.ref_encode_then_features.argtypes = [c_p, ctypes.c_int, c_p, ctypes.c_int, c_p]
+        L.ref_enc_tables.argtypes = [c_p, c_p]
     for fn, at in (("ref_state_destroy", [c_p]), ("ref_state_reset", [c_p]), ("ref_state_copy", [c_p, c_p]),
                    ("ref_synthesize_impl", [c_p, c_p, c_p, ctypes.c_int, ctypes.c_int]), ("ref_run_frame_network", [c_p, c_p]),
                    ("ref_synthesize_tail", [c_p, c_p, ctypes.c_int, ctypes.c_int]), ("ref_frame_network_deferred", [c_p, c_p]),
@@ -187,3 +193,38 @@ def stream_digests(pcm):
     """First 8 bytes of sha256 of every stream's PCM as uint64 [n] (a failing comparison names the stream)."""
     import hashlib
     return np.array([int.from_bytes(hashlib.sha256(np.ascontiguousarray(r).tobytes()).digest()[:8], "little") for r in pcm], dtype=np.uint64)
+
+
+# ---- the analysis side (SURVEY 8f N2): the compiled reference's encoder entry points, one fresh state per stream ----
+def ref_features(pcm, build="A"):
+    """pcm [n][T*160] int16 (or float32) -> features [n][T][36] via lpcnet_compute_single_frame_features(_float)."""
+    L = ref_lib(build)
+    p = np.ascontiguousarray(pcm)
+    n, T = p.shape[0], p.shape[1] // 160
+    out = np.zeros((n, T, 36), np.float32)
+    for s in range(n):
+        row = np.ascontiguousarray(p[s])
+        (L.ref_features_stream_float if p.dtype == np.float32 else L.ref_features_stream)(row.ctypes.data, T, out[s].ctypes.data)
+    return out
+
+
+def ref_encode(pcm, build="A"):
+    """pcm [n][P*640] int16 -> packets [n][P][8] via lpcnet_encode."""
+    L = ref_lib(build)
+    p = np.ascontiguousarray(pcm, dtype=np.int16)
+    n, P = p.shape[0], p.shape[1] // 640
+    out = np.zeros((n, P, 8), np.uint8)
+    for s in range(n):
+        L.ref_encode_stream(p[s].ctypes.data, P, out[s].ctypes.data)
+    return out
+
+
+def ref_features4(pcm, build="A"):
+    """pcm [n][P*640] int16 -> features [n][P*4][36] via lpcnet_compute_features."""
+    L = ref_lib(build)
+    p = np.ascontiguousarray(pcm, dtype=np.int16)
+    n, P = p.shape[0], p.shape[1] // 640
+    out = np.zeros((n, P * 4, 36), np.float32)
+    for s in range(n):
+        L.ref_features4_stream(p[s].ctypes.data, P, out[s].ctypes.data)
+    return out

@@ -181,3 +181,12 @@ def test_multi_create_refuses_without_devices(L):
         pytest.skip("a GPU is present")
     with pytest.raises(api.LPCNetB200Error, match="no CUDA device"):
         lpcnet_b200.Multi(8, H.blob("int8"), [0, 1])
+
+
+def test_analysis_tables_equal_the_reference_tables(L):
+    """half_window / dct_table as the engine generates them (double libm on the host) == the literals of src/lpcnet_tables.c."""
+    g = np.load(os.path.join(H.GOLDEN, "enc_A.npz"))
+    hw = np.zeros(160, np.float32); dct = np.zeros(324, np.float32)
+    L.lpcnet_b200_enc_tables(hw.ctypes.data, dct.ctypes.data)
+    assert np.array_equal(hw.view(np.uint32), g["half_window"].view(np.uint32))
+    assert np.array_equal(dct.view(np.uint32), g["dct_table"].view(np.uint32))
