@@ -565,7 +565,7 @@ __device__ void superframe(EncState &st, EncScratch &S, const EncTables &T, bool
 
 // MODE 0: lpcnet_compute_single_frame_features per frame; 1: lpcnet_encode per packet; 2: lpcnet_compute_features per packet
 template <int MODE>
-__global__ void __launch_bounds__(ENC_THREADS) enc_kernel(const EncArgs a)
+__global__ void __launch_bounds__(ENC_THREADS, 4) enc_kernel(const EncArgs a)
 {
     __shared__ EncState st;
     __shared__ EncScratch S;

@@ -23,10 +23,11 @@ namespace lpcnet_b200 {
 // per-stream row buffer that starts with the two carried frames (conv state).  One generic kernel, frame_gemm_kernel:
 //   Y[col][i] = act(bias[i] + sum_{j<M} W[j*N+i] * X[col][j]),   j ascending, one fmaf per term, accumulator starts at the bias
 // = the per-row FMA chain of sgemv_accum16 (vec_avx.h:618-643) for every output, so the result does not depend on the tiling.
-// Block tile 128 outputs x 32 columns x 16 k, 128 threads, thread tile 8 x 4 (32 FFMA per 3 LDS.128); W and X tiles are
-// double-buffered through shared memory (register-staged prefetch of the next k-tile while the current one is multiplied).
-// Small blocks on purpose: a layer has only ~1300 tiles at 4096 streams x 10 frames, 6 blocks per SM keep the SMs evenly loaded.
-constexpr int GT_N = 128, GT_C = 32, GT_K = 16, GT_XPAD = 36, GT_THREADS = 128;
+// Block tile 128 outputs x 32 columns x 16 k, 64 threads, thread tile 8 x 8 (64 FFMA per 4 LDS.128: with 8 x 4 tiles the kernel sat
+// on the shared-memory pipe at 91 %, profiles/r02e); W and X tiles are double-buffered through shared memory (register-staged
+// prefetch of the next k-tile while the current one is multiplied).  Small blocks on purpose: a layer has only ~1300 tiles at
+// 4096 streams x 10 frames, so many resident blocks per SM keep the SMs evenly loaded.
+constexpr int GT_N = 128, GT_C = 32, GT_K = 16, GT_XPAD = 36, GT_THREADS = 64;
 
 struct GemmArgs {
     const float *W, *bias; int M, N;       // W[j*N + i] (reference layout of dense / conv weights: dump_lpcnet.py:194-200,229-245)
@@ -44,37 +45,47 @@ __global__ void __launch_bounds__(GT_THREADS) frame_gemm_kernel(const GemmArgs a
     __shared__ __align__(16) float Xs[2][GT_K][GT_XPAD];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int c0 = blockIdx.x * GT_C, i0 = blockIdx.y * GT_N;
-    // ---- loader roles: X tile = 32 columns x 16 k (thread: column tid/4, 4 consecutive k), W tile = 16 k x 128 outputs (thread: 4 rows, one float4) ----
-    const int xc = c0 + (tid >> 2), kq = tid & 3;
-    const bool xvalid = xc < a.ncols;
-    const int xs_ = xvalid ? xc / a.F : 0, xf_ = xvalid ? xc - (xc / a.F) * a.F : 0;
-    const float *xp = a.X + ((size_t)xs_ * a.xS + xf_) * a.xF + 4 * kq;
+    // ---- loader roles: X tile = 32 columns x 16 k (thread: columns tid/4 and 16 + tid/4, 4 consecutive k each),
+    //      W tile = 16 k x 128 outputs (thread: 8 rows, one float4 each) ----
+    const int kq = tid & 3;
+    const float *xp[2]; bool xvalid[2];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int xc = c0 + (tid >> 2) + 16 * h;
+        xvalid[h] = xc < a.ncols;
+        const int xs_ = xvalid[h] ? xc / a.F : 0, xf_ = xvalid[h] ? xc - (xc / a.F) * a.F : 0;
+        xp[h] = a.X + ((size_t)xs_ * a.xS + xf_) * a.xF + 4 * kq;
+    }
     const int wq = tid & 31, wr = tid >> 5;
     const bool wvalid = i0 + 4 * wq < a.N;
     const float *wp = a.W + i0 + 4 * wq;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 wreg[4], xreg;
+    float4 wreg[8], xreg[2];
     auto gload = [&](int k0) {
 #pragma unroll
-        for (int e = 0; e < 4; e++) { const int k = k0 + wr + 4 * e; wreg[e] = (wvalid && k < a.M) ? ldg4(wp + (size_t)k * a.N) : zero4; }
-        xreg = (xvalid && k0 + 4 * kq < a.M) ? ldg4(xp + k0) : zero4;
+        for (int e = 0; e < 8; e++) { const int k = k0 + wr + 2 * e; wreg[e] = (wvalid && k < a.M) ? ldg4(wp + (size_t)k * a.N) : zero4; }
+#pragma unroll
+        for (int h = 0; h < 2; h++) xreg[h] = (xvalid[h] && k0 + 4 * kq < a.M) ? ldg4(xp[h] + k0) : zero4;
     };
     auto sstore = [&](int b) {
 #pragma unroll
-        for (int e = 0; e < 4; e++) *reinterpret_cast<float4 *>(&Ws[b][wr + 4 * e][4 * wq]) = wreg[e];
-        const int c = tid >> 2;
-        Xs[b][4 * kq + 0][c] = xreg.x; Xs[b][4 * kq + 1][c] = xreg.y; Xs[b][4 * kq + 2][c] = xreg.z; Xs[b][4 * kq + 3][c] = xreg.w;
+        for (int e = 0; e < 8; e++) *reinterpret_cast<float4 *>(&Ws[b][wr + 2 * e][4 * wq]) = wreg[e];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int c = (tid >> 2) + 16 * h;
+            Xs[b][4 * kq + 0][c] = xreg[h].x; Xs[b][4 * kq + 1][c] = xreg[h].y; Xs[b][4 * kq + 2][c] = xreg[h].z; Xs[b][4 * kq + 3][c] = xreg[h].w;
+        }
     };
-    // ---- compute roles: warp (wn, wc) owns 64 outputs x 16 columns; lane (ln, lc) outputs nA..nA+3, nA+32..nA+35, columns cc..cc+3 ----
-    const int wn = warp & 1, wc = warp >> 1, ln = lane & 7, lc = lane >> 3;
-    const int nA = wn * 64 + ln * 4, cc = wc * 16 + lc * 4;
-    float acc[8][4];
+    // ---- compute roles: warp wn owns 64 outputs x all 32 columns; lane (ln, lc) outputs nA..nA+3, nA+32..nA+35, columns cc..cc+7 ----
+    const int wn = warp, ln = lane & 7, lc = lane >> 3;
+    const int nA = wn * 64 + ln * 4, cc = lc * 8;
+    float acc[8][8];
 #pragma unroll
     for (int r = 0; r < 8; r++) {
         const int i = i0 + nA + (r & 3) + (r >> 2) * 32;
         const float b = i < a.N ? __ldg(&a.bias[i]) : 0.f;
 #pragma unroll
-        for (int c = 0; c < 4; c++) acc[r][c] = b;
+        for (int c = 0; c < 8; c++) acc[r][c] = b;
     }
     const int nk = (a.M + GT_K - 1) / GT_K;
     gload(0);
@@ -87,12 +98,13 @@ __global__ void __launch_bounds__(GT_THREADS) frame_gemm_kernel(const GemmArgs a
         auto step = [&](int kk) {
             const float4 wa = *reinterpret_cast<const float4 *>(&Ws[b][kk][nA]);
             const float4 wb = *reinterpret_cast<const float4 *>(&Ws[b][kk][nA + 32]);
-            const float4 x = *reinterpret_cast<const float4 *>(&Xs[b][kk][cc]);
-            const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w}, xv[4] = {x.x, x.y, x.z, x.w};
+            const float4 xa = *reinterpret_cast<const float4 *>(&Xs[b][kk][cc]);
+            const float4 xb = *reinterpret_cast<const float4 *>(&Xs[b][kk][cc + 4]);
+            const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w}, xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
             for (int r = 0; r < 8; r++)
 #pragma unroll
-                for (int c = 0; c < 4; c++) acc[r][c] = __fmaf_rn(w[r], xv[c], acc[r][c]);
+                for (int c = 0; c < 8; c++) acc[r][c] = __fmaf_rn(w[r], xv[c], acc[r][c]);
         };
         if (klen == GT_K) {
 #pragma unroll
@@ -105,7 +117,7 @@ __global__ void __launch_bounds__(GT_THREADS) frame_gemm_kernel(const GemmArgs a
     }
     // ---- epilogue: activation, warm-up zeroing, store ----
 #pragma unroll
-    for (int c = 0; c < 4; c++) {
+    for (int c = 0; c < 8; c++) {
         const int col = c0 + cc + c;
         if (col >= a.ncols) continue;
         const int s = col / a.F, f = col - s * a.F;
