@@ -831,3 +831,6 @@ double oracle_synthesize_batch(const OModel *m, const float *features, int strid
 { return run_batch(m, features, stride, NULL, n_streams, nframes, nthreads, pcm); }
 double oracle_decode_batch(const OModel *m, const unsigned char *packets, int n_streams, int npackets, int nthreads, short *pcm)
 { return run_batch(m, NULL, 0, packets, n_streams, npackets, nthreads, pcm); }
+
+/* ------------------------------------------------------------------ analysis side ------------------------------------------------------------------ */
+#include "lpcnet_enc_oracle.inc"

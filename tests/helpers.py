@@ -59,7 +59,7 @@ def rcp_table():
 def oracle_lib():
     so = os.path.join(ORACLE, "_build", "liblpcnet_oracle.so")
     src = os.path.join(ORACLE, "lpcnet_oracle.c")
-    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(os.path.join(ORACLE, "lpcnet_enc_oracle.inc"))):
         subprocess.check_call(["make", "-C", ORACLE, "port"], stdout=subprocess.DEVNULL)
     L = ctypes.CDLL(so)
     L.oracle_model_create.restype = c_p
@@ -95,6 +95,12 @@ def oracle_lib():
     L.oracle_synthesize_batch.argtypes = [c_p, c_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_p]
     L.oracle_decode_batch.restype = ctypes.c_double
     L.oracle_decode_batch.argtypes = [c_p, c_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_p]
+    L.oracle_enc_create.restype = c_p
+    L.oracle_enc_create.argtypes = [c_p]
+    L.oracle_enc_destroy.argtypes = [c_p]
+    L.oracle_enc_single_frame_features.argtypes = [c_p, c_p, c_p]
+    L.oracle_enc_encode.argtypes = [c_p, c_p, c_p]
+    L.oracle_enc_compute_features.argtypes = [c_p, c_p, c_p]
     return L
 
 
@@ -227,4 +233,36 @@ def ref_features4(pcm, build="A"):
     out = np.zeros((n, P * 4, 36), np.float32)
     for s in range(n):
         L.ref_features4_stream(p[s].ctypes.data, P, out[s].ctypes.data)
+    return out
+
+
+# ---- CPU restatement of the analysis side (oracle/lpcnet_enc_oracle.inc), one fresh state per stream ----
+def oracle_features(pcm):
+    L = oracle_lib()
+    p = np.ascontiguousarray(pcm, dtype=np.int16)
+    n, T = p.shape[0], p.shape[1] // 160
+    out = np.zeros((n, T, 36), np.float32)
+    for s in range(n):
+        e = L.oracle_enc_create(None)
+        for t in range(T):
+            L.oracle_enc_single_frame_features(e, p[s, t * 160:].ctypes.data, out[s, t].ctypes.data)
+        L.oracle_enc_destroy(e)
+    return out
+
+
+def oracle_encode(pcm, features4=False):
+    """pcm [n][P*640] -> packets [n][P][8] (lpcnet_encode), or with features4 the unquantised features [n][P*4][36] (lpcnet_compute_features)."""
+    L = oracle_lib()
+    p = np.ascontiguousarray(pcm, dtype=np.int16)
+    n, P = p.shape[0], p.shape[1] // 640
+    cb = codebooks()
+    out = np.zeros((n, P * 4, 36), np.float32) if features4 else np.zeros((n, P, 8), np.uint8)
+    for s in range(n):
+        e = L.oracle_enc_create(cb.ctypes.data)
+        for k in range(P):
+            if features4:
+                L.oracle_enc_compute_features(e, p[s, k * 640:].ctypes.data, out[s, 4 * k].ctypes.data)
+            else:
+                L.oracle_enc_encode(e, p[s, k * 640:].ctypes.data, out[s, k].ctypes.data)
+        L.oracle_enc_destroy(e)
     return out

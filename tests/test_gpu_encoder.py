@@ -142,6 +142,22 @@ def test_codec_round_trip_through_both_engines(eng):
     assert np.abs(out[:, 640:]).max() > 0
 
 
+def test_fresh_inputs_against_the_oracle_port(eng):
+    """48 other streams x 40 frames against the CPU restatement (oracle/lpcnet_enc_oracle.inc, pinned to the reference by the CPU suite)."""
+    n, T = 48, 40
+    pcm = make_pcm_batch(range(300, 300 + n), T)
+    e = eng.EncBatch(n, codebooks=H.codebooks())
+    f = e.compute_features(pcm)
+    e.reset()
+    pk = e.encode(pcm)
+    e.reset()
+    f4 = e.compute_features4(pcm)
+    e.close()
+    assert_same_floats(f, H.oracle_features(pcm), "features vs oracle port")
+    np.testing.assert_array_equal(pk, H.oracle_encode(pcm))
+    assert_same_floats(f4, H.oracle_encode(pcm, features4=True), "features4 vs oracle port")
+
+
 @pytest.mark.skipif(not H.have_ref("A"), reason="compiled reference (oracle/_ref) did not travel")
 def test_fresh_inputs_against_the_compiled_reference(eng):
     """96 other streams x 60 frames (15 packets): features and packets equal the compiled reference run on this host."""

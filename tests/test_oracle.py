@@ -231,3 +231,30 @@ def test_oracle_port_plc_entry_points_match_reference(build, tag):
         got = S.run_single("oracle", H.oracle_lib(), S.OracleState(kind, tag), f, stream, script)
         np.testing.assert_array_equal(got, want)
         assert np.abs(want).max() > 0
+
+
+# ---------------------------------------------------------------- analysis side
+def test_oracle_encoder_port_matches_reference_goldens():
+    """oracle/lpcnet_enc_oracle.inc (CPU restatement of src/lpcnet_enc.c) against the vectors the compiled reference produced:
+    per-frame features, packets and the unquantised 4-frame features, every float bit for bit."""
+    G = np.load(os.path.join(H.GOLDEN, "enc_A.npz"))
+    assert np.array_equal(H.oracle_features(G["pcm"]).view(np.uint32), G["features"].view(np.uint32))
+    assert np.array_equal(H.oracle_encode(G["pcm"]), G["packets"])
+    assert np.array_equal(H.oracle_encode(G["pcm"], features4=True).view(np.uint32), G["features4"].view(np.uint32))
+    # the packets carry voiced and unvoiced frames and several modulation values (the fixture exercises both branches of :654-665)
+    bits = np.zeros(G["packets"].shape[:2], np.uint64)
+    for i in range(8):
+        bits = (bits << np.uint64(8)) | G["packets"][:, :, i].astype(np.uint64)
+    modulation = ((bits >> np.uint64(48)) & np.uint64(7)).astype(int)
+    assert (modulation == 0).sum() >= 5 and len(set(modulation.ravel().tolist())) >= 3
+
+
+@pytest.mark.ref
+def test_oracle_encoder_port_matches_compiled_reference_on_fresh_streams():
+    if not H.have_ref("A"):
+        pytest.skip("compiled reference not present")
+    from fixtures import make_pcm_batch
+    pcm = make_pcm_batch(range(40, 52), 32)
+    assert np.array_equal(H.oracle_features(pcm).view(np.uint32), H.ref_features(pcm).view(np.uint32))
+    assert np.array_equal(H.oracle_encode(pcm), H.ref_encode(pcm))
+    assert np.array_equal(H.oracle_encode(pcm, features4=True).view(np.uint32), H.ref_features4(pcm).view(np.uint32))
