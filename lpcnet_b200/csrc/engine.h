@@ -363,6 +363,8 @@ struct FrameState {           // per-batch persistent state of the 100 Hz path
     float *vq_mem;            // [n][18] decoder memory
     int *frame_count;         // [n] frames seen since the stream's last reset, saturating at 1000 (lpcnet.c:119)
     float *work;              // scratch of the layer-by-layer conditioning network (frame_work_floats(n) floats; not part of the state)
+    cudaStream_t side;        // side stream + fork / join events: cepstrum -> LPC runs next to the conditioning network (NULL: in line)
+    cudaEvent_t ev_fork, ev_join;
 };
 
 // lpc_raw [nframes+2][n][16]: entry e = raw LPC of frame e-2 of the call (entries 0,1 = carry); frame f reads entry f + 2 - delay
@@ -381,6 +383,6 @@ LPCNET_DECLARE_LAUNCHERS(na128)
 LPCNET_DECLARE_LAUNCHERS(na256)
 LPCNET_DECLARE_LAUNCHERS(na384)
 int sample_kernel_smem_ok(uint32_t bytes);
-int streams_per_cta_for(int n_streams);   // min(32, ceil(n / SM count)) on the current device
+int streams_per_cta_for(int n_streams, int override_spc);   // min(32, ceil(n / SM count)) on the current device unless overridden
 
 }  // namespace lpcnet_b200

@@ -259,6 +259,25 @@ void launch_frame_network(const DeviceModel &m, const FrameState &fs, const floa
     float *E1 = fs.work, *E2 = E1 + (size_t)n * (FRAME_CHUNK + 2) * FRAME_IN, *P = E2 + (size_t)n * (FRAME_CHUNK + 2) * COND, *Q = P + (size_t)n * FRAME_CHUNK * COND;
     FrameIoArgs io{m.embed_pitch, fs.conv1_state, fs.conv2_state, d_features, stream_stride, frame_stride, n, F, fs.frame_count, E1, E2, P,
                    m.cfg.end2end ? lpc_raw + (size_t)2 * n * LPC_ORDER : nullptr};
+    // cepstrum -> LPC depends on the features only: it runs on a side stream next to the conditioning network (fork / join by events),
+    // so its 0.15 ms (a latency-bound warp-per-frame kernel) hides behind the GEMMs instead of adding to the step
+    const bool lpc_path = !m.cfg.end2end;                      // END2END: no cepstrum -> LPC path, no delay line (lpcnet.c:107-108)
+    const bool fork = lpc_path && fs.side != nullptr;
+    cudaStream_t ls = fork ? fs.side : st;
+    auto lpc_part = [&]() {
+        const int tpb = 128;
+        lpc_carry_in_kernel<<<(n * LPC_ORDER + tpb - 1) / tpb, tpb, 0, ls>>>(fs.lpc_carry, lpc_raw, n);
+        LpcArgs la{d_features, stream_stride, frame_stride, n, nframes, m.dct, reinterpret_cast<const c32 *>(m.twiddles), m.bitrev, lpc_raw};
+        long long tot = (long long)n * nframes;
+        lpc_kernel<<<(unsigned)((tot + LPC_WARPS - 1) / LPC_WARPS), LPC_WARPS * 32, 0, ls>>>(la);
+        lpc_carry_out_kernel<<<(n * LPC_ORDER + tpb - 1) / tpb, tpb, 0, ls>>>(fs.lpc_carry, lpc_raw, n, nframes);
+    };
+    if (fork) {
+        cudaEventRecord(fs.ev_fork, st);                       // everything queued so far (previous sample kernel reading lpc_raw, H2D of the features) is ordered before
+        cudaStreamWaitEvent(fs.side, fs.ev_fork, 0);
+        lpc_part();
+        cudaEventRecord(fs.ev_join, fs.side);
+    }
     frame_assemble_kernel<<<n, 128, 0, st>>>(io);
     const int ncols = n * F;
     auto gemm = [&](bool tanh_act, const float *W, const float *bias, int M, int N, const float *X, int xS, int xF,
@@ -278,13 +297,8 @@ void launch_frame_network(const DeviceModel &m, const FrameState &fs, const floa
     gemm(false, m.gad_w, m.gad_b, COND, na3, P, F, COND, condA, na3, (long long)n * na3, 0, nullptr, 0);
     gemm(false, m.gbd_w, m.gbd_b, COND, 3 * NB, P, F, COND, condB, 3 * NB, (long long)n * 3 * NB, 0, nullptr, 0);
     frame_finish_kernel<<<n, 128, 0, st>>>(io);
-    if (m.cfg.end2end) return;                                 // no cepstrum -> LPC path, no delay line (lpcnet.c:107-108)
-    const int tpb = 128;
-    lpc_carry_in_kernel<<<(n * LPC_ORDER + tpb - 1) / tpb, tpb, 0, st>>>(fs.lpc_carry, lpc_raw, n);
-    LpcArgs la{d_features, stream_stride, frame_stride, n, nframes, m.dct, reinterpret_cast<const c32 *>(m.twiddles), m.bitrev, lpc_raw};
-    long long tot = (long long)n * nframes;
-    lpc_kernel<<<(unsigned)((tot + LPC_WARPS - 1) / LPC_WARPS), LPC_WARPS * 32, 0, st>>>(la);
-    lpc_carry_out_kernel<<<(n * LPC_ORDER + tpb - 1) / tpb, tpb, 0, st>>>(fs.lpc_carry, lpc_raw, n, nframes);
+    if (fork) cudaStreamWaitEvent(st, fs.ev_join, 0);
+    else if (lpc_path) lpc_part();
 }
 int frame_network_launches(const DeviceModel &m) { return m.cfg.end2end ? 8 : 11; }
 size_t frame_work_floats(size_t n) { return n * ((size_t)(FRAME_CHUNK + 2) * (FRAME_IN + COND) + 2 * (size_t)FRAME_CHUNK * COND); }

@@ -235,7 +235,14 @@ def make_codebooks(seed=4321):
 
 
 def write_blob(path, arrays):
-    """'DNNw' records: 64-byte header + payload padded to 64 (write_lpcnet_weights.c:47-67)."""
+    """'DNNw' records: 64-byte header + payload padded to 64 (write_lpcnet_weights.c:47-67).  Written under a temporary name and
+    renamed: several processes (one per GPU under torchrun) may regenerate the same deterministic file at the same time."""
+    tmp = "%s.tmp%d" % (path, os.getpid())
+    _write_blob(tmp, arrays)
+    os.replace(tmp, path)
+
+
+def _write_blob(path, arrays):
     with open(path, "wb") as f:
         for name, typ, a in arrays:
             raw = a.tobytes()
@@ -416,9 +423,11 @@ def generate(out, seed=1234, c_sources=True, na=None, e2e=False, delay=None, gam
         c2, o8, _ = make_model(seed, variant="clamp")
         write_blob(os.path.join(out, "model_int8_clamp.bin"), c2 + o8)
     cbs = make_codebooks()
-    with open(os.path.join(out, "codebooks.bin"), "wb") as f:
+    tmp = os.path.join(out, "codebooks.bin.tmp%d" % os.getpid())
+    with open(tmp, "wb") as f:
         for a in cbs:
             f.write(a.tobytes())
+    os.replace(tmp, os.path.join(out, "codebooks.bin"))
     if c_sources:
         write_c_sources(out, na=na, e2e=e2e, delay=delay, gamma=gamma)
         write_codebook_c(os.path.join(out, "ceps_codebooks.c"), cbs)
