@@ -477,9 +477,12 @@ static int forward_to_sink(LPCNetB200Batch *b, const short *d_pcm, long long pcm
     if (!b->sink) return 0;
     CK(cudaEventRecord(b->sink_ev, st));
     CK(cudaStreamWaitEvent(b->sink_stream, b->sink_ev, 0));
-    CK(cudaMemcpy2DAsync(b->sink + b->sink_row0 * b->sink_pitch + (size_t)c0 * spf, b->sink_pitch * sizeof(short),
-                         d_pcm + (size_t)c0 * spf, pcm_stride * sizeof(short), (size_t)nf * spf * sizeof(short), b->n,
-                         cudaMemcpyDefault, b->sink_stream));       // (the sink may live on another device: UVA infers the route)
+    short *dst = b->sink + b->sink_row0 * b->sink_pitch + (size_t)c0 * spf;
+    if (c0 == 0 && (long long)nf * spf == pcm_stride && b->sink_pitch == pcm_stride)      // whole rows, same pitch: one contiguous block (one DMA descriptor
+        CK(cudaMemcpyAsync(dst, d_pcm, (size_t)b->n * pcm_stride * sizeof(short), cudaMemcpyDefault, b->sink_stream));   // instead of n row copies)
+    else
+        CK(cudaMemcpy2DAsync(dst, b->sink_pitch * sizeof(short), d_pcm + (size_t)c0 * spf, pcm_stride * sizeof(short), (size_t)nf * spf * sizeof(short), b->n,
+                             cudaMemcpyDefault, b->sink_stream));       // (the sink may live on another device: UVA infers the route)
     return 0;
 }
 

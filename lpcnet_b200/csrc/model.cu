@@ -349,6 +349,7 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
     }
     uint16_t *metaB = reinterpret_cast<uint16_t *>(&img[oMB]);
     uint32_t *dirB = reinterpret_cast<uint32_t *>(&img[M.dirB]);
+    const uint32_t quadsA_total = blk;
     blk = 0;
     for (int rg = 0; rg < 6; rg++) {
         const auto &lst = rowsB[rg];
@@ -363,6 +364,17 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
                 }
             } else put_quads(lst.data() + b0, b1 - b0, blk, oWB, oMB);
             blk += dirB_h[rg * kparts + k][1];
+        }
+    }
+    if (!is_float) {
+        // the int8 kernel keeps each compute warp's quads in tensor memory: 2 columns per quad, 128 columns per warp (sample_kernel.cu)
+        for (int w = 0; w < nwc; w++) {
+            const uint32_t firstA = dirA[((w * gpw + 0) * 3 + 1) * 2], lastA = w + 1 < nwc ? dirA[(((w + 1) * gpw + 0) * 3 + 1) * 2] : quadsA_total;
+            const uint32_t nb = w < 6 * kparts ? dirB[w * 2 + 1] : 0;
+            if (2 * ((lastA - firstA) + 4 + nb + 4) > 128) {
+                set_error("model: compute warp %d walks %u + %u quads, more than its 128 tensor-memory columns hold", w, lastA - firstA, nb);
+                return -1;
+            }
         }
     }
     if (is_float) memcpy(&img[L.wBrecF - M.sm_image], wBrec->data, 3 * NB * NB * 4);    // float [in 16][out 48] (sgemv_accum16 layout)

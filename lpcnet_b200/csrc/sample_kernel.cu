@@ -151,25 +151,51 @@ __device__ __forceinline__ void imma16816_v(int (&c)[4], const int2 &a, uint32_t
     asm volatile("mma.sync.aligned.m16n8k16.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
                  : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a.x), "r"(a.y), "r"(b0));
 }
-// A stream of quads (several lists back to back in shared memory) walked with a two-deep operand pipeline:
-// set 0 / set 1 hold the A fragment (x) and B fragment (w) of the next two quads, eA / eB the meta entries of the two
-// quads after those.  Right after a quad is multiplied its registers are reloaded with the quad two positions ahead, so
-// every LDS has two multiplications (and their bookkeeping) to complete, also across list boundaries.  The image keeps
-// six quads of readable slack behind the arrays; what is loaded past the end of a stream is never used.
-//   w    : shared address of the current quad's weights + lane*4     (B fragment word of this lane)
-//   meta : shared address of the current quad's meta + t*2           (xs_offset of slot t's column block)
-//   xs   : shared address of the state buffer; the lane's 8-byte vector of slot t is at xs + (meta entry ^ lc), lc = (half << 6) | (gid << 3)
+// ---- tensor memory as the operand store of the B side ----
+// Per quad a lane needs three things: its A fragment (gathered from the quantised state: shared memory, it changes every sample),
+// its B fragment word (weights) and its slot's column offset (meta).  The last two are constants of the model and are private to
+// one lane of one warp, so they do not have to travel through the L1/shared-memory data pipe — the unit that bounds this kernel
+// (DESIGN.md 4.1): at kernel start every compute warp copies its own quads from the shared-memory image into TENSOR MEMORY
+// (tcgen05.st, two 32-bit columns per quad: {weights word, meta}), and the GEMV pipeline reads them back with tcgen05.ld
+// (SASS LDTM), which has its own datapath (12-cycle latency, 64 B/clk) and leaves the LSU pipe to the state gather, the
+// activations' table look-ups and the conditioning tiles.  A warp can only address the 32 TMEM lanes of its quarter
+// (warp id mod 4); the four compute warps of a quarter get 128 columns each (TMEM_COLS_PER_WARP; model.cu checks the budget).
+constexpr uint32_t TMEM_COLS = 512, TMEM_COLS_PER_WARP = 128, QUAD_SLACK = 4;     // QUAD_SLACK prefetched-but-unused quads behind a stream
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t a, uint32_t b)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// {weights word, meta} of the quad at column `taddr` (asynchronous: valid after tmem_wait_ld on the same registers)
+__device__ __forceinline__ void tmem_ld2(uint32_t &w, uint32_t &m, uint32_t taddr)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(w), "=r"(m) : "r"(taddr));
+}
+// completes every tcgen05.ld this thread has issued; the registers are operands so that no use can be scheduled above the wait
+__device__ __forceinline__ void tmem_wait_ld(uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &d)
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(a), "+r"(b), "+r"(c), "+r"(d) :: "memory");
+}
+
+// A stream of quads (several lists back to back) walked with a two-deep operand pipeline:
+// set 0 / set 1 hold the A fragment (x) and B fragment (w) of the next two quads, nW* / nM* the {weights, meta} of the two quads
+// after those, fetched from tensor memory one pipeline step ahead.  Right after a quad is multiplied its registers are reloaded
+// with the quad two positions ahead, so every LDS has two multiplications (and their bookkeeping) to complete, also across list
+// boundaries.  QUAD_SLACK readable quads follow every stream; what is loaded past the end of a stream is never used.
+//   col : tensor-memory address (lane quarter | column) of the quad in set 0
+//   xs  : shared address of the state buffer; the lane's 8-byte vector of slot t is at xs + (meta ^ lc), lc = (half << 6) | (gid << 3)
 struct QuadPipe {
-    uint32_t w, meta, xs, lc;
+    uint32_t col, xs, lc;
     int2 x0, x1;
-    uint32_t w0, w1, eA, eB;
-    __device__ __forceinline__ void start(uint32_t w_, uint32_t meta_, uint32_t xs_, uint32_t lc_)
+    uint32_t w0, w1, nW0, nM0, nW1, nM1;
+    __device__ __forceinline__ void start(uint32_t col_, uint32_t xs_, uint32_t lc_)
     {
-        w = w_; meta = meta_; xs = xs_; lc = lc_;
-        const uint32_t e0 = lds16(meta), e1 = lds16(meta + QUAD_META_BYTES);
-        eA = lds16(meta + 2 * QUAD_META_BYTES); eB = lds16(meta + 3 * QUAD_META_BYTES);
-        w0 = lds32(w); w1 = lds32(w + QUAD_BYTES);
-        x0 = lds64(xs + (e0 ^ lc)); x1 = lds64(xs + (e1 ^ lc));
+        col = col_; xs = xs_; lc = lc_;
+        uint32_t m0, m1;
+        tmem_ld2(w0, m0, col); tmem_ld2(w1, m1, col + 2);
+        tmem_wait_ld(w0, m0, w1, m1);
+        tmem_ld2(nW0, nM0, col + 4); tmem_ld2(nW1, nM1, col + 6);
+        x0 = lds64(xs + (m0 ^ lc)); x1 = lds64(xs + (m1 ^ lc));
     }
     // acc[2jj+i] += sum over the next `nq` quads of the stream, for stream gid+8jj (of one half) and neuron 2t+i of the row group
     __device__ __forceinline__ void list(int (&acc)[4], int nq)
@@ -177,19 +203,25 @@ struct QuadPipe {
 #pragma unroll 1
         for (; nq >= 2; nq -= 2) {
             imma16816_v(acc, x0, w0);
-            x0 = lds64(xs + (eA ^ lc)); w0 = lds32(w + 2 * QUAD_BYTES); eA = lds16(meta + 4 * QUAD_META_BYTES);
+            tmem_wait_ld(nW0, nM0, nW1, nM1);                     // issued one step ago
+            x0 = lds64(xs + (nM0 ^ lc)); w0 = nW0;
             imma16816_v(acc, x1, w1);
-            x1 = lds64(xs + (eB ^ lc)); w1 = lds32(w + 3 * QUAD_BYTES); eB = lds16(meta + 5 * QUAD_META_BYTES);
-            w += 2 * QUAD_BYTES; meta += 2 * QUAD_META_BYTES;
+            x1 = lds64(xs + (nM1 ^ lc)); w1 = nW1;
+            col += 4;
+            tmem_ld2(nW0, nM0, col + 4); tmem_ld2(nW1, nM1, col + 6);
         }
-        if (nq) {                                                // odd tail: multiply set 0, reload it, and let the sets trade places
+        if (nq) {                                                // odd tail: multiply set 0, and let the sets trade places
             imma16816_v(acc, x0, w0);
-            const int2 xn = lds64(xs + (eA ^ lc)); const uint32_t wn = lds32(w + 2 * QUAD_BYTES), en = lds16(meta + 4 * QUAD_META_BYTES);
-            x0 = x1; w0 = w1; eA = eB;
-            x1 = xn; w1 = wn; eB = en;
-            w += QUAD_BYTES; meta += QUAD_META_BYTES;
+            tmem_wait_ld(nW0, nM0, nW1, nM1);
+            x0 = x1; w0 = w1;
+            x1 = lds64(xs + (nM0 ^ lc)); w1 = nW0;
+            col += 2;
+            tmem_ld2(nW0, nM0, col + 4); tmem_ld2(nW1, nM1, col + 6);
         }
     }
+    // The look-ahead loads of the last step are still in flight when a stream ends: they must land before the registers they
+    // write are given to anything else (tcgen05.ld completes asynchronously, outside the register scoreboard).
+    __device__ __forceinline__ void finish() { tmem_wait_ld(nW0, nM0, nW1, nM1); }
 };
 
 // Stream slots of a CTA: slot (half hh, row si) holds stream  cta_s0 + 2*si + hh  of the batch, live while 2*si + hh < spc
@@ -252,7 +284,8 @@ struct ComputeCtx {
     uint32_t gid8;              // (lane >> 2) * 8
     int gid, t;
     int warp, lane;
-    uint32_t wA, metaA, wB, metaB;      // shared addresses (lane / slot offsets folded in)
+    uint32_t tmA, tmB;                  // tensor-memory address (lane quarter | column) of the warp's first GRU_A / GRU_B quad
+    uint32_t qA0;                       // global index of the warp's first GRU_A quad (the directory holds global indices)
     uint32_t xs0;                       // shared address of state buffer 0
     const uint32_t *dirA, *dirB;
     const float *parA;                  // + 2t folded in
@@ -275,7 +308,7 @@ template <int H>
 __device__ __forceinline__ void gemv_rh(const ComputeCtx &C, int (&Sh)[GPW][4], int (&Sg)[GPW][4], int cur)
 {
     QuadPipe Q;
-    Q.start(C.wA + C.dirA[2] * QUAD_BYTES, C.metaA + C.dirA[2] * QUAD_META_BYTES, C.xs0 + cur * XS_BYTES, C.gid8 | (H << 6));
+    Q.start(C.tmA + 2 * (C.dirA[2] - C.qA0), C.xs0 + cur * XS_BYTES, C.gid8 | (H << 6));
 #pragma unroll
     for (int sl = 0; sl < GPW; sl++) {
         const uint32_t *dir = C.dirA + sl * 3 * 2;
@@ -284,6 +317,7 @@ __device__ __forceinline__ void gemv_rh(const ComputeCtx &C, int (&Sh)[GPW][4], 
         Q.list(Sg[sl], (int)dir[3]);                              // the warp's lists are stored r0 h0 r1 h1 ... (model.cu)
         Q.list(Sh[sl], (int)dir[5]);
     }
+    Q.finish();
 }
 
 // gates r, z, candidate and state update of half H; Sh / Sg = GEMV sums of the candidate / reset gate
@@ -364,13 +398,14 @@ __device__ __forceinline__ void activations(const ComputeCtx &C, float (&h)[GPW]
     // ---- update gate z (nnet.c:426-430) ----
     {
         QuadPipe Q;
-        Q.start(C.wA + C.dirA[0] * QUAD_BYTES, C.metaA + C.dirA[0] * QUAD_META_BYTES, xs_cur, lc);
+        Q.start(C.tmA + 2 * (C.dirA[0] - C.qA0), xs_cur, lc);
 #pragma unroll
         for (int sl = 0; sl < GPW; sl++) {
 #pragma unroll
             for (int i = 0; i < 4; i++) Sg[sl][i] = 0;
             Q.list(Sg[sl], (int)C.dirA[sl * 3 * 2 + 1]);          // z0 z1 z2 are contiguous too
         }
+        Q.finish();
     }
     mbar_wait(mb_full + 8 * (kz & 3), (kz >> 2) & 1);
 #pragma unroll
@@ -470,10 +505,11 @@ __device__ __forceinline__ void grub(const ComputeCtx &C, const SampleParams &P,
     float *hBs = reinterpret_cast<float *>(tile_hb + T_HBS);
     if (warp < NWB) {
         int acc[4] = {0, 0, 0, 0};
-        const uint32_t q0 = C.dirB[warp * 2], nq = C.dirB[warp * 2 + 1];
+        const uint32_t nq = C.dirB[warp * 2 + 1];
         QuadPipe Q;
-        Q.start(C.wB + q0 * QUAD_BYTES, C.metaB + q0 * QUAD_META_BYTES, C.xs0 + nxt * XS_BYTES, lc);
+        Q.start(C.tmB, C.xs0 + nxt * XS_BYTES, lc);
         Q.list(acc, (int)nq);
+        Q.finish();
         const int rgp = warp / KPARTS, part = warp % KPARTS;
         int *dst = accB + (part * 3 * NB + rgp * 8 + 2 * t) * ACCB_ROW + gid;
         dst[0] = acc[0]; dst[ACCB_ROW] = acc[1]; dst[8] = acc[2]; dst[ACCB_ROW + 8] = acc[3];
@@ -539,7 +575,15 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
         for (int hh = 0; hh < 2; hh++) { mbar_init(smem_u32(smem + MB_IDX) + 8 * hh, ARRIVALS_PER_WARP); mbar_init(smem_u32(smem + MB_X) + 8 * hh, NWC * ARRIVALS_PER_WARP); mbar_init(smem_u32(smem + MB_ACCB) + 8 * hh, NWB * ARRIVALS_PER_WARP); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // tensor memory for the GEMV operands: warp 0 allocates all 512 columns (one CTA per SM), the base address travels through shared memory
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM_MBAR + 120);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (threadIdx.x == 0) {
         mbar_expect_tx(bar, L.image_bytes);
         const uint32_t CH = 16384;
@@ -560,11 +604,23 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
         const uint32_t *grpA = reinterpret_cast<const uint32_t *>(smem + SM_IMAGE + IM_GRPA);
         C.dirA = reinterpret_cast<const uint32_t *>(smem + SM_IMAGE + IM_DIRA) + warp * GPW * 3 * 2;
         C.parA = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_PARA) + warp * GPW * 3 * 16 + 2 * C.t;
-        C.metaA = smem_u32(smem + L.metaA) + C.t * 2;
-        C.wA = smem_u32(smem + L.wA) + lane * 4;
         C.dirB = reinterpret_cast<const uint32_t *>(smem + SM_IMAGE + IM_DIRB);
-        C.metaB = smem_u32(smem + L.metaB) + C.t * 2;
-        C.wB = smem_u32(smem + L.wB) + lane * 4;
+        {   // this warp's quads: shared-memory image -> tensor memory, {weights word of the lane, meta of the lane's slot} per quad, GRU_A stream
+            // (r0 h0 r1 h1 ... z0 z1 ...: contiguous in the image), QUAD_SLACK readable quads, then the warp's GRU_B stream + slack
+            const uint32_t tbase = *tmem_slot + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(warp >> 2) * TMEM_COLS_PER_WARP;
+            const uint32_t zl = ((GPW - 1) * 3 + 0) * 2;                                   // directory entry of the warp's last list (z of its last slot)
+            C.qA0 = C.dirA[2];
+            const uint32_t nqa = C.dirA[zl] + C.dirA[zl + 1] - C.qA0 + QUAD_SLACK;
+            const uint32_t wsrc = smem_u32(smem + L.wA) + lane * 4, msrc = smem_u32(smem + L.metaA) + C.t * 2;
+            for (uint32_t q = 0; q < nqa; q++) tmem_st2(tbase + 2 * q, lds32(wsrc + (C.qA0 + q) * QUAD_BYTES), lds16(msrc + (C.qA0 + q) * QUAD_META_BYTES));
+            C.tmA = tbase; C.tmB = tbase + 2 * nqa;
+            if (warp < NWB) {
+                const uint32_t q0 = C.dirB[warp * 2], nqb = C.dirB[warp * 2 + 1] + QUAD_SLACK;
+                const uint32_t wsb = smem_u32(smem + L.wB) + lane * 4, msb = smem_u32(smem + L.metaB) + C.t * 2;
+                for (uint32_t q = 0; q < nqb; q++) tmem_st2(C.tmB + 2 * q, lds32(wsb + (q0 + q) * QUAD_BYTES), lds16(msb + (q0 + q) * QUAD_META_BYTES));
+            }
+            tmem_wait_st();
+        }
         C.parB = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_PARB);
         C.wBrec = smem + SM_IMAGE + IM_WBREC;
         C.xs0 = smem_u32(smem + SM_XS);
@@ -655,6 +711,13 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
         if (warp < NFIN) {
 #pragma unroll
             for (int hh = 0; hh < 2; hh++) if (live_fin[hh]) P.hB[(size_t)jb_fin * n + s_fin[hh]] = hb[hh];
+        }
+        // every compute warp is done with its tensor-memory columns: warp 0 returns the allocation
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        bar_sync(BAR_X, CNT_C);
+        if (warp == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "n"(TMEM_COLS) : "memory");
         }
     } else if (warp < NWC + NWP) {
         // =====================================================  producer warps  =====================================================
