@@ -161,6 +161,7 @@ __device__ __forceinline__ void imma16816_v(int (&c)[4], const int2 &a, uint32_t
 // activations' table look-ups and the conditioning tiles.  A warp can only address the 32 TMEM lanes of its quarter
 // (warp id mod 4); the four compute warps of a quarter get 128 columns each (TMEM_COLS_PER_WARP; model.cu checks the budget).
 constexpr uint32_t TMEM_COLS = 512, TMEM_COLS_PER_WARP = 128, QUAD_SLACK = 4;     // QUAD_SLACK prefetched-but-unused quads behind a stream
+constexpr uint32_t TMEM_H_COL = 96;                                              // columns 96.. of a warp's range: the lane's fp32 GRU_A state, [half][group][4]
 __device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t a, uint32_t b)
 {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(a), "r"(b) : "memory");
@@ -170,6 +171,19 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ void tmem_ld2(uint32_t &w, uint32_t &m, uint32_t taddr)
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(w), "=r"(m) : "r"(taddr));
+}
+// four consecutive columns <-> four floats (the fp32 GRU_A state of a lane parks in tensor memory between its activations, see below)
+__device__ __forceinline__ void tmem_ld4f(float (&v)[4], uint32_t taddr)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st4f(uint32_t taddr, const float (&v)[4])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld4f(float (&v)[4])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]) :: "memory");
 }
 // completes every tcgen05.ld this thread has issued; the registers are operands so that no use can be scheduled above the wait
 __device__ __forceinline__ void tmem_wait_ld(uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &d)
@@ -285,6 +299,7 @@ struct ComputeCtx {
     int gid, t;
     int warp, lane;
     uint32_t tmA, tmB;                  // tensor-memory address (lane quarter | column) of the warp's first GRU_A / GRU_B quad
+    uint32_t tmH;                       // ... of the lane's parked fp32 GRU_A state: [half][GPW][4] columns
     uint32_t qA0;                       // global index of the warp's first GRU_A quad (the directory holds global indices)
     uint32_t xs0;                       // shared address of state buffer 0
     const uint32_t *dirA, *dirB;
@@ -322,8 +337,15 @@ __device__ __forceinline__ void gemv_rh(const ComputeCtx &C, int (&Sh)[GPW][4], 
 
 // gates r, z, candidate and state update of half H; Sh / Sg = GEMV sums of the candidate / reset gate
 template <int H, bool FAST>
-__device__ __forceinline__ void activations(const ComputeCtx &C, float (&h)[GPW][4], int (&Sh)[GPW][4], int (&Sg)[GPW][4], uint32_t k0, int cur)
+__device__ __forceinline__ void activations(const ComputeCtx &C, int (&Sh)[GPW][4], int (&Sg)[GPW][4], uint32_t k0, int cur)
 {
+    // The fp32 state of the lane's (stream, neuron) pairs of this half is only needed here: between its activations it is parked in
+    // tensor memory (12-cycle private storage) instead of holding GPW*4 registers per half through the GEMV phases — at the 80-register
+    // cap of a 768-thread CTA those registers were what spilled to local memory (through the LSU pipe this kernel is bound by).
+    float h[GPW][4];
+    tmem_wait_st();                                              // the state stored one sample ago has landed
+#pragma unroll
+    for (int sl = 0; sl < GPW; sl++) tmem_ld4f(h[sl], C.tmH + (H * GPW + sl) * 4);
     uint8_t *smem = C.smem;
     const int gid = C.gid, t = C.t, lane = C.lane, warp = C.warp;
     // per-gate choice of the RCPPS implementation (LPCNET_RCP_ARITH mask)
@@ -354,6 +376,8 @@ __device__ __forceinline__ void activations(const ComputeCtx &C, float (&h)[GPW]
     (void)t; (void)warp; (void)rcp_r; (void)rcp_z; (void)rcp_h; (void)nxt; (void)xs_cur; (void)lc; (void)xs_nxt; (void)tile_r; (void)tile_z; (void)tile_h; (void)mb_full; (void)mb_empty; (void)lane;
     // ---- reset gate r (nnet.c:431-435) with the gathered input term; keep rec_h * r (nnet.c:436-440) ----
     mbar_wait(mb_full + 8 * (kr & 3), (kr >> 2) & 1);
+#pragma unroll
+    for (int sl = 0; sl < GPW; sl++) tmem_wait_ld4f(h[sl]);
 #pragma unroll
     for (int sl = 0; sl < GPW; sl++) {
         const float *par = C.parA + sl * 3 * 16;
@@ -478,6 +502,8 @@ __device__ __forceinline__ void activations(const ComputeCtx &C, float (&h)[GPW]
             // other buffer: readers of the old state are unaffected
             *reinterpret_cast<uint16_t *>(xs_nxt + (C.xoff[sl] ^ (H << 6)) + 4 * jj) = (uint16_t)__byte_perm(q[0], q[1], 0x0040);
         }
+#pragma unroll
+    for (int sl = 0; sl < GPW; sl++) tmem_st4f(C.tmH + (H * GPW + sl) * 4, h[sl]);
     warp_arrive(smem_u32(smem + MB_X) + 8 * H, lane);            // this warp's part of the new quantised state is written, candidate-gate tile consumed
 }
 
@@ -605,9 +631,10 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
         C.dirA = reinterpret_cast<const uint32_t *>(smem + SM_IMAGE + IM_DIRA) + warp * GPW * 3 * 2;
         C.parA = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_PARA) + warp * GPW * 3 * 16 + 2 * C.t;
         C.dirB = reinterpret_cast<const uint32_t *>(smem + SM_IMAGE + IM_DIRB);
+        const uint32_t tbase_w = *tmem_slot + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(warp >> 2) * TMEM_COLS_PER_WARP;
         {   // this warp's quads: shared-memory image -> tensor memory, {weights word of the lane, meta of the lane's slot} per quad, GRU_A stream
             // (r0 h0 r1 h1 ... z0 z1 ...: contiguous in the image), QUAD_SLACK readable quads, then the warp's GRU_B stream + slack
-            const uint32_t tbase = *tmem_slot + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(warp >> 2) * TMEM_COLS_PER_WARP;
+            const uint32_t tbase = tbase_w;
             const uint32_t zl = ((GPW - 1) * 3 + 0) * 2;                                   // directory entry of the warp's last list (z of its last slot)
             C.qA0 = C.dirA[2];
             const uint32_t nqa = C.dirA[zl] + C.dirA[zl + 1] - C.qA0 + QUAD_SLACK;
@@ -629,16 +656,25 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
 #pragma unroll
         for (int j = 0; j < 4; j++) sj[j] = slot_stream<ONE>(cta_s0, j >> 1, C.gid + 8 * (j & 1), spc, n, livej[j]);
 
-        float h[2][GPW][4];                                              // fp32 state: [half][group][stream jj][neuron i] at 2jj+i
+        // restored fp32 state: [half][group][stream jj][neuron i] at 2jj+i -> the lane's tensor-memory columns, quantised copy -> xs buffer 0
+        C.tmH = tbase_w + TMEM_H_COL;
 #pragma unroll
         for (int sl = 0; sl < GPW; sl++) {
             const int g = (int)grpA[warp * GPW + sl];
             C.gcol[sl] = 8 * g + 2 * C.t;
             C.xoff[sl] = xs_offset(2 * g + (C.t >> 1), C.gid) + (C.t & 1) * 2;
 #pragma unroll
-            for (int j = 0; j < 4; j++)
+            for (int hh2 = 0; hh2 < 2; hh2++) {
+                float hv[4];
 #pragma unroll
-                for (int i = 0; i < 2; i++) h[j >> 1][sl][2 * (j & 1) + i] = P.hA[(size_t)(C.gcol[sl] + i) * n + sj[j]];
+                for (int jj = 0; jj < 2; jj++)
+#pragma unroll
+                    for (int i = 0; i < 2; i++) hv[2 * jj + i] = P.hA[(size_t)(C.gcol[sl] + i) * n + sj[2 * hh2 + jj]];
+                tmem_st4f(C.tmH + (hh2 * GPW + sl) * 4, hv);
+#pragma unroll
+                for (int jj = 0; jj < 2; jj++)
+                    *reinterpret_cast<uint16_t *>(smem + SM_XS + (C.xoff[sl] ^ (hh2 << 6)) + 4 * jj) = (uint16_t)(quant_u8(hv[2 * jj]) | (quant_u8(hv[2 * jj + 1]) << 8));
+            }
         }
         // GRU_B neuron finished by this lane (warps < NFIN): neuron 2*warp + (lane >> 4), stream lane & 15 of each half
         const int jb_fin = min(2 * warp + (lane >> 4), NB - 1);
@@ -649,13 +685,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
             s_fin[hh] = slot_stream<ONE>(cta_s0, hh, lane & 15, spc, n, live_fin[hh]);
             hb[hh] = P.hB[(size_t)jb_fin * n + s_fin[hh]];
         }
-        // quantised copies of the restored state: xs buffer 0 <- q(hA), xb[half][0] <- q(hB)
-#pragma unroll
-        for (int sl = 0; sl < GPW; sl++)
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                *reinterpret_cast<uint16_t *>(smem + SM_XS + (C.xoff[sl] ^ ((j >> 1) << 6)) + 4 * (j & 1)) =
-                    (uint16_t)(quant_u8(h[j >> 1][sl][2 * (j & 1)]) | (quant_u8(h[j >> 1][sl][2 * (j & 1) + 1]) << 8));
+        // quantised copy of the restored GRU_B state: xb[half][0] <- q(hB)
         if (warp < NFIN) {
 #pragma unroll
             for (int hh = 0; hh < 2; hh++)
@@ -670,7 +700,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
                 for (int t_ = 0; t_ < spf; t_++, step++, k += 3) {
                     int Sh[GPW][4], Sg[GPW][4];
                     gemv_rh<0>(C, Sh, Sg, step & 1);
-                    activations<0, FAST>(C, h[0], Sh, Sg, k, step & 1);
+                    activations<0, FAST>(C, Sh, Sg, k, step & 1);
                     grub<0, FAST>(C, P, hb[0], k, step & 1, f, s_fin[0], step & 1, step);
                 }
         } else {
@@ -685,7 +715,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
                 TRACE(P, step, 2, tl);       // = HB of half B (previous sample) signalled
                 mbar_wait(smem_u32(smem + MB_FULL) + 8 * (k & 3), (k >> 2) & 1);
                 TRACE(P, step, 3, tl);       // r tile of half A present
-                activations<0, FAST>(C, h[0], Sh, Sg, k, step & 1);
+                activations<0, FAST>(C, Sh, Sg, k, step & 1);
                 TRACE(P, step, 4, tl);
                 gemv_rh<1>(C, Sh, Sg, step & 1);
                 TRACE(P, step, 5, tl);
@@ -693,21 +723,28 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
                 TRACE(P, step, 6, tl);       // = HB of half A signalled
                 mbar_wait(smem_u32(smem + MB_FULL) + 8 * ((k + 3) & 3), ((k + 3) >> 2) & 1);
                 TRACE(P, step, 7, tl);       // r tile of half B present
-                activations<1, FAST>(C, h[1], Sh, Sg, k + 3, step & 1);
+                activations<1, FAST>(C, Sh, Sg, k + 3, step & 1);
                 TRACE(P, step, 8, tl);
                 f_prev = f;
             }
         if (step > 0) grub<1, FAST>(C, P, hb[1], k - 3, (step - 1) & 1, f_prev, s_fin[1], (step - 1) & 1);
         }
         // ---- save the recurrent state ----
+        tmem_wait_st();
 #pragma unroll
         for (int sl = 0; sl < GPW; sl++)
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (livej[j]) {
-                    P.hA[(size_t)C.gcol[sl] * n + sj[j]] = h[j >> 1][sl][2 * (j & 1)];
-                    P.hA[(size_t)(C.gcol[sl] + 1) * n + sj[j]] = h[j >> 1][sl][2 * (j & 1) + 1];
-                }
+            for (int hh2 = 0; hh2 < 2; hh2++) {
+                float hv[4];
+                tmem_ld4f(hv, C.tmH + (hh2 * GPW + sl) * 4);
+                tmem_wait_ld4f(hv);
+#pragma unroll
+                for (int jj = 0; jj < 2; jj++)
+                    if (livej[2 * hh2 + jj]) {
+                        P.hA[(size_t)C.gcol[sl] * n + sj[2 * hh2 + jj]] = hv[2 * jj];
+                        P.hA[(size_t)(C.gcol[sl] + 1) * n + sj[2 * hh2 + jj]] = hv[2 * jj + 1];
+                    }
+            }
         if (warp < NFIN) {
 #pragma unroll
             for (int hh = 0; hh < 2; hh++) if (live_fin[hh]) P.hB[(size_t)jb_fin * n + s_fin[hh]] = hb[hh];
