@@ -100,6 +100,12 @@ __device__ __forceinline__ f32x2 k2(float c) { return pk2(c, c); }
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// 1 - z for two values: fma(z, -1, 1) = rn(1 - z)
+__device__ __forceinline__ f32x2 one_minus2(f32x2 z) { return fma2(z, k2(-1.f), k2(1.f)); }
+// x + y where x (and maybe y) is the result of a packed multiply: written as fma(x, ONE, y) = rn(x*1 + y) = rn(x + y) with a ONE = {1.f, 1.f}
+// that the compiler cannot see through (it is read from shared memory at kernel start), so the multiply that produced x cannot be
+// contracted into it — which ptxas does to a packed mul followed by a packed add (see above).  Same instruction count as an add.
+__device__ __forceinline__ f32x2 oadd2(f32x2 x, f32x2 one, f32x2 y) { return fma2(x, one, y); }
 // numerator * x and denominator of the rational approximations (before the reciprocal), two values at a time:
 // X2 = x*x; num = fma(fma(N2,X2,N1),X2,N0) * x; den = fma(fma(D2,X2,D1),X2,D0)          (vec_avx.h:393-440)
 __device__ __forceinline__ void rational2(f32x2 x, float N0, float N1, float N2, float D0, float D1, float D2, f32x2 &num, f32x2 &den)

@@ -371,8 +371,9 @@ static int build_host_model(DeviceModel *m, HostModel &hm, const unsigned char *
         for (int w = 0; w < nwc; w++) {
             const uint32_t firstA = dirA[((w * gpw + 0) * 3 + 1) * 2], lastA = w + 1 < nwc ? dirA[(((w + 1) * gpw + 0) * 3 + 1) * 2] : quadsA_total;
             const uint32_t nb = w < 6 * kparts ? dirB[w * 2 + 1] : 0;
-            if (2 * ((lastA - firstA) + 4 + nb + 4) > 96) {        // columns 96.. hold the parked fp32 state
-                set_error("model: compute warp %d walks %u + %u quads, more than its 96 tensor-memory columns hold", w, lastA - firstA, nb);
+            const uint32_t room = 128 - 8 * (uint32_t)gpw;          // the last 8*gpw columns hold the parked fp32 state, 2 tail quads follow the streams
+            if (2 * ((lastA - firstA) + nb + 2) > room) {
+                set_error("model: compute warp %d walks %u + %u quads, more than its %u tensor-memory columns hold", w, lastA - firstA, nb, room);
                 return -1;
             }
         }

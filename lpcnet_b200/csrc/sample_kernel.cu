@@ -48,6 +48,12 @@
                                // instead of the shared-memory table (exact either way).  The table costs ~3.4 bank-conflicted wavefronts per
                                // look-up on the LSU pipe, the arithmetic form 8 more issue slots: all three gates arithmetic (7) measured 5 % slower
 #endif
+#ifndef LPCNET_LDTM_X4
+#define LPCNET_LDTM_X4 1       // fetch the operands of two quads with one tcgen05.ld.x4 (one LDTM + one R2UR less per pair of quads)
+#endif
+#ifndef LPCNET_PACK_ACT
+#define LPCNET_PACK_ACT 1      // GRU_A activations: also the mul -> add pieces run two neurons at a time (oadd2, devmath.cuh)
+#endif
 #ifndef LPCNET_GATHER_NOALLOC
 #define LPCNET_GATHER_NOALLOC 0
 #endif
@@ -160,8 +166,12 @@ __device__ __forceinline__ void imma16816_v(int (&c)[4], const int2 &a, uint32_t
 // (SASS LDTM), which has its own datapath (12-cycle latency, 64 B/clk) and leaves the LSU pipe to the state gather, the
 // activations' table look-ups and the conditioning tiles.  A warp can only address the 32 TMEM lanes of its quarter
 // (warp id mod 4); the four compute warps of a quarter get 128 columns each (TMEM_COLS_PER_WARP; model.cu checks the budget).
-constexpr uint32_t TMEM_COLS = 512, TMEM_COLS_PER_WARP = 128, QUAD_SLACK = 4;     // QUAD_SLACK prefetched-but-unused quads behind a stream
-constexpr uint32_t TMEM_H_COL = 96;                                              // columns 96.. of a warp's range: the lane's fp32 GRU_A state, [half][group][4]
+constexpr uint32_t TMEM_COLS = 512, TMEM_COLS_PER_WARP = 128;
+// Behind the end of a stream the pipeline has fetched four more quads and formed shared-memory addresses from the meta of the first
+// two (never multiplied).  The GRU_A stream is followed by the warp's GRU_B stream (valid metas of the same state layout), the last
+// stream by QUAD_TAIL copies of a valid quad; what is fetched beyond those is the parked state below (fetched only, never used).
+constexpr uint32_t QUAD_TAIL = 2;
+constexpr uint32_t TMEM_H_COL = TMEM_COLS_PER_WARP - 8 * (uint32_t)GPW;         // last columns of a warp's range: the lane's fp32 GRU_A state, [half][group][4]
 __device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t a, uint32_t b)
 {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(a), "r"(b) : "memory");
@@ -171,6 +181,15 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ void tmem_ld2(uint32_t &w, uint32_t &m, uint32_t taddr)
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(w), "=r"(m) : "r"(taddr));
+}
+// the {weights word, meta} pairs of two consecutive quads with one instruction (four columns)
+__device__ __forceinline__ void tmem_ld22(uint32_t &w0, uint32_t &m0, uint32_t &w1, uint32_t &m1, uint32_t taddr)
+{
+#if LPCNET_LDTM_X4
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(m0), "=r"(w1), "=r"(m1) : "r"(taddr));
+#else
+    tmem_ld2(w0, m0, taddr); tmem_ld2(w1, m1, taddr + 2);
+#endif
 }
 // four consecutive columns <-> four floats (the fp32 GRU_A state of a lane parks in tensor memory between its activations, see below)
 __device__ __forceinline__ void tmem_ld4f(float (&v)[4], uint32_t taddr)
@@ -208,7 +227,7 @@ struct QuadPipe {
         uint32_t m0, m1;
         tmem_ld2(w0, m0, col); tmem_ld2(w1, m1, col + 2);
         tmem_wait_ld(w0, m0, w1, m1);
-        tmem_ld2(nW0, nM0, col + 4); tmem_ld2(nW1, nM1, col + 6);
+        tmem_ld22(nW0, nM0, nW1, nM1, col + 4);
         x0 = lds64(xs + (m0 ^ lc)); x1 = lds64(xs + (m1 ^ lc));
     }
     // acc[2jj+i] += sum over the next `nq` quads of the stream, for stream gid+8jj (of one half) and neuron 2t+i of the row group
@@ -222,7 +241,7 @@ struct QuadPipe {
             imma16816_v(acc, x1, w1);
             x1 = lds64(xs + (nM1 ^ lc)); w1 = nW1;
             col += 4;
-            tmem_ld2(nW0, nM0, col + 4); tmem_ld2(nW1, nM1, col + 6);
+            tmem_ld22(nW0, nM0, nW1, nM1, col + 4);
         }
         if (nq) {                                                // odd tail: multiply set 0, and let the sets trade places
             imma16816_v(acc, x0, w0);
@@ -230,7 +249,7 @@ struct QuadPipe {
             x0 = x1; w0 = w1;
             x1 = lds64(xs + (nM0 ^ lc)); w1 = nW0;
             col += 2;
-            tmem_ld2(nW0, nM0, col + 4); tmem_ld2(nW1, nM1, col + 6);
+            tmem_ld22(nW0, nM0, nW1, nM1, col + 4);
         }
     }
     // The look-ahead loads of the last step are still in flight when a stream ends: they must land before the registers they
@@ -307,6 +326,7 @@ struct ComputeCtx {
     const float *parB;
     const uint8_t *wBrec;
     RcpShared rcp;
+    f32x2 one2;                         // {1.f, 1.f} read from shared memory (opaque to the compiler: oadd2, devmath.cuh)
     uint8_t *smem;
     int gcol[GPW];                      // neuron index of this lane's first neuron of each group: 8*g + 2t
     uint32_t xoff[GPW];                 // byte offset (in a state buffer) of this lane's two quantised neurons, stream gid of half 0 (half 1: ^ 64, stream gid+8: + 4)
@@ -389,23 +409,40 @@ __device__ __forceinline__ void activations(const ComputeCtx &C, int (&Sh)[GPW][
             const float2 gv = *reinterpret_cast<const float2 *>(tile_r + 8 * jj * GIN_ROW + C.gcol[sl]);
             const float gin[2] = {gv.x, gv.y};
             if constexpr (FAST) {
-                // mul -> add pieces scalar, the rest two neurons at a time (devmath.cuh)
                 int a[2], ah[2];
+#if LPCNET_PACK_ACT
+                {   // both neurons of the lane at a time; every mul -> add of the reference goes through oadd2
+                    const f32x2 hv2 = pk2(h[sl][2 * jj], h[sl][2 * jj + 1]), ONE = C.one2;
+                    float a0, a1, b0, b1;
+                    upk2(oadd2(mul2(add2(oadd2(mul2(pk2(dr.x, dr.y), hv2), ONE, pk2(br.x, br.y)), pk2(gv.x, gv.y)), k2(LPCNET_SCALE)), ONE, k2(LPCNET_CVT_MAGIC)), a0, a1);
+                    upk2(oadd2(mul2(oadd2(mul2(pk2(dh.x, dh.y), hv2), ONE, pk2(bh.x, bh.y)), k2(LPCNET_SCALE)), ONE, k2(LPCNET_CVT_MAGIC)), b0, b1);
+                    a[0] = __float_as_int(a0) + Sg[sl][2 * jj]; a[1] = __float_as_int(a1) + Sg[sl][2 * jj + 1];
+                    ah[0] = __float_as_int(b0) + Sh[sl][2 * jj]; ah[1] = __float_as_int(b1) + Sh[sl][2 * jj + 1];
+                }
+#else
+                // mul -> add pieces scalar, the rest two neurons at a time (devmath.cuh)
 #pragma unroll
                 for (int i = 0; i < 2; i++) {
                     const float hv = h[sl][2 * jj + i];
                     a[i] = acc_init_t<true>(__fadd_rn(__fadd_rn(bri[i], __fmul_rn(dri[i], hv)), gin[i])) + Sg[sl][2 * jj + i];
                     ah[i] = acc_init_t<true>(__fadd_rn(bhi[i], __fmul_rn(dhi[i], hv))) + Sh[sl][2 * jj + i];
                 }
+#endif
                 f32x2 num, den;
                 rational2(acc_finish2(a[0], a[1]), LPCNET_SIGMOID_COEF, num, den);
                 float n0, n1, d0, d1, rh0, rh1;
                 upk2(num, n0, n1); upk2(den, d0, d1);
                 const float r0 = fmaxf(0.f, fminf(1.f, __fmaf_rn(n0, rcp_emul(d0, rcp_r), 0.5f)));
                 const float r1 = fmaxf(0.f, fminf(1.f, __fmaf_rn(n1, rcp_emul(d1, rcp_r), 0.5f)));
+#if LPCNET_PACK_ACT
+                upk2(mul2(acc_finish2(ah[0], ah[1]), pk2(r0, r1)), rh0, rh1);
+                Sh[sl][2 * jj] = __float_as_int(rh0);
+                Sh[sl][2 * jj + 1] = __float_as_int(rh1);
+#else
                 upk2(acc_finish2(ah[0], ah[1]), rh0, rh1);
                 Sh[sl][2 * jj] = __float_as_int(__fmul_rn(rh0, r0));
                 Sh[sl][2 * jj + 1] = __float_as_int(__fmul_rn(rh1, r1));
+#endif
             } else {
 #pragma unroll
                 for (int i = 0; i < 2; i++) {
@@ -443,9 +480,18 @@ __device__ __forceinline__ void activations(const ComputeCtx &C, int (&Sh)[GPW][
             const float gin[2] = {gv.x, gv.y};
             if constexpr (FAST) {
                 int a[2];
+#if LPCNET_PACK_ACT
+                {
+                    const f32x2 ONE = C.one2;
+                    float a0, a1;
+                    upk2(oadd2(mul2(add2(oadd2(mul2(pk2(dz.x, dz.y), pk2(h[sl][2 * jj], h[sl][2 * jj + 1])), ONE, pk2(bz.x, bz.y)), pk2(gv.x, gv.y)), k2(LPCNET_SCALE)), ONE, k2(LPCNET_CVT_MAGIC)), a0, a1);
+                    a[0] = __float_as_int(a0) + Sg[sl][2 * jj]; a[1] = __float_as_int(a1) + Sg[sl][2 * jj + 1];
+                }
+#else
 #pragma unroll
                 for (int i = 0; i < 2; i++)
                     a[i] = acc_init_t<true>(__fadd_rn(__fadd_rn(bzi[i], __fmul_rn(dzi[i], h[sl][2 * jj + i])), gin[i])) + Sg[sl][2 * jj + i];
+#endif
                 f32x2 num, den;
                 rational2(acc_finish2(a[0], a[1]), LPCNET_SIGMOID_COEF, num, den);
                 float n0, n1, d0, d1;
@@ -479,12 +525,20 @@ __device__ __forceinline__ void activations(const ComputeCtx &C, int (&Sh)[GPW][
                 upk2(mul2(num, pk2(rcp_emul(d0, rcp_h), rcp_emul(d1, rcp_h))), t0, t1);
                 const float hh[2] = {fmaxf(-1.f, fminf(1.f, t0)), fmaxf(-1.f, fminf(1.f, t1))};
                 float hn[2];
+#if LPCNET_PACK_ACT
+                {
+                    const f32x2 z2 = pk2(__int_as_float(Sg[sl][2 * jj]), __int_as_float(Sg[sl][2 * jj + 1]));
+                    upk2(oadd2(mul2(z2, pk2(h[sl][2 * jj], h[sl][2 * jj + 1])), C.one2, mul2(one_minus2(z2), pk2(hh[0], hh[1]))), hn[0], hn[1]);
+                    h[sl][2 * jj] = hn[0]; h[sl][2 * jj + 1] = hn[1];
+                }
+#else
 #pragma unroll
                 for (int i = 0; i < 2; i++) {
                     const float z = __int_as_float(Sg[sl][2 * jj + i]);
                     hn[i] = __fadd_rn(__fmul_rn(z, h[sl][2 * jj + i]), __fmul_rn(__fsub_rn(1.f, z), hh[i]));
                     h[sl][2 * jj + i] = hn[i];
                 }
+#endif
                 // quantised bytes in the low bytes of the biased patterns: fma -> add, safe to pack
                 float q0, q1;
                 upk2(add2(fma2(pk2(hn[0], hn[1]), k2(127.f), k2(127.f)), k2(LPCNET_CVT_MAGIC)), q0, q1);
@@ -601,6 +655,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
         for (int hh = 0; hh < 2; hh++) { mbar_init(smem_u32(smem + MB_IDX) + 8 * hh, ARRIVALS_PER_WARP); mbar_init(smem_u32(smem + MB_X) + 8 * hh, NWC * ARRIVALS_PER_WARP); mbar_init(smem_u32(smem + MB_ACCB) + 8 * hh, NWB * ARRIVALS_PER_WARP); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (threadIdx.x == 32) *reinterpret_cast<float *>(smem + SM_MBAR + 124) = 1.f;     // ComputeCtx::one2 (last free word of the mbarrier block)
     // tensor memory for the GEMV operands: warp 0 allocates all 512 columns (one CTA per SM), the base address travels through shared memory
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + SM_MBAR + 120);
     if (warp == 0) {
@@ -627,25 +682,29 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
         mbar_wait(bar, 0);
         ComputeCtx C;
         C.gid = lane >> 2; C.t = lane & 3; C.gid8 = C.gid * 8; C.warp = warp; C.lane = lane; C.smem = smem; C.rcp = rcp;
+        { const float one = *reinterpret_cast<const volatile float *>(smem + SM_MBAR + 124); C.one2 = pk2(one, one); }
         const uint32_t *grpA = reinterpret_cast<const uint32_t *>(smem + SM_IMAGE + IM_GRPA);
         C.dirA = reinterpret_cast<const uint32_t *>(smem + SM_IMAGE + IM_DIRA) + warp * GPW * 3 * 2;
         C.parA = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_PARA) + warp * GPW * 3 * 16 + 2 * C.t;
         C.dirB = reinterpret_cast<const uint32_t *>(smem + SM_IMAGE + IM_DIRB);
         const uint32_t tbase_w = *tmem_slot + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(warp >> 2) * TMEM_COLS_PER_WARP;
         {   // this warp's quads: shared-memory image -> tensor memory, {weights word of the lane, meta of the lane's slot} per quad, GRU_A stream
-            // (r0 h0 r1 h1 ... z0 z1 ...: contiguous in the image), QUAD_SLACK readable quads, then the warp's GRU_B stream + slack
+            // (r0 h0 r1 h1 ... z0 z1 ...: contiguous in the image), then the warp's GRU_B stream, then QUAD_TAIL copies of the first quad
             const uint32_t tbase = tbase_w;
             const uint32_t zl = ((GPW - 1) * 3 + 0) * 2;                                   // directory entry of the warp's last list (z of its last slot)
             C.qA0 = C.dirA[2];
-            const uint32_t nqa = C.dirA[zl] + C.dirA[zl + 1] - C.qA0 + QUAD_SLACK;
+            const uint32_t nqa = C.dirA[zl] + C.dirA[zl + 1] - C.qA0;
             const uint32_t wsrc = smem_u32(smem + L.wA) + lane * 4, msrc = smem_u32(smem + L.metaA) + C.t * 2;
             for (uint32_t q = 0; q < nqa; q++) tmem_st2(tbase + 2 * q, lds32(wsrc + (C.qA0 + q) * QUAD_BYTES), lds16(msrc + (C.qA0 + q) * QUAD_META_BYTES));
             C.tmA = tbase; C.tmB = tbase + 2 * nqa;
+            uint32_t tail = C.tmB;
             if (warp < NWB) {
-                const uint32_t q0 = C.dirB[warp * 2], nqb = C.dirB[warp * 2 + 1] + QUAD_SLACK;
+                const uint32_t q0 = C.dirB[warp * 2], nqb = C.dirB[warp * 2 + 1];
                 const uint32_t wsb = smem_u32(smem + L.wB) + lane * 4, msb = smem_u32(smem + L.metaB) + C.t * 2;
                 for (uint32_t q = 0; q < nqb; q++) tmem_st2(C.tmB + 2 * q, lds32(wsb + (q0 + q) * QUAD_BYTES), lds16(msb + (q0 + q) * QUAD_META_BYTES));
+                tail += 2 * nqb;
             }
+            for (uint32_t q = 0; q < QUAD_TAIL; q++) tmem_st2(tail + 2 * q, lds32(wsrc + C.qA0 * QUAD_BYTES), lds16(msrc + C.qA0 * QUAD_META_BYTES));
             tmem_wait_st();
         }
         C.parB = reinterpret_cast<const float *>(smem + SM_IMAGE + IM_PARB);
