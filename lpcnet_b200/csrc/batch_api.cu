@@ -129,7 +129,7 @@ extern "C" __attribute__((visibility("default"))) int lpcnet_b200_debug_read_tra
 {
     if (!g_trace) return -1;
     cudaDeviceSynchronize();
-    return cudaMemcpy(out, g_trace, 8 * 32 * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
+    return cudaMemcpy(out, g_trace, (8 * 32 + 8 * 32 * 16) * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;   // + [8 samples][32 warps][16 events] per-warp stamps
 }
 #endif
 
@@ -317,7 +317,7 @@ LPCNetB200Batch *lpcnet_b200_batch_create_ex(int n_streams, const unsigned char 
     al((void **)&b->fs.lpc_carry, sizeof(float) * 2 * LPC_ORDER * n); al((void **)&b->fs.vq_mem, sizeof(float) * NB_BANDS * n);
     al((void **)&b->fs.frame_count, sizeof(int) * n);
     al((void **)&b->fs.work, sizeof(float) * frame_work_floats(n));
-    al((void **)&b->condA, sizeof(float) * (size_t)CHUNK * n * 3 * na); al((void **)&b->condB, sizeof(float) * (size_t)CHUNK * n * 3 * NB);
+    al((void **)&b->condA, sizeof(float) * (size_t)CHUNK * condA_frame_floats(b->model.is_float != 0, n, na)); al((void **)&b->condB, sizeof(float) * (size_t)CHUNK * n * 3 * NB);
     al((void **)&b->lpc_raw, sizeof(float) * (size_t)(CHUNK + 2) * n * LPC_ORDER);
     if (ok && cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) ok = false;
     if (ok && (cudaStreamCreateWithFlags(&b->fs.side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&b->fs.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
@@ -405,10 +405,10 @@ static int launch_sample(LPCNetB200Batch *b, int pos, int nf, int spf, short *pc
     p.one_half = p.spc <= HALF && !b->env_two_halves;
     p.fast_cvt = ((b->model.fast_cvt && !b->env_exact_cvt) ? 1 : 0) | (preload << 8);   // env LPCNET_B200_EXACT_CVT: force the conversion-unit path (tests)
 #ifdef LPCNET_TRACE
-    { static long long *d_trace = nullptr; if (!d_trace) { CK(cudaMalloc(&d_trace, 8 * 32 * 8)); CK(cudaMemset(d_trace, 0, 8 * 32 * 8)); } p.trace = d_trace; g_trace = d_trace; }
+    { static long long *d_trace = nullptr; if (!d_trace) { CK(cudaMalloc(&d_trace, (8 * 32 + 8 * 32 * 16) * 8)); CK(cudaMemset(d_trace, 0, (8 * 32 + 8 * 32 * 16) * 8)); } p.trace = d_trace; g_trace = d_trace; }
 #endif
     const int d = b->model.cfg.end2end ? 0 : b->model.cfg.features_delay;   // frame f uses lpc_raw entry f + 2 - d (frame_kernels.cu)
-    p.condA = b->condA + (size_t)pos * n * 3 * na;
+    p.condA = b->condA + (size_t)pos * condA_frame_floats(b->model.is_float != 0, n, na);
     p.condB = b->condB + (size_t)pos * n * 3 * NB;
     p.lpc_raw = b->lpc_raw + (size_t)(pos + 2 - d) * n * LPC_ORDER;
     p.gamma_pow = b->model.gamma_pow;
@@ -917,7 +917,9 @@ int lpcnet_b200_debug_frame_network(LPCNetB200Batch *b, const float *features, i
                          b->condA, b->condB, b->lpc_raw, b->stream);
     for (int &v : *b->fc) v = std::min(1000, v + nframes);
     b->cond_last = nframes - 1;
-    std::vector<float> hA((size_t)nframes * n * 3 * na), hB((size_t)nframes * n * 3 * NB), hl((size_t)(nframes + 2) * n * LPC_ORDER), gp(LPC_ORDER);
+    const bool isf = b->model.is_float != 0;
+    const size_t fA = condA_frame_floats(isf, n, na);
+    std::vector<float> hA((size_t)nframes * fA), hB((size_t)nframes * n * 3 * NB), hl((size_t)(nframes + 2) * n * LPC_ORDER), gp(LPC_ORDER);
     CK(cudaMemcpyAsync(hA.data(), b->condA, hA.size() * 4, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaMemcpyAsync(hB.data(), b->condB, hB.size() * 4, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaMemcpyAsync(hl.data(), b->lpc_raw, hl.size() * 4, cudaMemcpyDeviceToHost, b->stream));
@@ -925,7 +927,8 @@ int lpcnet_b200_debug_frame_network(LPCNetB200Batch *b, const float *features, i
     CK(cudaStreamSynchronize(b->stream));
     const int d = b->model.cfg.end2end ? 0 : b->model.cfg.features_delay;
     for (int s = 0; s < n; s++) for (int f = 0; f < nframes; f++) {
-        memcpy(ga + ((size_t)s * nframes + f) * 3 * na, &hA[((size_t)f * n + s) * 3 * na], sizeof(float) * 3 * na);
+        if (isf) memcpy(ga + ((size_t)s * nframes + f) * 3 * na, &hA[((size_t)f * n + s) * 3 * na], sizeof(float) * 3 * na);
+        else for (int g = 0; g < 3; g++) memcpy(ga + ((size_t)s * nframes + f) * 3 * na + (size_t)g * na, &hA[(size_t)f * fA + ((size_t)g * n + s) * (na + 8)], sizeof(float) * na);
         memcpy(gb + ((size_t)s * nframes + f) * 3 * NB, &hB[((size_t)f * n + s) * 3 * NB], sizeof(float) * 3 * NB);
         for (int i = 0; i < LPC_ORDER; i++) lpc[((size_t)s * nframes + f) * LPC_ORDER + i] = hl[((size_t)(f + 2 - d) * n + s) * LPC_ORDER + i] * gp[i];
     }

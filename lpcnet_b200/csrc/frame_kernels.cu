@@ -30,7 +30,7 @@ namespace lpcnet_b200 {
 constexpr int GT_N = 128, GT_C = 32, GT_K = 16, GT_XPAD = 36, GT_THREADS = 64;
 
 struct GemmArgs {
-    const float *W, *bias; int M, N;       // W[j*N + i] (reference layout of dense / conv weights: dump_lpcnet.py:194-200,229-245)
+    const float *W, *bias; int M, N, ldw;  // W[j*ldw + i], i < N (reference layout of dense / conv weights: dump_lpcnet.py:194-200,229-245; ldw > N: a column slice)
     const float *X; int xS, xF;            // column (s, f) reads its M inputs at X + ((size_t)s*xS + f)*xF  (conv: overlapping windows, xF < M)
     float *Y; long long ys, yf, y0;        // output i of column (s, f) goes to Y + s*ys + f*yf + y0 + i
     int F, ncols;                          // frames per stream in this call, ncols = n*F
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(GT_THREADS) frame_gemm_kernel(const GemmArgs a
     float4 wreg[8], xreg[2];
     auto gload = [&](int k0) {
 #pragma unroll
-        for (int e = 0; e < 8; e++) { const int k = k0 + wr + 2 * e; wreg[e] = (wvalid && k < a.M) ? ldg4(wp + (size_t)k * a.N) : zero4; }
+        for (int e = 0; e < 8; e++) { const int k = k0 + wr + 2 * e; wreg[e] = (wvalid && k < a.M) ? ldg4(wp + (size_t)k * a.ldw) : zero4; }
 #pragma unroll
         for (int h = 0; h < 2; h++) xreg[h] = (xvalid[h] && k0 + 4 * kq < a.M) ? ldg4(xp[h] + k0) : zero4;
     };
@@ -281,8 +281,8 @@ void launch_frame_network(const DeviceModel &m, const FrameState &fs, const floa
     frame_assemble_kernel<<<n, 128, 0, st>>>(io);
     const int ncols = n * F;
     auto gemm = [&](bool tanh_act, const float *W, const float *bias, int M, int N, const float *X, int xS, int xF,
-                    float *Y, long long ys, long long yf, long long y0, const int *fc, int zthr) {
-        GemmArgs g{W, bias, M, N, X, xS, xF, Y, ys, yf, y0, F, ncols, fc, zthr, m.rcp16};
+                    float *Y, long long ys, long long yf, long long y0, const int *fc, int zthr, int ldw = 0) {
+        GemmArgs g{W, bias, M, N, ldw ? ldw : N, X, xS, xF, Y, ys, yf, y0, F, ncols, fc, zthr, m.rcp16};
         dim3 grid((ncols + GT_C - 1) / GT_C, (N + GT_N - 1) / GT_N);
         if (tanh_act) frame_gemm_kernel<true><<<grid, GT_THREADS, 0, st>>>(g);
         else frame_gemm_kernel<false><<<grid, GT_THREADS, 0, st>>>(g);
@@ -294,13 +294,19 @@ void launch_frame_network(const DeviceModel &m, const FrameState &fs, const floa
     gemm(true, m.dense1_w, m.dense1_b, COND, COND, P, F, COND, Q, (long long)F * COND, COND, 0, nullptr, 0);
     gemm(true, m.dense2_w, m.dense2_b, COND, COND, Q, F, COND, P, (long long)F * COND, COND, 0, nullptr, 0);
     // gru_a_dense_feature (128 -> 3*na, linear) and gru_b_dense_feature (128 -> 48, linear): outputs frame-major [f][n][.]
-    gemm(false, m.gad_w, m.gad_b, COND, na3, P, F, COND, condA, na3, (long long)n * na3, 0, nullptr, 0);
+    if (m.is_float) gemm(false, m.gad_w, m.gad_b, COND, na3, P, F, COND, condA, na3, (long long)n * na3, 0, nullptr, 0);
+    else {
+        // int8 flavour: one GEMM per gate (a column slice of the weight matrix) into the gate-major, tile-pitched layout (condA_frame_floats)
+        const long long crow = m.na + 8, fA = (long long)condA_frame_floats(false, (size_t)n, m.na);
+        for (int g = 0; g < 3; g++)
+            gemm(false, m.gad_w + (size_t)g * m.na, m.gad_b + (size_t)g * m.na, COND, m.na, P, F, COND, condA + (size_t)g * n * crow, crow, fA, 0, nullptr, 0, na3);
+    }
     gemm(false, m.gbd_w, m.gbd_b, COND, 3 * NB, P, F, COND, condB, 3 * NB, (long long)n * 3 * NB, 0, nullptr, 0);
     frame_finish_kernel<<<n, 128, 0, st>>>(io);
     if (fork) cudaStreamWaitEvent(st, fs.ev_join, 0);
     else if (lpc_path) lpc_part();
 }
-int frame_network_launches(const DeviceModel &m) { return m.cfg.end2end ? 8 : 11; }
+int frame_network_launches(const DeviceModel &m) { return (m.cfg.end2end ? 8 : 11) + (m.is_float ? 0 : 2); }
 size_t frame_work_floats(size_t n) { return n * ((size_t)(FRAME_CHUNK + 2) * (FRAME_IN + COND) + 2 * (size_t)FRAME_CHUNK * COND); }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -54,6 +54,18 @@
 #ifndef LPCNET_PACK_ACT
 #define LPCNET_PACK_ACT 1      // GRU_A activations: also the mul -> add pieces run two neurons at a time (oadd2, devmath.cuh)
 #endif
+#ifndef LPCNET_COND_TMA
+#define LPCNET_COND_TMA 0      // 1: the conditioning rows of a gather tile come by TMA ahead of the sampled indices (gather_half_tma below): the tile
+                               // fill drops from 3.7 k to 2.7 k cycles, but the same bytes then cross the shared-memory port twice (TMA write + LDS) and
+                               // the step does not get shorter (measured 1 % longer, profiles/r02q_sweep.txt); kept as a build option
+#endif
+#ifndef LPCNET_FCW_PREFETCH
+#define LPCNET_FCW_PREFETCH 0  // 1: the sampler prefetches the dual_fc rows of the tree levels that are read from global memory into L1 two levels
+                               // ahead (CCTL.PF1); measured neutral (profiles/r02q_sweep.txt), off
+#endif
+#ifndef LPCNET_EXPERIMENT
+#define LPCNET_EXPERIMENT 0    // timing experiments only (wrong output): 1 = sampler delayed by 1000 cycles, 2 = sampler skips the two lowest tree levels
+#endif
 #ifndef LPCNET_GATHER_NOALLOC
 #define LPCNET_GATHER_NOALLOC 0
 #endif
@@ -66,8 +78,17 @@
 // tuning builds (-DLPCNET_TRACE): clock64 stamps of CTA 0 for samples 200..207 of a launch
 #ifdef LPCNET_TRACE
 #define TRACE(P_, step_, ev_, lane_) do { if (blockIdx.x == 0 && (lane_) == 0 && (step_) >= 200 && (step_) < 208) (P_).trace[((step_) - 200) * 32 + (ev_)] = clock64(); } while (0)
+#ifdef LPCNET_TRACE_W0
+#define TRACEC TRACE         // the detailed stamps of compute warp 0 (they cost that warp ~12 extra clock reads + stores per sample)
+#else
+#define TRACEC(P_, step_, ev_, lane_) do { } while (0)
+#endif
+// the same stamp for every warp: [8 samples][32 warps][16 events] behind the first table
+#define TRACEW(P_, step_, ev_) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (step_) >= 200 && (step_) < 208) (P_).trace[256 + (((step_) - 200) * 32 + (threadIdx.x >> 5)) * 16 + (ev_)] = clock64(); } while (0)
 #else
 #define TRACE(P_, step_, ev_, lane_) do { } while (0)
+#define TRACEC(P_, step_, ev_, lane_) do { } while (0)
+#define TRACEW(P_, step_, ev_) do { } while (0)
 #endif
 
 namespace lpcnet_b200 {
@@ -257,8 +278,9 @@ struct QuadPipe {
     __device__ __forceinline__ void finish() { tmem_wait_ld(nW0, nM0, nW1, nM1); }
 };
 
-// Stream slots of a CTA: slot (half hh, row si) holds stream  cta_s0 + 2*si + hh  of the batch, live while 2*si + hh < spc
-// (the halves share a partially filled CTA evenly); in the half-A-only schedule (ONE, spc <= 16) slot (0, si) holds stream
+// Stream slots of a CTA: the CTA's spc streams are split between the halves, half A takes the first ceil(spc/2): slot (half hh, row si)
+// holds stream  cta_s0 + hh*ceil(spc/2) + si  — the rows of a half are CONSECUTIVE streams, so their conditioning rows are one
+// contiguous piece of condA (engine.h, condA_frame_floats); in the half-A-only schedule (ONE, spc <= 16) slot (0, si) holds stream
 // cta_s0 + si and half B is dead.  Dead slots shadow the batch's last stream: loads valid, stores masked.
 template <bool ONE>
 __device__ __forceinline__ int slot_stream(int cta_s0, int hh, int si, int spc, int n, bool &live)
@@ -268,10 +290,12 @@ __device__ __forceinline__ int slot_stream(int cta_s0, int hh, int si, int spc, 
         live = hh == 0 && si < spc && g < n;
         return min(g, n - 1);
     }
-    const int c = 2 * si + hh, g = cta_s0 + c;
-    live = c < spc && g < n;
+    const int na_ = (spc + 1) >> 1, c = hh * na_ + si, g = cta_s0 + c;
+    live = si < (hh ? spc - na_ : na_) && g < n;
     return min(g, n - 1);
 }
+// the conditioning row (gate, stream) of a frame: condA_frame_floats (engine.h)
+__device__ __forceinline__ const float *cond_row(const float *cond_f, int n, int gate, int sg) { return cond_f + ((size_t)gate * n + sg) * GIN_ROW; }
 
 // Producer warps: ONE gate's input term for the 16 streams of a half,
 //   G[si][k] = ((cond[s][k] + E_sig[a_s][k]) + E_pred[b_s][k]) + E_exc[c_s][k]        (nnet.c:484-491, left to right)
@@ -291,7 +315,7 @@ __device__ __forceinline__ void gather_half(float *__restrict__ G, const float *
         bool live;
         const int sg = slot_stream<ONE>(cta_s0, hh, si, spc, n, live);
         if (!live) continue;                                     // dead slot: its tile row is never used for anything that is stored
-        const float *c = cond_f + (size_t)sg * (3 * NA) + col;
+        const float *c = cond_row(cond_f, n, gate, sg) + lane * 4;
         const float *e0 = emb_sig + idx_h[si] * (3 * NA) + col;
         const float *e1 = emb_pred + idx_h[HALF + si] * (3 * NA) + col;
         const float *e2 = emb_exc + idx_h[2 * HALF + si] * (3 * NA) + col;
@@ -308,6 +332,76 @@ __device__ __forceinline__ void gather_half(float *__restrict__ G, const float *
             r.z = __fadd_rn(__fadd_rn(__fadd_rn(a[j].z, b[j].z), d[j].z), e[j].z);
             r.w = __fadd_rn(__fadd_rn(__fadd_rn(a[j].w, b[j].w), d[j].w), e[j].w);
             *reinterpret_cast<float4 *>(g + 128 * j) = r;
+        }
+    }
+}
+
+// The same tile with the conditioning row prefetched.  Of the four rows that make a tile row only three depend on the indices the
+// sampler has just produced; the conditioning row is known a whole frame ahead.  Producer 0 therefore starts one TMA bulk copy per
+// live tile row (NA*4 bytes, straight into the row's place in the tile) for all three tiles of a half-step BEFORE it waits for the
+// indices (kernel body), and the gather proper adds the three embedding rows in place:
+//   G[si][k] = ((G[si][k] + E_sig[a][k]) + E_pred[b][k]) + E_exc[c][k]
+// Three dependent loads per element instead of four: the 12 LDG.128 a lane keeps in flight cover FOUR 128-column row pieces instead of
+// three, and a tile is two latency-bound load batches per producer instead of three (the tile fill is on the serial chain of a
+// sample: indices -> tiles -> activations -> GRU_B -> sampler -> indices).  Work split: rows 0..FULL_ROWS-1 are dealt whole, row
+// p + NWP*b to producer p in batch b; the pieces of the remaining rows go round the producers, one per batch.
+// Rows >= late0 (only for the r tile, which takes the slot the half's GRU_B state scratch lives in: engine.h, Geom::late_row0) could
+// not be prefetched (the sampler may still be reading the scratch): their conditioning piece is loaded here like the others.
+constexpr int FULL_ROWS = (HALF / NWP) * NWP, GATHER_BATCHES = HALF / NWP;
+static_assert((HALF - FULL_ROWS) * (NA / 128) <= GATHER_BATCHES * NWP, "one piece of the shared rows per producer and batch");
+template <bool ONE>
+__device__ __forceinline__ void gather_half_tma(float *__restrict__ G, const float *__restrict__ cond_f, int n, int cta_s0, int hh, int spc, int nl, int late0,
+                                                const float *__restrict__ emb_sig, const float *__restrict__ emb_pred,
+                                                const float *__restrict__ emb_exc, const int *__restrict__ idx_h,
+                                                int gate, int p, int lane)
+{
+    constexpr int NCH = NA / 128;
+    const int col = gate * NA + lane * 4;
+#pragma unroll 1
+    for (int b = 0; b < GATHER_BATCHES; b++) {
+        const int r = p + NWP * b;                               // whole row
+        const int c = p + NWP * b, rs = FULL_ROWS + c / NCH, cj = c % NCH;   // piece cj of shared row rs
+        const bool hasr = r < nl, hass = c < (HALF - FULL_ROWS) * NCH && rs < nl, lates = hass && rs >= late0;
+        float4 B[NCH], D[NCH], E[NCH], sb, sd, se, sc;
+        if (hasr) {
+            const float *e0 = emb_sig + idx_h[r] * (3 * NA) + col;
+            const float *e1 = emb_pred + idx_h[HALF + r] * (3 * NA) + col;
+            const float *e2 = emb_exc + idx_h[2 * HALF + r] * (3 * NA) + col;
+#pragma unroll
+            for (int j = 0; j < NCH; j++) { B[j] = GLD(e0 + 128 * j); D[j] = GLD(e1 + 128 * j); E[j] = GLD(e2 + 128 * j); }
+        }
+        if (hass) {
+            sb = GLD(emb_sig + idx_h[rs] * (3 * NA) + col + 128 * cj);
+            sd = GLD(emb_pred + idx_h[HALF + rs] * (3 * NA) + col + 128 * cj);
+            se = GLD(emb_exc + idx_h[2 * HALF + rs] * (3 * NA) + col + 128 * cj);
+            if (lates) {
+                bool live;
+                const int sg = slot_stream<ONE>(cta_s0, hh, rs, spc, n, live);
+                sc = GLD(cond_row(cond_f, n, gate, sg) + lane * 4 + 128 * cj);
+            }
+        }
+        if (hasr) {
+            float *g = G + r * GIN_ROW + lane * 4;
+#pragma unroll
+            for (int j = 0; j < NCH; j++) {
+                const float4 a = *reinterpret_cast<const float4 *>(g + 128 * j);
+                float4 o;
+                o.x = __fadd_rn(__fadd_rn(__fadd_rn(a.x, B[j].x), D[j].x), E[j].x);
+                o.y = __fadd_rn(__fadd_rn(__fadd_rn(a.y, B[j].y), D[j].y), E[j].y);
+                o.z = __fadd_rn(__fadd_rn(__fadd_rn(a.z, B[j].z), D[j].z), E[j].z);
+                o.w = __fadd_rn(__fadd_rn(__fadd_rn(a.w, B[j].w), D[j].w), E[j].w);
+                *reinterpret_cast<float4 *>(g + 128 * j) = o;
+            }
+        }
+        if (hass) {
+            float *g = G + rs * GIN_ROW + lane * 4 + 128 * cj;
+            if (!lates) sc = *reinterpret_cast<const float4 *>(g);
+            float4 o;
+            o.x = __fadd_rn(__fadd_rn(__fadd_rn(sc.x, sb.x), sd.x), se.x);
+            o.y = __fadd_rn(__fadd_rn(__fadd_rn(sc.y, sb.y), sd.y), se.y);
+            o.z = __fadd_rn(__fadd_rn(__fadd_rn(sc.z, sb.z), sd.z), se.z);
+            o.w = __fadd_rn(__fadd_rn(__fadd_rn(sc.w, sb.w), sd.w), se.w);
+            *reinterpret_cast<float4 *>(g) = o;
         }
     }
 }
@@ -579,7 +673,7 @@ __device__ __forceinline__ void grub(const ComputeCtx &C, const SampleParams &P,
     const uint32_t mb_full = smem_u32(smem + MB_FULL), mb_empty = smem_u32(smem + MB_EMPTY);
     (void)t; (void)warp; (void)rcp; (void)nxt; (void)xs_cur; (void)lc; (void)xs_nxt; (void)tile_r; (void)tile_z; (void)tile_h; (void)mb_full; (void)mb_empty; (void)lane;
     mbar_wait(smem_u32(smem + MB_X) + 8 * H, par);               // new quantised GRU_A state complete; candidate-gate tile dead: GRU_B scratch may use it
-    TRACE(P, trstep, 27, warp == 0 ? lane : 1);
+    TRACEC(P, trstep, 27, warp == 0 ? lane : 1);
     // ---------------- GRU_B input GEMV (48 x 384 int8, dense): warp = (row group, K part) ----------------
     int *accB = reinterpret_cast<int *>(tile_hb + T_ACCB);
     float *hBs = reinterpret_cast<float *>(tile_hb + T_HBS);
@@ -595,7 +689,7 @@ __device__ __forceinline__ void grub(const ComputeCtx &C, const SampleParams &P,
         dst[0] = acc[0]; dst[ACCB_ROW] = acc[1]; dst[8] = acc[2]; dst[ACCB_ROW + 8] = acc[3];
         warp_arrive(smem_u32(smem + MB_ACCB) + 8 * H, lane);
     }
-    TRACE(P, trstep, 28, warp == 0 ? lane : 1);
+    TRACEC(P, trstep, 28, warp == 0 ? lane : 1);
     // ---------------- GRU_B finish (nnet.c:346-371): warp < NFIN, lane = (neuron parity, stream of the half) ----------------
     uint32_t *xb = reinterpret_cast<uint32_t *>(smem + SM_XB) + H * (2 * 4 * HALF);
     if (warp < NFIN) {
@@ -613,7 +707,7 @@ __device__ __forceinline__ void grub(const ComputeCtx &C, const SampleParams &P,
             rh = dp4a_us(xw, *reinterpret_cast<const int *>(C.wBrec + ((((2 * NB + jb) >> 3) * 4 + k) * 8 + ((2 * NB + jb) & 7)) * 4), rh);
         }
         mbar_wait(smem_u32(smem + MB_ACCB) + 8 * H, par);      // all K-part partial sums are in accB
-        TRACE(P, trstep, 29, warp == 0 ? lane : 1);
+        TRACEC(P, trstep, 29, warp == 0 ? lane : 1);
         int az = acc_init(__fadd_rn(C.parB[jb], cbz)), ar = acc_init(__fadd_rn(C.parB[NB + jb], cbr)), ah = acc_init(__fadd_rn(C.parB[2 * NB + jb], cbh));
 #pragma unroll
         for (int kp = 0; kp < KPARTS; kp++) {
@@ -652,6 +746,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         for (int b = 0; b < NTILE; b++) { mbar_init(smem_u32(smem + MB_FULL) + 8 * b, NWP * ARRIVALS_PER_WARP); mbar_init(smem_u32(smem + MB_EMPTY) + 8 * b, NWC * ARRIVALS_PER_WARP); }
+        for (int b = 0; b < NTILE; b++) mbar_init(smem_u32(smem + MB_COND) + 8 * b, 1);
         for (int hh = 0; hh < 2; hh++) { mbar_init(smem_u32(smem + MB_IDX) + 8 * hh, ARRIVALS_PER_WARP); mbar_init(smem_u32(smem + MB_X) + 8 * hh, NWC * ARRIVALS_PER_WARP); mbar_init(smem_u32(smem + MB_ACCB) + 8 * hh, NWB * ARRIVALS_PER_WARP); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -767,23 +862,23 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
             for (int t_ = 0; t_ < spf; t_++, step++, k += 6) {
                 int Sh[GPW][4], Sg[GPW][4];                              // candidate-gate sums (later rec_h * r) / r-gate, then z-gate sums (later z)
                 const int tl = warp == 0 ? lane : 1; (void)tl;    // (lane selector of the TRACE stamps)
-                TRACE(P, step, 0, tl);
+                TRACEC(P, step, 0, tl); TRACEW(P, step, 0);
                 gemv_rh<0>(C, Sh, Sg, step & 1);
-                TRACE(P, step, 1, tl);
+                TRACEC(P, step, 1, tl); TRACEW(P, step, 1);
                 if (step > 0) grub<1, FAST>(C, P, hb[1], k - 3, (step - 1) & 1, f_prev, s_fin[1], (step - 1) & 1);
-                TRACE(P, step, 2, tl);       // = HB of half B (previous sample) signalled
+                TRACEC(P, step, 2, tl); TRACEW(P, step, 2);       // = HB of half B (previous sample) signalled
                 mbar_wait(smem_u32(smem + MB_FULL) + 8 * (k & 3), (k >> 2) & 1);
-                TRACE(P, step, 3, tl);       // r tile of half A present
+                TRACEC(P, step, 3, tl); TRACEW(P, step, 3);       // r tile of half A present
                 activations<0, FAST>(C, Sh, Sg, k, step & 1);
-                TRACE(P, step, 4, tl);
+                TRACEC(P, step, 4, tl); TRACEW(P, step, 4);
                 gemv_rh<1>(C, Sh, Sg, step & 1);
-                TRACE(P, step, 5, tl);
+                TRACEC(P, step, 5, tl); TRACEW(P, step, 5);
                 grub<0, FAST>(C, P, hb[0], k, step & 1, f, s_fin[0], step & 1, step);
-                TRACE(P, step, 6, tl);       // = HB of half A signalled
+                TRACEC(P, step, 6, tl); TRACEW(P, step, 6);       // = HB of half A signalled
                 mbar_wait(smem_u32(smem + MB_FULL) + 8 * ((k + 3) & 3), ((k + 3) >> 2) & 1);
-                TRACE(P, step, 7, tl);       // r tile of half B present
+                TRACEC(P, step, 7, tl); TRACEW(P, step, 7);       // r tile of half B present
                 activations<1, FAST>(C, Sh, Sg, k + 3, step & 1);
-                TRACE(P, step, 8, tl);
+                TRACEC(P, step, 8, tl); TRACEW(P, step, 8);
                 f_prev = f;
             }
         if (step > 0) grub<1, FAST>(C, P, hb[1], k - 3, (step - 1) & 1, f_prev, s_fin[1], (step - 1) & 1);
@@ -820,19 +915,55 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
         const int p = warp - NWC;
         const uint32_t mb_full = smem_u32(smem + MB_FULL), mb_empty = smem_u32(smem + MB_EMPTY), mb_idx = smem_u32(smem + MB_IDX);
         uint32_t k = 0, it = 0;
+#if LPCNET_COND_TMA
+        const uint32_t mb_cond = smem_u32(smem + MB_COND);
+        int nlive[2] = {0, 0};                                           // live tile rows of the halves (the live slots of a half are its first rows)
+        for (int hh = 0; hh < 2; hh++)
+            for (int si = 0; si < HALF; si++) { bool live; slot_stream<ONE>(cta_s0, hh, si, spc, n, live); nlive[hh] += live ? 1 : 0; }
+#endif
         for (int f = 0; f < P.nframes; f++) {
-            const float *condA_f = P.condA + (size_t)f * n * (3 * NA);
+            const float *condA_f = P.condA + (size_t)f * n * (3 * GIN_ROW);
             for (int t_ = 0; t_ < spf; t_++, it++)
 #pragma unroll 1
                 for (int hh = 0; hh < (one ? 1 : 2); hh++) {
+#if LPCNET_COND_TMA
+                    const int nl = nlive[hh];
+                    if (p == 0) {
+                        // conditioning rows of the half-step's three tiles, ahead of the indices (gather_half_tma).  A slot is written only
+                        // after every compute warp has released its previous contents; the r tile takes the slot whose last rows hold the
+                        // half's GRU_B state scratch, which the sampler reads until it publishes the indices: those rows are left out here.
+#pragma unroll 1
+                        for (int gi = 0; gi < 3; gi++) {
+                            const uint32_t kk = k + gi;
+                            const int gate = gi == 0 ? 1 : (gi == 1 ? 0 : 2), rows = gi == 0 ? min(nl, LATE_ROW0) : nl;
+                            mbar_wait(mb_empty + 8 * (kk & 3), ((kk >> 2) & 1) ^ 1);
+                            if (lane == 0) {
+                                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic accesses of the old contents before the async-proxy writes
+                                mbar_expect_tx(mb_cond + 8 * (kk & 3), (uint32_t)rows * (GIN_ROW * 4));
+                                if (rows > 0) {                                              // the rows of a half are consecutive streams: ONE bulk copy, pitch = tile pitch
+                                    bool live;
+                                    const int sg0 = slot_stream<ONE>(cta_s0, hh, 0, spc, n, live);
+                                    bulk_g2s(smem_u32(smem + SM_TILES + (kk & 3) * TILE_BYTES), cond_row(condA_f, n, gate, sg0), (uint32_t)rows * (GIN_ROW * 4), mb_cond + 8 * (kk & 3));
+                                }
+                            }
+                            __syncwarp();
+                        }
+                    }
+#endif
                     mbar_wait(mb_idx + 8 * hh, it & 1);                  // indices of this sample of the half are in idx_s
                     TRACE(P, (int)it, 10 + 4 * hh, p == 0 ? lane : 1);
 #pragma unroll 1
                     for (int gi = 0; gi < 3; gi++, k++) {
                         const int gate = gi == 0 ? 1 : (gi == 1 ? 0 : 2);    // fill order r, z, h
+#if LPCNET_COND_TMA
+                        mbar_wait(mb_cond + 8 * (k & 3), (k >> 2) & 1);      // conditioning rows landed (issued after the slot was released)
+                        gather_half_tma<ONE>(reinterpret_cast<float *>(smem + SM_TILES + (k & 3) * TILE_BYTES), condA_f, n, cta_s0, hh, spc, nl, gi == 0 ? LATE_ROW0 : HALF,
+                                    P.emb_sig, P.emb_pred, P.emb_exc, idx_s + hh * 3 * HALF, gate, p, lane);
+#else
                         mbar_wait(mb_empty + 8 * (k & 3), ((k >> 2) & 1) ^ 1);  // previous contents of the tile consumed
                         gather_half<ONE>(reinterpret_cast<float *>(smem + SM_TILES + (k & 3) * TILE_BYTES), condA_f, n, cta_s0, hh, spc,
                                     P.emb_sig, P.emb_pred, P.emb_exc, idx_s + hh * 3 * HALF, gate, p, lane);
+#endif
                         warp_arrive(mb_full + 8 * (k & 3), lane);
                         TRACE(P, (int)it, 11 + 4 * hh + gi, p == 0 ? lane : 1);
                     }
@@ -907,8 +1038,11 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
 #pragma unroll
                 for (int j = 0; j < NB; j++) hbv[j] = hBs[j * HALF + si];
                 int val = 0;
+#if LPCNET_EXPERIMENT == 1
+                { const long long t0 = clock64(); while (clock64() - t0 < 1000) { } }      // (timing experiment: a slower sampler)
+#endif
 #pragma unroll
-                for (int b = 0; b < 8; b++) {                            // sample_mdense, nnet.c:186-211
+                for (int b = 0; b < (LPCNET_EXPERIMENT == 2 ? 6 : 8); b++) {                            // sample_mdense, nnet.c:186-211
                     const int i = (1 << b) | val;
                     // this lane's channel: a sequential 16-term chain
                     float w16[16], sum, fac;
@@ -932,6 +1066,21 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
                     const float other = __shfl_xor_sync(0xffffffffu, mine, 16);
                     const float tot = __fadd_rn(mine, other);            // channel 0 + channel 1 (commutative: both lanes get the same bits)
                     val = (val << 1) | (thr[b] < tot ? 1 : 0);
+#if LPCNET_FCW_PREFETCH
+                    // The node of level b+2 is one of two adjacent rows (288 bytes) once this decision is known.  If that level's rows are not in
+                    // shared memory, start them towards L1 now: an L2 round trip (~1 k cycles under load, twice per sample) leaves the serial
+                    // chain indices -> tiles -> GRU -> sampler -> indices.
+                    if (b + 2 < 8 && ch == 0) {
+                        const int i2 = (1 << (b + 2)) | (val << 1);
+                        if (!(b + 2 < 3 || (b + 2 < 6 && i2 + 1 < fcw_nodes))) {
+                            const char *r2 = reinterpret_cast<const char *>(P.fcw + (size_t)i2 * FCW_ROW);
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(r2));
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(r2 + 128));
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(r2 + 256));
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(r2 + 2 * FCW_ROW * 4 - 4));
+                        }
+                    }
+#endif
                 }
                 int exc = val;
                 float pcm;

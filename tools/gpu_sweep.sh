@@ -14,10 +14,10 @@ for so in lpcnet_b200/variants/lib_*.so; do
   echo "$k | $par | $t" | tee -a gpurun_out/sweep_${TAG}.txt
 done
 if [ -f lpcnet_b200/variants/lib_trace.so ]; then
-  LPCNET_B200_SO=$PWD/lpcnet_b200/variants/lib_trace.so timeout 120 python tools/trace_run.py > gpurun_out/trace_${TAG}.txt 2>&1; tail -45 gpurun_out/trace_${TAG}.txt
+  LPCNET_B200_SO=$PWD/lpcnet_b200/variants/lib_trace.so timeout 120 python tools/trace_run.py > gpurun_out/trace_${TAG}.txt 2>&1; tail -64 gpurun_out/trace_${TAG}.txt
 fi
-timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -8 | tee gpurun_out/pytest_${TAG}.txt
-timeout 300 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err
+timeout 300 python -m pytest tests -m gpu -q -x 2>&1 | tail -8 | tee gpurun_out/pytest_${TAG}.txt
+timeout 150 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err
 python - <<PY
 import json
 d=json.loads(open("gpurun_out/bench_${TAG}.json").read().strip().splitlines()[-1])

@@ -6,12 +6,9 @@ sys.path.insert(0, ROOT)
 # geometry / option variants of the int8 per-sample kernel (compile-time macros of sample_kernel.cu / engine.h).  Measured in
 # round 1: 16 compute warps + 6 producers is the best geometry (12 and 24 compute warps are within 5 %).
 VARIANTS = {
-    "default": [],                            # LDTM.x4 + packed activations
-    "base": ["LPCNET_LDTM_X4=0", "LPCNET_PACK_ACT=0"],     # the kernel before these two
-    "no_x4": ["LPCNET_LDTM_X4=0"],
-    "no_pack": ["LPCNET_PACK_ACT=0"],
-    "arith_r": ["LPCNET_RCP_ARITH=1"],        # table-free RCPPS for one gate: trades LSU wavefronts for issue slots
-    "arith_h": ["LPCNET_RCP_ARITH=4"],
+    "default": [],
+    "exp_slow_sampler": ["LPCNET_EXPERIMENT=1"],
+    "exp_short_sampler": ["LPCNET_EXPERIMENT=2"],
 }
 if sys.argv[1] == "build":
     from lpcnet_b200 import build
