@@ -66,6 +66,10 @@
 #ifndef LPCNET_EXPERIMENT
 #define LPCNET_EXPERIMENT 0    // timing experiments only (wrong output): 1 = sampler delayed by 1000 cycles, 2 = sampler skips the two lowest tree levels
 #endif
+#ifndef LPCNET_GRUB_FIRST
+#define LPCNET_GRUB_FIRST 3    // bit 0 / bit 1: GRU_B of half A / half B runs right after the half's activations, before the other half's first GEMVs
+                               // (the GRU_B state is what the half's sampler waits for: 19.52 -> 19.05 ms per 1600 samples, profiles/r02r_sweep.txt)
+#endif
 #ifndef LPCNET_GATHER_NOALLOC
 #define LPCNET_GATHER_NOALLOC 0
 #endif
@@ -863,17 +867,29 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
                 int Sh[GPW][4], Sg[GPW][4];                              // candidate-gate sums (later rec_h * r) / r-gate, then z-gate sums (later z)
                 const int tl = warp == 0 ? lane : 1; (void)tl;    // (lane selector of the TRACE stamps)
                 TRACEC(P, step, 0, tl); TRACEW(P, step, 0);
+#if LPCNET_GRUB_FIRST & 2
+                if (step > 0) grub<1, FAST>(C, P, hb[1], k - 3, (step - 1) & 1, f_prev, s_fin[1], (step - 1) & 1);
+                TRACEC(P, step, 1, tl); TRACEW(P, step, 1);
+                gemv_rh<0>(C, Sh, Sg, step & 1);
+#else
                 gemv_rh<0>(C, Sh, Sg, step & 1);
                 TRACEC(P, step, 1, tl); TRACEW(P, step, 1);
                 if (step > 0) grub<1, FAST>(C, P, hb[1], k - 3, (step - 1) & 1, f_prev, s_fin[1], (step - 1) & 1);
+#endif
                 TRACEC(P, step, 2, tl); TRACEW(P, step, 2);       // = HB of half B (previous sample) signalled
                 mbar_wait(smem_u32(smem + MB_FULL) + 8 * (k & 3), (k >> 2) & 1);
                 TRACEC(P, step, 3, tl); TRACEW(P, step, 3);       // r tile of half A present
                 activations<0, FAST>(C, Sh, Sg, k, step & 1);
                 TRACEC(P, step, 4, tl); TRACEW(P, step, 4);
+#if LPCNET_GRUB_FIRST & 1
+                grub<0, FAST>(C, P, hb[0], k, step & 1, f, s_fin[0], step & 1, step);
+                TRACEC(P, step, 5, tl); TRACEW(P, step, 5);
+                gemv_rh<1>(C, Sh, Sg, step & 1);
+#else
                 gemv_rh<1>(C, Sh, Sg, step & 1);
                 TRACEC(P, step, 5, tl); TRACEW(P, step, 5);
                 grub<0, FAST>(C, P, hb[0], k, step & 1, f, s_fin[0], step & 1, step);
+#endif
                 TRACEC(P, step, 6, tl); TRACEW(P, step, 6);       // = HB of half A signalled
                 mbar_wait(smem_u32(smem + MB_FULL) + 8 * ((k + 3) & 3), ((k + 3) >> 2) & 1);
                 TRACEC(P, step, 7, tl); TRACEW(P, step, 7);       // r tile of half B present

@@ -7,8 +7,10 @@ sys.path.insert(0, ROOT)
 # round 1: 16 compute warps + 6 producers is the best geometry (12 and 24 compute warps are within 5 %).
 VARIANTS = {
     "default": [],
-    "exp_slow_sampler": ["LPCNET_EXPERIMENT=1"],
-    "exp_short_sampler": ["LPCNET_EXPERIMENT=2"],
+    "tma": ["LPCNET_COND_TMA=1"],
+    "pf": ["LPCNET_FCW_PREFETCH=1"],
+    "tma_pf": ["LPCNET_COND_TMA=1", "LPCNET_FCW_PREFETCH=1"],
+    "arith_r": ["LPCNET_RCP_ARITH=1"],
 }
 if sys.argv[1] == "build":
     from lpcnet_b200 import build
