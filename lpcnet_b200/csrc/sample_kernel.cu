@@ -70,6 +70,9 @@
 #define LPCNET_GRUB_FIRST 3    // bit 0 / bit 1: GRU_B of half A / half B runs right after the half's activations, before the other half's first GEMVs
                                // (the GRU_B state is what the half's sampler waits for: 19.52 -> 19.05 ms per 1600 samples, profiles/r02r_sweep.txt)
 #endif
+#ifndef LPCNET_FIN_FIRST_WARP
+#define LPCNET_FIN_FIRST_WARP (NWC - NFIN)   // the NFIN compute warps that finish GRU_B: the LAST ones, which carry no (or the least) GRU_B GEMV work
+#endif
 #ifndef LPCNET_GATHER_NOALLOC
 #define LPCNET_GATHER_NOALLOC 0
 #endif
@@ -106,6 +109,7 @@ enum {
     BAR_HB = 3       // (+ half) finishing warps arrive, sampler waits: GRU_B state of the half's sample is in hBs
 };
 constexpr int CNT_C = NWC * 32, CNT_HB = NFIN * 32 + 32;
+constexpr int FIN0 = LPCNET_FIN_FIRST_WARP;
 __device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -694,10 +698,10 @@ __device__ __forceinline__ void grub(const ComputeCtx &C, const SampleParams &P,
         warp_arrive(smem_u32(smem + MB_ACCB) + 8 * H, lane);
     }
     TRACEC(P, trstep, 28, warp == 0 ? lane : 1);
-    // ---------------- GRU_B finish (nnet.c:346-371): warp < NFIN, lane = (neuron parity, stream of the half) ----------------
+    // ---------------- GRU_B finish (nnet.c:346-371): warps FIN0 .. FIN0+NFIN-1, lane = (neuron parity, stream of the half) ----------------
     uint32_t *xb = reinterpret_cast<uint32_t *>(smem + SM_XB) + H * (2 * 4 * HALF);
-    if (warp < NFIN) {
-        const int jb = 2 * warp + (lane >> 4), si = lane & 15;
+    if (warp >= FIN0 && warp < FIN0 + NFIN) {
+        const int jb = 2 * (warp - FIN0) + (lane >> 4), si = lane & 15;
         const float *condBp = P.condB + ((size_t)f * P.n_streams + s_fin) * (3 * NB);
         const float cbz = __ldg(condBp + jb), cbr = __ldg(condBp + NB + jb), cbh = __ldg(condBp + 2 * NB + jb);
         const uint32_t *xbc = xb + cur * 4 * HALF;
@@ -834,8 +838,9 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
                     *reinterpret_cast<uint16_t *>(smem + SM_XS + (C.xoff[sl] ^ (hh2 << 6)) + 4 * jj) = (uint16_t)(quant_u8(hv[2 * jj]) | (quant_u8(hv[2 * jj + 1]) << 8));
             }
         }
-        // GRU_B neuron finished by this lane (warps < NFIN): neuron 2*warp + (lane >> 4), stream lane & 15 of each half
-        const int jb_fin = min(2 * warp + (lane >> 4), NB - 1);
+        // GRU_B neuron finished by this lane (warps FIN0 .. FIN0+NFIN-1): neuron 2*(warp - FIN0) + (lane >> 4), stream lane & 15 of each half
+        const bool fin_warp = warp >= FIN0 && warp < FIN0 + NFIN;
+        const int jb_fin = min(max(2 * (warp - FIN0), 0) + (lane >> 4), NB - 1);
         int s_fin[2]; bool live_fin[2];
         float hb[2];
 #pragma unroll
@@ -844,7 +849,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
             hb[hh] = P.hB[(size_t)jb_fin * n + s_fin[hh]];
         }
         // quantised copy of the restored GRU_B state: xb[half][0] <- q(hB)
-        if (warp < NFIN) {
+        if (fin_warp) {
 #pragma unroll
             for (int hh = 0; hh < 2; hh++)
                 reinterpret_cast<uint8_t *>(smem + SM_XB)[(((hh * 2 + 0) * 4 + (jb_fin >> 2)) * HALF + (lane & 15)) * 4 + (jb_fin & 3)] = (uint8_t)quant_u8(hb[hh]);
@@ -915,7 +920,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
                         P.hA[(size_t)(C.gcol[sl] + 1) * n + sj[2 * hh2 + jj]] = hv[2 * jj + 1];
                     }
             }
-        if (warp < NFIN) {
+        if (fin_warp) {
 #pragma unroll
             for (int hh = 0; hh < 2; hh++) if (live_fin[hh]) P.hB[(size_t)jb_fin * n + s_fin[hh]] = hb[hh];
         }

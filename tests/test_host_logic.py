@@ -129,7 +129,9 @@ def test_smem_image_replays_to_the_dense_model(L):
                 np.testing.assert_array_equal(parA[w, sl, q, 1], arrs["sparse_gru_a_recurrent_weights_diag"][q * 384 + 8 * g:q * 384 + 8 * g + 8])
         loads.append(tot)
     np.testing.assert_array_equal(got, want_A)
-    assert sum(loads) == nA and max(loads) <= 1.2 * (sum(loads) / NWC)    # LPT balancing of the compute warps
+    # LPT balancing of the compute warps: the warps that also walk the GRU_B GEMV (first 12) and / or finish GRU_B (last 8) get lighter
+    # GRU_A lists (model.cu), so the quad counts differ by class but stay within +-35 % of the mean
+    assert sum(loads) == nA and max(loads) <= 1.35 * (sum(loads) / NWC) and min(loads) >= 0.65 * (sum(loads) / NWC)
     assert clashes <= 0.15 * 4 * nA                                       # slots of a quad mostly in different bank groups
 
     dirB = img[DIRB:DIRB + 6 * KP * 2 * 4].view(np.uint32).reshape(6, KP, 2)
