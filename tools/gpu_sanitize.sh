@@ -17,6 +17,6 @@ PY
 # racecheck runs on the checking build (python tools/build_check_variant.py): see warp_arrive() in sample_kernel.cu
 for tool in memcheck racecheck; do
   if [ $tool = racecheck ] && [ -f lpcnet_b200/variants/lib_arriveall.so ]; then export LPCNET_B200_SO=lpcnet_b200/variants/lib_arriveall.so; fi
-  timeout 1500 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san.py > gpurun_out/sanitizer_$tool.txt 2>&1
+  timeout 240 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san.py > gpurun_out/sanitizer_$tool.txt 2>&1
   tail -6 gpurun_out/sanitizer_$tool.txt
 done
