@@ -73,6 +73,11 @@
 #ifndef LPCNET_FIN_FIRST_WARP
 #define LPCNET_FIN_FIRST_WARP (NWC - NFIN)   // the NFIN compute warps that finish GRU_B: the LAST ones, which carry no (or the least) GRU_B GEMV work
 #endif
+#ifndef LPCNET_TREE_PAR
+#define LPCNET_TREE_PAR 0      // 1: sampler evaluates the seven nodes of the first three tree levels side by side (see the sampler loop); bit-exact but
+                               // 3.9 % slower (19.25 vs 18.53 ms, profiles/r02x_sweep.txt): four more dot products per sample and more spilled state in the
+                               // sampler cost more than the two serial rounds they save
+#endif
 #ifndef LPCNET_GATHER_NOALLOC
 #define LPCNET_GATHER_NOALLOC 0
 #endif
@@ -1062,8 +1067,33 @@ __global__ void __launch_bounds__(SAMPLE_THREADS, 1) lpcnet_sample_kernel(const 
 #if LPCNET_EXPERIMENT == 1
                 { const long long t0 = clock64(); while (clock64() - t0 < 1000) { } }      // (timing experiment: a slower sampler)
 #endif
+#if LPCNET_TREE_PAR
+                // The nodes of the first three tree levels (1..7, rows always in shared memory) do not depend on any decision: all seven are
+                // evaluated side by side (seven independent 16-term chains interleave in the pipeline) and the three decisions are then just
+                // compares, instead of three strictly serial load -> chain -> tanh -> shuffle -> compare rounds on the sample's critical path.
+                {
+                    float totn[8];
 #pragma unroll
-                for (int b = 0; b < (LPCNET_EXPERIMENT == 2 ? 6 : 8); b++) {                            // sample_mdense, nnet.c:186-211
+                    for (int nd = 1; nd < 8; nd++) {
+                        const float *wr = fcw + nd * FCW_ROW;
+                        const float4 a0 = *reinterpret_cast<const float4 *>(wr), a1 = *reinterpret_cast<const float4 *>(wr + 4);
+                        const float4 a2 = *reinterpret_cast<const float4 *>(wr + 8), a3 = *reinterpret_cast<const float4 *>(wr + 12);
+                        const float w16[16] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w, a3.x, a3.y, a3.z, a3.w};
+                        float sum = wr[2 * NB - ch * NB + ch];
+                        const float fac = wr[2 * NB - ch * NB + 2 + ch];
+#pragma unroll
+                        for (int j = 0; j < NB; j++) sum = __fadd_rn(sum, __fmul_rn(w16[j], hbv[j]));
+                        const float mine = __fmul_rn(fac, tanh_approx(sum, rcp));
+                        totn[nd] = __fadd_rn(mine, __shfl_xor_sync(0xffffffffu, mine, 16));
+                    }
+                    val = thr[0] < totn[1] ? 1 : 0;
+                    val = (val << 1) | (thr[1] < (val ? totn[3] : totn[2]) ? 1 : 0);
+                    const float t3 = (val & 2) ? ((val & 1) ? totn[7] : totn[6]) : ((val & 1) ? totn[5] : totn[4]);
+                    val = (val << 1) | (thr[2] < t3 ? 1 : 0);
+                }
+#endif
+#pragma unroll
+                for (int b = (LPCNET_TREE_PAR ? 3 : 0); b < (LPCNET_EXPERIMENT == 2 ? 6 : 8); b++) {                            // sample_mdense, nnet.c:186-211
                     const int i = (1 << b) | val;
                     // this lane's channel: a sequential 16-term chain
                     float w16[16], sum, fac;

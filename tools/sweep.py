@@ -6,9 +6,8 @@ sys.path.insert(0, ROOT)
 # geometry / option variants of the int8 per-sample kernel (compile-time macros of sample_kernel.cu / engine.h).  Measured in
 # round 1: 16 compute warps + 6 producers is the best geometry (12 and 24 compute warps are within 5 %).
 VARIANTS = {
-    "default": [],                                   # GRU_B finished by the last 8 compute warps
-    "fin_first": ["LPCNET_FIN_FIRST_WARP=0"],        # ... by the first 8 (which also walk the GRU_B GEMV)
-    "fin_mid": ["LPCNET_FIN_FIRST_WARP=4"],
+    "default": [],                                   # first three tree levels evaluated side by side
+    "tree_serial": ["LPCNET_TREE_PAR=0"],
 }
 if sys.argv[1] == "build":
     from lpcnet_b200 import build
