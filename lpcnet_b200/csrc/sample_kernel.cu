@@ -19,12 +19,16 @@
 //                     summation order is free): M = the 16 streams of the half, N = the 8 neurons of a row group, K = four
 //                     8x4 weight blocks ("quad") whose column blocks may be anywhere (block-sparse): the A fragment of lane
 //                     (gid, t) is gathered from the quantised state with ONE LDS.64 (the words of streams gid, gid+8 for
-//                     the column block of slot t), the B fragment is one LDS.32 of the quad's weights.  The accumulator
-//                     layout makes lane (gid, t) own neurons 2t, 2t+1 of the group for streams gid, gid+8 of each half:
-//                     the fp32 state of those (stream, neuron) pairs lives in its registers for the whole launch and the
-//                     activations are evaluated there.  The sums do not depend on the sampled excitation, so they are
-//                     computed before the gathered input term is waited for:
+//                     the column block of slot t); the B fragment (the lane's word of the quad's weights) and the slot's column
+//                     offset are lane-private constants of the model and live in TENSOR MEMORY (tcgen05.st once per launch,
+//                     tcgen05.ld.x4 = the operands of two quads, one pipeline step ahead).  The accumulator layout makes lane
+//                     (gid, t) own neurons 2t, 2t+1 of the group for streams gid, gid+8 of each half: the fp32 state of those
+//                     (stream, neuron) pairs is private to the lane for the whole launch (parked in tensor memory between the
+//                     half's activations) and the activations are evaluated there.  The sums do not depend on the sampled
+//                     excitation, so they are computed before the gathered input term is waited for:
 //                     acc = rne((bias + diag*h + gin)*16256) + S  is the same integer the reference gets.
+//                     Order of a step: GRU_B(B, previous sample) | GEMV r,h (A) | activations A | GRU_B(A) | GEMV r,h (B) |
+//                     activations B  (GRU_B right behind its activations: its state is what the half's sampler waits for).
 //   NWP producer warps gather the GRU_A input term cond + E_sig[a] + E_pred[b] + E_exc[c] (compute_gru_a_input), one gate of
 //                     one half at a time, with 512-byte contiguous LDG.128 into a ring of four [16][392] fp32 tiles
 //                     (full/empty mbarriers) that the compute lanes read conflict-free.
@@ -440,10 +444,10 @@ struct ComputeCtx {
 };
 
 // One GRU_A + GRU_B step of half H (16 streams).  k0 = index of the half-step's first tile fill (gate r; z and h follow).
-// A half-step of the compute warps is issued in three pieces so that no CTA-wide barrier is waited for right after it
-// is armed:   gemv_rh<H>  |  grub<other half, previous half-step>  |  activations<H> (ends by ARRIVING on MB_X[H])
-// and grub<H> (which WAITS on MB_X[H]) only runs after the next half-step's first GEMVs.
-// k0 = index of the half-step's first tile fill (gate r; z and h follow).
+// A half-step of the compute warps is three pieces:  gemv_rh<H>  |  activations<H> (ends by ARRIVING on MB_X[H])  |  grub<H> (WAITS on MB_X[H]).
+// grub<H> used to run only after the other half's gemv_rh, so that no CTA-wide barrier was waited for right after it was armed; but the
+// GRU_B state is what the half's sampler waits for, i.e. it is on the serial chain of a sample, while a warp that waits at the barrier only
+// gives its issue slots to the others: LPCNET_GRUB_FIRST (default) runs it right behind the activations (-2.9 % per step).
 
 // GEMVs of the candidate and reset gates of half H (need only the previous state)
 template <int H>
