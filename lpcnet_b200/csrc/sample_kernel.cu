@@ -61,7 +61,8 @@
 #ifndef LPCNET_COND_TMA
 #define LPCNET_COND_TMA 0      // 1: the conditioning rows of a gather tile come by TMA ahead of the sampled indices (gather_half_tma below): the tile
                                // fill drops from 3.7 k to 2.7 k cycles, but the same bytes then cross the shared-memory port twice (TMA write + LDS) and
-                               // the step does not get shorter (measured 1 % longer, profiles/r02q_sweep.txt); kept as a build option
+                               // the step does not get shorter (measured 1 % longer, profiles/r02q_sweep.txt); kept as a build option (bit-exact in the
+                               // golden / oracle / grid-shape tests of the 384-unit model; the 128- and 256-unit builds of it have not been run)
 #endif
 #ifndef LPCNET_FCW_PREFETCH
 #define LPCNET_FCW_PREFETCH 0  // 1: the sampler prefetches the dual_fc rows of the tree levels that are read from global memory into L1 two levels
