@@ -236,3 +236,32 @@ def test_python_mirror_matches_reference_operator_names():
     for m in ("load_model", "synthesize", "reset"):
         assert hasattr(lpcnet_b200.LPCNet, m)
     assert hasattr(lpcnet_b200.LPCNetDecoder, "decode")
+
+
+@pytest.mark.parametrize("tag,na", [("na128", 128), ("na256", 256), ("na256e2e", 256), ("", 384)])
+def test_images_of_all_gru_a_sizes_respect_the_kernel_budgets(L, tag, na):
+    """Every supported GRU_A size builds a shared-memory image that fits one SM; every neuron group is owned by exactly one compute
+    warp; and what a compute warp keeps in tensor memory (2 columns per quad of its GRU_A and GRU_B lists + 2 tail quads + the parked
+    state, 8 columns per neuron group) fits its 128 columns (sample_kernel.cu)."""
+    r, img, lay = _image(L, H.blob("int8", tag))
+    wA, metaA, wB, metaB, image_bytes, total, nA, nB, SM_IMAGE, PARA, DIRA, GRPA, DIRB, WBREC, PARB, FCW, NWC, GPW, FCN, KP, NA = [int(v) for v in lay[:21]]
+    assert r == image_bytes and NA == na and NWC * GPW * 8 == na
+    assert total == SM_IMAGE + image_bytes and total <= 227 * 1024 and FCN in (8, 16, 32, 64)
+    img = img[:image_bytes]
+    dirA = img[DIRA:DIRA + NWC * GPW * 3 * 2 * 4].view(np.uint32).reshape(NWC, GPW, 3, 2)
+    grpA = img[GRPA:GRPA + NWC * GPW * 4].view(np.uint32).reshape(NWC, GPW)
+    dirB = img[DIRB:DIRB + 6 * KP * 2 * 4].view(np.uint32).reshape(6 * KP, 2)
+    assert sorted(grpA.reshape(-1).tolist()) == list(range(na // 8))
+    assert int(dirA[:, :, :, 1].sum()) == nA and int(dirB[:, 1].sum()) == nB
+    # the warp's lists are contiguous and in the order the kernel walks them: r0 h0 r1 h1 ... | z0 z1 ... (first quad of the warp = r of slot 0)
+    for w in range(NWC):
+        q = int(dirA[w, 0, 1, 0])
+        for sl in range(GPW):
+            for gate in (1, 2):
+                assert int(dirA[w, sl, gate, 0]) == q
+                q += int(dirA[w, sl, gate, 1])
+        for sl in range(GPW):
+            assert int(dirA[w, sl, 0, 0]) == q
+            q += int(dirA[w, sl, 0, 1])
+        quads = int(dirA[w, :, :, 1].sum()) + (int(dirB[w, 1]) if w < 6 * KP else 0)
+        assert 2 * (quads + 2) + 8 * GPW <= 128
